@@ -1,0 +1,699 @@
+// C ABI of libamro_b200.so (include/amro_b200.h): host orchestration around the CUDA kernels.
+// There is no CPU fallback: every compute entry point needs a CUDA device and fails with AMRO_ECUDA otherwise.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.hpp"
+#include "kernels.hpp"
+#include "topology.hpp"
+
+namespace amro {
+
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* msg) { snprintf(g_last_error, sizeof g_last_error, "%s", msg); }
+
+namespace {
+
+struct Timer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+void use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail(AMRO_ECUDA, "no usable CUDA device (%s); amro_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) fail(AMRO_EINVAL, "device %d out of range (have %d)", device, n);
+  AMRO_CUDA(cudaSetDevice(device));
+}
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  float ms() const { float t = 0.f; cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+// strided host matrix -> dense device matrix [rows x cols], ld = rows
+void upload_matrix(DevBuf<double>& dst, const double* src, int64_t rows, int64_t cols, int64_t ld, cudaStream_t st) {
+  dst.alloc((size_t)std::max<int64_t>(rows * cols, 1));
+  if (rows == 0 || cols == 0) return;
+  AMRO_CUDA(cudaMemcpy2DAsync(dst.p, rows * sizeof(double), src, ld * sizeof(double), rows * sizeof(double), cols,
+                              cudaMemcpyHostToDevice, st));
+}
+
+}  // namespace
+}  // namespace amro
+
+using namespace amro;
+
+// --------------------------------------------------------------------------------------------------------
+// Topology handle
+// --------------------------------------------------------------------------------------------------------
+struct amro_topology {
+  HostTopology H;
+  int device = -1;
+  double compile_ms = 0.0;
+  int coresident[2] = {0, 0};  // cooperative-launch capacity of k_fast<false/true>
+  // shared / fast path
+  DevBuf<int64_t> day_start, day_seg_start, seg_row_start, orig_row, pos_of;
+  DevBuf<double> seg_N;
+  DevBuf<uint32_t> meta_src, meta_info, meta_nseg, init_seg;
+  // general path (uploaded on first use)
+  bool general_ready = false;
+  DevBuf<int64_t> order, push_src, push_dst;
+  DevBuf<uint32_t> seg_of_pos;
+  DevBuf<double> h, w;
+  DevBuf<int32_t> count_day;
+  // workspace reused across runs (parameter-inference loops call amro_simulate thousands of times)
+  DevBuf<uint4> ws_state, ws_init;
+  DevBuf<int32_t> ws_pressure, ws_counts;
+  DevBuf<unsigned int> ws_barrier;
+  DevBuf<double> ws_params;
+
+  void ensure_general() {
+    if (general_ready) return;
+    order.upload(H.order.data(), H.order.size());
+    push_src.upload(H.push_src.data(), H.push_src.size());
+    push_dst.upload(H.push_dst.data(), H.push_dst.size());
+    std::vector<uint32_t> sop((size_t)H.Rp);
+    for (int64_t s = 0; s < H.n_seg; ++s)
+      for (int64_t p = H.seg_row_start[s]; p < H.seg_row_start[s + 1]; ++p) sop[p] = (uint32_t)s;
+    seg_of_pos.upload(sop.data(), sop.size());
+    h.upload(H.h.data(), H.h.size());
+    w.upload(H.w.data(), H.w.size());
+    count_day.upload(H.count_day.data(), H.count_day.size());
+    AMRO_CUDA(cudaStreamSynchronize(0));
+    general_ready = true;
+  }
+};
+
+template <class T>
+static void ensure_size(DevBuf<T>& b, size_t n) {
+  if (b.n < n || b.p == nullptr) b.alloc(n);
+}
+
+extern "C" {
+
+const char* amro_last_error(void) { return g_last_error; }
+const char* amro_version(void) { return AMRO_B200_VERSION; }
+
+int amro_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_cols, int64_t ld,
+                         const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                         int64_t n_init, int device, amro_topology** out) {
+  return guarded([&] {
+    if (!out) fail(AMRO_EINVAL, "out is NULL");
+    *out = nullptr;
+    Timer tm;
+    std::unique_ptr<amro_topology> t(new amro_topology);
+    compile_topology(ward_matrix, n_rows, n_cols, ld, tppw, t_rows, t_cols, t_ld, n_init, t->H);
+    t->device = device;
+    if (device >= 0) {  // device < 0: host-only handle (inspection / CPU tests); amro_simulate refuses it
+      use_device(device);
+      const HostTopology& H = t->H;
+      t->day_start.upload(H.day_start.data(), H.day_start.size());
+      t->day_seg_start.upload(H.day_seg_start.data(), H.day_seg_start.size());
+      t->seg_row_start.upload(H.seg_row_start.data(), H.seg_row_start.size());
+      t->seg_N.upload(H.seg_N.data(), H.seg_N.size());
+      if (!H.identity_order) {
+        t->orig_row.upload(H.order.data(), (size_t)H.Rp);
+        t->pos_of.upload(H.pos_of.data(), H.pos_of.size());
+      }
+      if (H.fast_eligible) {
+        t->meta_src.upload(H.meta_src.data(), H.meta_src.size());
+        t->meta_info.upload(H.meta_info.data(), H.meta_info.size());
+        t->meta_nseg.upload(H.meta_nseg.data(), H.meta_nseg.size());
+        t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
+        t->coresident[0] = fast_max_coresident_ctas(device, false);
+        t->coresident[1] = fast_max_coresident_ctas(device, true);
+      }
+      AMRO_CUDA(cudaStreamSynchronize(0));
+    }
+    t->compile_ms = tm.ms();
+    *out = t.release();
+  });
+}
+
+void amro_topology_destroy(amro_topology* topo) {
+  if (!topo) return;
+  if (topo->device >= 0) cudaSetDevice(topo->device);
+  delete topo;
+}
+
+int amro_topology_get_info(const amro_topology* topo, amro_topology_info* info) {
+  return guarded([&] {
+    if (!topo || !info) fail(AMRO_EINVAL, "NULL argument");
+    const HostTopology& H = topo->H;
+    std::memset(info, 0, sizeof *info);
+    info->n_rows = H.R; info->n_rows_stepped = H.Rp; info->n_init = H.n_init; info->total_days = H.total_days;
+    info->n_days_out = H.n_days_out; info->n_segments = H.n_seg; info->max_rows_per_day = H.max_rows_per_day;
+    info->fast_eligible = H.fast_eligible; info->ring_eligible = H.ring_eligible; info->identity_order = H.identity_order;
+    info->device = topo->device; info->compile_ms = topo->compile_ms;
+    snprintf(info->why_not_fast, sizeof info->why_not_fast, "%s", H.why_not_fast.c_str());
+  });
+}
+
+}  // extern "C"
+
+// Host arrays of a compiled topology, for the CPU tests of the compiler (not part of the public header).
+extern "C" int amro_topology_debug_arrays(const amro_topology* topo, const int64_t** order, const int64_t** day_start,
+                                          const int64_t** day_seg_start, const int64_t** seg_row_start,
+                                          const double** seg_N, const uint32_t** meta_src, const uint32_t** meta_info,
+                                          const uint32_t** meta_nseg, const uint32_t** init_seg,
+                                          const int64_t** push_src, const int64_t** push_dst, int64_t* n_push) {
+  return guarded([&] {
+    if (!topo) fail(AMRO_EINVAL, "NULL topology");
+    const HostTopology& H = topo->H;
+    *order = H.order.data(); *day_start = H.day_start.data(); *day_seg_start = H.day_seg_start.data();
+    *seg_row_start = H.seg_row_start.data(); *seg_N = H.seg_N.data();
+    *meta_src = H.meta_src.empty() ? nullptr : H.meta_src.data();
+    *meta_info = H.meta_info.empty() ? nullptr : H.meta_info.data();
+    *meta_nseg = H.meta_nseg.empty() ? nullptr : H.meta_nseg.data();
+    *init_seg = H.init_seg.empty() ? nullptr : H.init_seg.data();
+    *push_src = H.push_src.data(); *push_dst = H.push_dst.data(); *n_push = (int64_t)H.push_src.size();
+  });
+}
+
+// --------------------------------------------------------------------------------------------------------
+// amro_simulate
+// --------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceInputs {  // device views of the run's inputs (uploaded copies or the caller's device pointers)
+  const double* params; int64_t p_ld;
+  const double* icp; int64_t icp_rs, icp_cs;
+  const double* idp; int64_t idp_rs, idp_cs;
+  const double* u_col; const double* u_det; int64_t u_ld;
+  const double* u_icol; const double* u_idet; int64_t ui_ld;
+};
+
+uint64_t schedule_u64(int v) { return (uint64_t)(int64_t)v; }  // int -> unsigned 64-bit, as `uword % int` does (:391-392)
+
+void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
+  const HostTopology& H = T->H;
+  const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
+  const int64_t S = A->n_sims, S_pad = (S + 7) / 8 * 8, n_slices = S_pad / 8;
+  if (A->sim_offset % 8 != 0) fail(AMRO_EINVAL, "sim_offset must be a multiple of 8 on the fast path");
+  const bool want_traj = A->keep_trajectory || A->state_out || A->pressure_out;
+  const bool ring = !want_traj && H.ring_eligible;
+  const int cap = T->coresident[replay ? 1 : 0];
+  if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
+  int teams, G;
+  if (n_slices >= cap) { teams = cap; G = 1; }
+  else {
+    teams = (int)n_slices;
+    G = (int)(cap / n_slices);
+    const int64_t useful = std::max<int64_t>(1, (H.max_rows_per_day + 31) / 32);  // a CTA wants >= one warp of records
+    G = (int)std::min<int64_t>(G, useful);
+  }
+  const int64_t n_sets = ring ? teams : n_slices;
+  const int64_t n_slots = ring ? 2 * std::max<int64_t>(H.max_rows_per_day, 1) : std::max<int64_t>(H.R, 1);
+
+  ensure_size(T->ws_state, (size_t)(n_sets * n_slots));
+  ensure_size(T->ws_init, (size_t)(n_sets * H.n_init));
+  ensure_size(T->ws_pressure, (size_t)(n_sets * std::max<int64_t>(H.n_seg, 1) * 8));
+  ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
+  ensure_size(T->ws_barrier, (size_t)teams);
+  ensure_size(T->ws_params, (size_t)(S_pad * 6));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S_pad, st));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * teams, st));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_params.p, 0, sizeof(double) * S_pad * 6, st));
+  AMRO_CUDA(cudaMemcpy2DAsync(T->ws_params.p, S_pad * sizeof(double), in.params, in.p_ld * sizeof(double),
+                              S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
+
+  FastArgs f{};
+  f.meta_src = T->meta_src.p; f.meta_info = T->meta_info.p; f.meta_nseg = T->meta_nseg.p; f.init_seg = T->init_seg.p;
+  f.orig_row = H.identity_order ? nullptr : T->orig_row.p;
+  f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
+  f.seg_N = T->seg_N.p;
+  f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.max_rows_per_day = std::max<int64_t>(H.max_rows_per_day, 1);
+  f.params = T->ws_params.p; f.p_ld = S_pad;
+  f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
+  f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
+  f.S = S; f.n_slices = n_slices;
+  f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
+  f.ttd = A->time_to_detect;
+  f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
+  f.ring = ring ? 1 : 0;
+  f.u_col = in.u_col; f.u_det = in.u_det; f.u_ld = in.u_ld;
+  f.u_icol = in.u_icol; f.u_idet = in.u_idet; f.ui_ld = in.ui_ld;
+  DevBuf<double> d_p;
+  if (A->p_out) {
+    if (!replay) fail(AMRO_EINVAL, "p_out on the fast path needs rng_mode = AMRO_RNG_REPLAY");
+    if (on_device) f.p_out = A->p_out;
+    else { d_p.alloc((size_t)(H.R * S)); AMRO_CUDA(cudaMemsetAsync(d_p.p, 0xFF, sizeof(double) * H.R * S, st)); f.p_out = d_p.p; }
+  }
+  f.state = T->ws_state.p; f.init_state = T->ws_init.p; f.n_slots = n_slots;
+  f.pressure = T->ws_pressure.p;
+  f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
+  f.team_barrier = T->ws_barrier.p; f.teams = teams; f.ctas_per_team = G;
+
+  EventPair ev;
+  AMRO_CUDA(cudaEventRecord(ev.a, st));
+  fast_launch(st, f, replay, teams * G);
+  AMRO_CUDA(cudaEventRecord(ev.b, st));
+  A->launches = 1;
+
+  // ---- outputs ---------------------------------------------------------------------------------------------
+  const size_t cbytes = sizeof(int32_t) * (size_t)(H.n_days_out * S);
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
+  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  if (A->state_out) {
+    if (on_device) {
+      fast_expand(st, f.state, n_slots, H.identity_order ? nullptr : T->pos_of.p, H.R, S, 0, S, A->state_out,
+                  A->state_out + A->so_ld * S, A->so_ld);
+      A->launches++;
+    } else {
+      // expand a block of simulations at a time into the reference's float64 columns, then copy them out
+      const int64_t chunk = std::max<int64_t>(8, std::min<int64_t>(S_pad, ((int64_t)1 << 28) / std::max<int64_t>(H.R, 1) / 8 * 8));
+      DevBuf<double> buf;
+      buf.alloc((size_t)(2 * H.R * chunk));
+      for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+        const int64_t ns = std::min(chunk, S - s0);
+        fast_expand(st, f.state, n_slots, H.identity_order ? nullptr : T->pos_of.p, H.R, S, s0, ns, buf.p, buf.p + H.R * chunk, H.R);
+        A->launches++;
+        AMRO_CUDA(cudaMemcpy2DAsync(A->state_out + A->so_ld * s0, A->so_ld * sizeof(double), buf.p, H.R * sizeof(double),
+                                    H.R * sizeof(double), ns, cudaMemcpyDeviceToHost, st));
+        AMRO_CUDA(cudaMemcpy2DAsync(A->state_out + A->so_ld * (S + s0), A->so_ld * sizeof(double), buf.p + H.R * chunk,
+                                    H.R * sizeof(double), H.R * sizeof(double), ns, cudaMemcpyDeviceToHost, st));
+        AMRO_CUDA(cudaStreamSynchronize(st));
+      }
+    }
+  }
+  if (A->pressure_out) {
+    if (on_device) { fast_export_pressure(st, f.pressure, H.n_seg, S, A->pressure_out, H.n_seg); }
+    else {
+      DevBuf<int32_t> pb;
+      pb.alloc((size_t)(H.n_seg * S));
+      fast_export_pressure(st, f.pressure, H.n_seg, S, pb.p, H.n_seg);
+      AMRO_CUDA(cudaMemcpyAsync(A->pressure_out, pb.p, sizeof(int32_t) * H.n_seg * S, cudaMemcpyDeviceToHost, st));
+      AMRO_CUDA(cudaStreamSynchronize(st));
+    }
+    A->launches++;
+  }
+  if (A->p_out && !on_device) AMRO_CUDA(cudaMemcpyAsync(A->p_out, d_p.p, sizeof(double) * H.R * S, cudaMemcpyDeviceToHost, st));
+  AMRO_CUDA(cudaStreamSynchronize(st));
+  A->kernel_ms = ev.ms();
+  A->path_used = AMRO_PATH_FAST;
+}
+
+void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
+  const HostTopology& H = T->H;
+  T->ensure_general();
+  const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
+  const int64_t S = A->n_sims, R = H.R, D = H.total_days + 1;
+  DevBuf<double> planes, F, tmp, d_p;
+  DevBuf<int32_t> counts;
+  double *C, *Dp;
+  int64_t ld;
+  if (on_device && A->state_out) { C = A->state_out; Dp = A->state_out + A->so_ld * S; ld = A->so_ld; }
+  else { planes.alloc((size_t)(2 * R * S)); C = planes.p; Dp = planes.p + R * S; ld = R; }
+  F.alloc((size_t)(std::max<int64_t>(H.max_segs_per_day, 1) * S));
+  int64_t max_push = 0;
+  for (int64_t d = 0; d < D; ++d) max_push = std::max(max_push, H.day_push_start[d + 1] - H.day_push_start[d]);
+  tmp.alloc((size_t)(std::max<int64_t>(max_push, 1) * 2 * S));
+  counts.alloc((size_t)(2 * H.n_days_out * S));
+  AMRO_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S, st));
+
+  GenArgs g{};
+  g.C = C; g.D = Dp; g.ld = ld;
+  g.h = T->h.p; g.w = T->w.p; g.hw_stride = 1;
+  g.order = T->order.p; g.seg_of_pos = T->seg_of_pos.p; g.seg_row_start = T->seg_row_start.p; g.seg_N = T->seg_N.p;
+  g.params = in.params; g.p_ld = in.p_ld; g.S = S; g.F = F.p; g.ttd = A->time_to_detect;
+  g.replay = replay; g.u_col = in.u_col; g.u_det = in.u_det; g.u_ld = in.u_ld;
+  g.seed = (uint64_t)(int64_t)A->seed; g.sim_offset = (uint64_t)A->sim_offset;
+  if (A->p_out) {
+    if (on_device) g.p_out = A->p_out;
+    else { d_p.alloc((size_t)(R * S)); AMRO_CUDA(cudaMemsetAsync(d_p.p, 0xFF, sizeof(double) * R * S, st)); g.p_out = d_p.p; }
+    g.p_out_ld = R;
+  }
+  const uint64_t tsh = schedule_u64(A->testing_schedule_hospitalized), tsa = schedule_u64(A->testing_schedule_arrivals);
+
+  EventPair ev;
+  AMRO_CUDA(cudaEventRecord(ev.a, st));
+  int launches = 1;
+  gen_init(st, C, Dp, ld, R, S, H.n_init, in.icp, in.icp_rs, in.icp_cs, in.idp, in.idp_rs, in.idp_cs, replay,
+           in.u_icol, in.u_idet, in.ui_ld, g.seed, g.sim_offset);
+  for (int64_t d = 0; d < D; ++d) {
+    const int64_t sa = H.day_seg_start[d], sb = H.day_seg_start[d + 1];
+    const int64_t ra = H.day_start[d], rb = H.day_start[d + 1];
+    if (rb > ra) {
+      gen_pressure(st, g, sa, sb);
+      gen_update(st, g, ra, rb, sa, ((uint64_t)d % tsh) == 0, ((uint64_t)d % tsa) == 0);
+      launches += 2;
+    }
+    const int64_t pa = H.day_push_start[d], pb = H.day_push_start[d + 1];
+    if (pb > pa) { gen_propagate(st, C, Dp, ld, S, T->push_src.p + pa, T->push_dst.p + pa, pb - pa, tmp.p); launches += 2; }
+  }
+  if (A->counts_colonized) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
+  if (A->counts_detected) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
+  AMRO_CUDA(cudaEventRecord(ev.b, st));
+  AMRO_CUDA(cudaGetLastError());
+
+  const size_t cbytes = sizeof(int32_t) * (size_t)(H.n_days_out * S);
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, counts.p, cbytes, kind, st));
+  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, counts.p + H.n_days_out * S, cbytes, kind, st));
+  if (A->state_out && !on_device)
+    AMRO_CUDA(cudaMemcpy2DAsync(A->state_out, A->so_ld * sizeof(double), planes.p, R * sizeof(double), R * sizeof(double),
+                                2 * S, cudaMemcpyDeviceToHost, st));
+  if (A->p_out && !on_device) AMRO_CUDA(cudaMemcpyAsync(A->p_out, d_p.p, sizeof(double) * R * S, cudaMemcpyDeviceToHost, st));
+  AMRO_CUDA(cudaStreamSynchronize(st));
+  A->kernel_ms = ev.ms();
+  A->launches = launches;
+  A->path_used = AMRO_PATH_GENERAL;
+}
+
+}  // namespace
+
+extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
+  return guarded([&] {
+    if (!T || !A) fail(AMRO_EINVAL, "NULL argument");
+    if (T->device < 0) fail(AMRO_ECUDA, "topology was compiled host-only (device < 0); amro_b200 has no CPU fallback");
+    use_device(T->device);
+    const HostTopology& H = T->H;
+    const int64_t S = A->n_sims;
+    if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");  // :365 with zero simulations
+    if (!A->parameters || !A->icp || !A->idp) fail(AMRO_EINVAL, "parameters / icp / idp must not be NULL");
+    if (A->p_rows < S) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");                // :98 parameters(s, .)
+    if (A->testing_schedule_hospitalized == 0 || A->testing_schedule_arrivals == 0)
+      fail(AMRO_EINVAL, "testing schedule of 0: the reference divides by zero here (abm_wards.cpp:391-392)");
+    const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
+    if (replay && (!A->u_col || !A->u_det || !A->u_icol || !A->u_idet))
+      fail(AMRO_EINVAL, "replay mode needs u_col, u_det, u_icol and u_idet");
+    if ((A->state_out || A->p_out) && (double)H.R * (double)S * 8.0 > 64e9)
+      fail(AMRO_EINVAL, "state_out / p_out of %lld x %lld float64 is too large; run a slice of the simulations", (long long)H.R, (long long)S);
+
+    int path = A->path;
+    const bool fast_ok = H.fast_eligible && std::abs(A->time_to_detect) <= kMaxAbsTtd && H.total_days <= kMaxAbsTtd &&
+                         (A->sim_offset % 8 == 0);
+    if (path == AMRO_PATH_AUTO) path = fast_ok ? AMRO_PATH_FAST : AMRO_PATH_GENERAL;
+    if (path == AMRO_PATH_FAST && !fast_ok)
+      fail(AMRO_EINVAL, "fast path not available: %s", H.fast_eligible ? "time_to_detect / number of days / sim_offset out of range" : H.why_not_fast.c_str());
+    if (path == AMRO_PATH_GENERAL && (double)H.R * (double)S * 16.0 > 120e9)
+      fail(AMRO_EINVAL, "general path needs %lld x %lld x 16 bytes of state; too large", (long long)H.R, (long long)S);
+
+    const bool on_device = A->pointers_on_device != 0;
+    cudaStream_t st = on_device ? (cudaStream_t)A->stream : (cudaStream_t)0;
+    EventPair ev;
+    AMRO_CUDA(cudaEventRecord(ev.a, st));
+
+    DeviceInputs in{};
+    DevBuf<double> d_par, d_icp, d_idp, d_uc, d_ud, d_uic, d_uid;
+    if (on_device) {
+      in.params = A->parameters; in.p_ld = A->p_ld;
+      in.icp = A->icp; in.icp_rs = A->icp_rs; in.icp_cs = A->icp_cs;
+      in.idp = A->idp; in.idp_rs = A->idp_rs; in.idp_cs = A->idp_cs;
+      in.u_col = A->u_col; in.u_det = A->u_det; in.u_ld = A->u_ld;
+      in.u_icol = A->u_icol; in.u_idet = A->u_idet; in.ui_ld = A->ui_ld;
+    } else {
+      upload_matrix(d_par, A->parameters, S, 6, A->p_ld, st);
+      in.params = d_par.p; in.p_ld = S;
+      auto up_prob = [&](DevBuf<double>& dst, const double* src, int64_t rs, int64_t cs, const double*& dp, int64_t& drs, int64_t& dcs) {
+        if (rs == 0 && cs == 0) { dst.upload(src, 1, st); dp = dst.p; drs = 0; dcs = 0; return; }
+        std::vector<double> dense((size_t)(H.n_init * S));
+        for (int64_t s = 0; s < S; ++s) for (int64_t r = 0; r < H.n_init; ++r) dense[r + H.n_init * s] = src[r * rs + s * cs];
+        dst.upload(dense.data(), dense.size(), st);
+        AMRO_CUDA(cudaStreamSynchronize(st));  // `dense` dies at the end of this lambda
+        dp = dst.p; drs = 1; dcs = H.n_init;
+      };
+      up_prob(d_icp, A->icp, A->icp_rs, A->icp_cs, in.icp, in.icp_rs, in.icp_cs);
+      up_prob(d_idp, A->idp, A->idp_rs, A->idp_cs, in.idp, in.idp_rs, in.idp_cs);
+      if (replay) {
+        upload_matrix(d_uc, A->u_col, H.R, S, A->u_ld, st); upload_matrix(d_ud, A->u_det, H.R, S, A->u_ld, st);
+        upload_matrix(d_uic, A->u_icol, H.n_init, S, A->ui_ld, st); upload_matrix(d_uid, A->u_idet, H.n_init, S, A->ui_ld, st);
+        in.u_col = d_uc.p; in.u_det = d_ud.p; in.u_ld = H.R; in.u_icol = d_uic.p; in.u_idet = d_uid.p; in.ui_ld = H.n_init;
+      }
+    }
+    if (path == AMRO_PATH_FAST) run_fast(T, A, in, st, on_device);
+    else run_general(T, A, in, st, on_device);
+    AMRO_CUDA(cudaEventRecord(ev.b, st));
+    AMRO_CUDA(cudaEventSynchronize(ev.b));
+    A->total_ms = ev.ms();
+  });
+}
+
+// --------------------------------------------------------------------------------------------------------
+// One-call equivalents of the reference's Python entry points
+// --------------------------------------------------------------------------------------------------------
+namespace {
+
+struct TopoGuard {
+  amro_topology* t = nullptr;
+  ~TopoGuard() { amro_topology_destroy(t); }
+};
+
+// mean(X,1) / stddev(X,1,1) over simulations with Armadillo's operation order
+// (armadillo_bits/op_mean_meat.hpp:105-133, op_var_meat.hpp:85-106,175-219, arrayops_meat.hpp:917-936)
+void row_mean_sd(const double* x, int64_t n_days, int64_t S, int64_t ld, double* mean, double* sd) {
+  for (int64_t d = 0; d < n_days; ++d) {
+    if (mean) {
+      double acc = 0.0;
+      for (int64_t s = 0; s < S; ++s) acc += x[d + ld * s];
+      mean[d] = acc / (double)S;
+    }
+    if (sd) {
+      double var = 0.0;
+      if (S >= 2) {
+        double a1 = 0.0, a2 = 0.0;
+        int64_t i;
+        for (i = 0; i + 1 < S; i += 2) { a1 += x[d + ld * i]; a2 += x[d + ld * (i + 1)]; }
+        if (i < S) a1 += x[d + ld * i];
+        const double m = (a1 + a2) / (double)S;
+        double q = 0.0, l = 0.0;
+        for (i = 0; i + 1 < S; i += 2) {
+          const double ti = m - x[d + ld * i], tj = m - x[d + ld * (i + 1)];
+          q += (ti * ti) + (tj * tj);
+          l += ti + tj;
+        }
+        if (i < S) { const double ti = m - x[d + ld * i]; q += ti * ti; l += ti; }
+        var = (q - (l * l) / (double)S) / (double)S;
+      }
+      sd[d] = std::sqrt(var);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, int64_t i_cols, int64_t i_ld,
+                                            const double* idp, int64_t d_rows, int64_t d_cols, int64_t d_ld,
+                                            const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
+                                            const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                                            const double* parameters, int64_t p_rows, int64_t p_cols, int64_t p_ld,
+                                            int time_to_detect, int tsh, int tsa, int seed, int device, double* out) {
+  return guarded([&] {
+    const int64_t S = i_cols, R = n_rows;
+    if (!out) fail(AMRO_EINVAL, "out is NULL");
+    // argument checks in the order the reference trips over them (abm_wards.cpp:356-375)
+    if (t_rows == 0 || t_cols == 0) fail(AMRO_ERUNTIME, "max(): object has no elements");
+    if (S < 1 || i_rows < 1 || i_rows > R) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
+    if (d_cols != S) fail(AMRO_ERUNTIME, "relational operator: incompatible matrix dimensions: %lldx%lld and %lldx%lld",
+                          (long long)d_rows, (long long)S, (long long)d_rows, (long long)d_cols);
+    if (d_rows != i_rows) fail(AMRO_ERUNTIME, "element-wise multiplication: incompatible matrix dimensions: %lldx%lld and %lldx%lld",
+                               (long long)d_rows, (long long)S, (long long)i_rows, (long long)S);
+    if (p_cols < 6) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");
+    TopoGuard g;
+    int rc = amro_topology_create(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device, &g.t);
+    if (rc) throw Error(rc, amro_last_error());
+    amro_sim_args a{};
+    a.n_sims = S; a.sim_offset = 0; a.time_to_detect = time_to_detect;
+    a.testing_schedule_hospitalized = tsh; a.testing_schedule_arrivals = tsa; a.seed = seed;
+    a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 1;
+    a.parameters = parameters; a.p_rows = p_rows; a.p_ld = p_ld;
+    a.icp = icp; a.icp_rs = 1; a.icp_cs = i_ld;
+    a.idp = idp; a.idp_rs = 1; a.idp_cs = d_ld;
+    a.state_out = out + 6 * R; a.so_ld = R;
+    rc = amro_simulate(g.t, &a);
+    if (rc) throw Error(rc, amro_last_error());
+    for (int64_t c = 0; c < 6; ++c) std::memcpy(out + c * R, ward_matrix + c * w_ld, sizeof(double) * (size_t)R);  // :375
+  });
+}
+
+extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
+                                          const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                                          double icp, double idp, int64_t initial_patients,
+                                          double alpha, double beta, double gamma, double rho_hospital,
+                                          double alpha2, double rho_imported, int64_t n_sims,
+                                          int64_t time_to_detect, int64_t tsh, int64_t tsa, int seed,
+                                          int device, int bug_compatible, int64_t* n_days, double* out) {
+  return guarded([&] {
+    if (n_rows < 1 || w_cols < 1) fail(AMRO_ERUNTIME, "max(): object has no elements");
+    if (!out) {  // shape query: max(ward_matrix[:,0]) + 1 (abm_wards.cpp:440)
+      double m = ward_matrix[0];
+      for (int64_t r = 1; r < n_rows; ++r) m = std::max(m, ward_matrix[r]);
+      if (!(m >= 0.0) || m > 1e7) fail(AMRO_EINVAL, "ward_matrix: largest day out of range");
+      if (n_days) *n_days = (int64_t)m + 1;
+      return;
+    }
+    const int64_t S = n_sims;
+    if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
+    TopoGuard g;
+    int rc = amro_topology_create(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device, &g.t);
+    if (rc) throw Error(rc, amro_last_error());
+    const int64_t Dd = g.t->H.n_days_out;
+    std::vector<double> par((size_t)(S * 6));
+    const double v[6] = {alpha, beta, gamma, rho_hospital, alpha2, rho_imported};
+    for (int c = 0; c < 6; ++c) for (int64_t s = 0; s < S; ++s) par[s + S * c] = v[c];     // :584-590
+    std::vector<int32_t> cc((size_t)(Dd * S)), cd((size_t)(Dd * S));
+    amro_sim_args a{};
+    a.n_sims = S; a.time_to_detect = (int)time_to_detect;                                    // uword -> const int& (:606-608)
+    a.testing_schedule_hospitalized = (int)tsh; a.testing_schedule_arrivals = (int)tsa; a.seed = seed;
+    a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 0;
+    a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
+    a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
+    a.counts_colonized = cc.data(); a.counts_detected = cd.data();
+    rc = amro_simulate(g.t, &a);
+    if (rc) throw Error(rc, amro_last_error());
+    std::vector<double> xc((size_t)(Dd * S)), xd((size_t)(Dd * S)), mc(Dd), md(Dd), sc(Dd), sd(Dd);
+    for (size_t i = 0; i < xc.size(); ++i) { xc[i] = (double)cc[i]; xd[i] = (double)cd[i]; }
+    row_mean_sd(xc.data(), Dd, S, Dd, mc.data(), sc.data());                                 // :617-620
+    row_mean_sd(xd.data(), Dd, S, Dd, md.data(), sd.data());
+    for (int64_t d = 0; d < Dd; ++d) {
+      out[d] = (double)d;
+      if (bug_compatible) {  // :625-628 write sd over the mean columns and leave 3-4 zero
+        out[d + Dd * 1] = sc[d]; out[d + Dd * 2] = sd[d]; out[d + Dd * 3] = 0.0; out[d + Dd * 4] = 0.0;
+      } else {
+        out[d + Dd * 1] = mc[d]; out[d + Dd * 2] = md[d]; out[d + Dd * 3] = sc[d]; out[d + Dd * 4] = sd[d];
+      }
+    }
+    if (n_days) *n_days = Dd;
+  });
+}
+
+extern "C" int amro_progress_patients(double* ward_matrix, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                      const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                                      double total_patients,
+                                      const double* parameters, int64_t p_rows, int64_t p_cols, int64_t p_ld,
+                                      int64_t n_sims, int time_to_detect, int detect_hosp, int detect_arr,
+                                      int rng_mode, int64_t seed, int64_t call_index,
+                                      const double* u_col, const double* u_det, int device, double* p_out) {
+  return guarded([&] {
+    const int64_t S = n_sims, n = n_rows;
+    std::vector<int64_t> order, seg_row_start;
+    std::vector<double> seg_N;
+    compile_day(ward_matrix, n, n_cols, ld, tppw, t_rows, t_cols, t_ld, total_patients, order, seg_row_start, seg_N);
+    const int64_t n_seg = (int64_t)seg_N.size();
+    if (S == 0 || n_seg == 0) return;
+    // bounds the reference's element accessors enforce (abm_wards.cpp:92-112)
+    if (6 + 2 * S > n_cols) fail(AMRO_EINDEX, "Mat::col(): index out of bounds");
+    if (p_rows < S || p_cols < 6) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");
+    const bool replay = rng_mode == AMRO_RNG_REPLAY;
+    if (replay && (!u_col || !u_det)) fail(AMRO_EINVAL, "replay mode needs u_col and u_det");
+    use_device(device);
+    cudaStream_t st = 0;
+    DevBuf<double> M, par, F, uc, ud, dp;
+    DevBuf<int64_t> d_order, d_srs;
+    DevBuf<uint32_t> d_sop;
+    DevBuf<double> d_N;
+    upload_matrix(M, ward_matrix, n, 6 + 2 * S, ld, st);
+    upload_matrix(par, parameters, S, 6, p_ld, st);
+    std::vector<uint32_t> sop((size_t)n);
+    for (int64_t s = 0; s < n_seg; ++s) for (int64_t p = seg_row_start[s]; p < seg_row_start[s + 1]; ++p) sop[p] = (uint32_t)s;
+    d_order.upload(order.data(), order.size(), st); d_srs.upload(seg_row_start.data(), seg_row_start.size(), st);
+    d_sop.upload(sop.data(), sop.size(), st); d_N.upload(seg_N.data(), seg_N.size(), st);
+    F.alloc((size_t)(n_seg * S));
+    if (replay) { uc.upload(u_col, (size_t)(n * S), st); ud.upload(u_det, (size_t)(n * S), st); }
+    if (p_out) { dp.alloc((size_t)(n * S)); AMRO_CUDA(cudaMemsetAsync(dp.p, 0xFF, sizeof(double) * n * S, st)); }
+    GenArgs g{};
+    g.C = M.p + n * 6; g.D = M.p + n * (6 + S); g.ld = n;
+    g.h = M.p + n * 3; g.w = M.p + n * 4; g.hw_stride = 1;
+    g.order = d_order.p; g.seg_of_pos = d_sop.p; g.seg_row_start = d_srs.p; g.seg_N = d_N.p;
+    g.params = par.p; g.p_ld = S; g.S = S; g.F = F.p; g.ttd = time_to_detect;
+    g.replay = replay; g.u_col = uc.p; g.u_det = ud.p; g.u_ld = n;
+    g.seed = (uint64_t)seed + 0x9E3779B97F4A7C15ull * (uint64_t)call_index; g.sim_offset = 0;
+    g.p_out = p_out ? dp.p : nullptr; g.p_out_ld = n;
+    gen_pressure(st, g, 0, n_seg);
+    gen_update(st, g, 0, n, 0, detect_hosp, detect_arr);
+    AMRO_CUDA(cudaGetLastError());
+    // the reference mutates the caller's matrix in place (C and D columns)
+    AMRO_CUDA(cudaMemcpy2DAsync(ward_matrix + 6 * ld, ld * sizeof(double), M.p + n * 6, n * sizeof(double), n * sizeof(double),
+                                2 * S, cudaMemcpyDeviceToHost, st));
+    if (p_out) AMRO_CUDA(cudaMemcpyAsync(p_out, dp.p, sizeof(double) * n * S, cudaMemcpyDeviceToHost, st));
+    AMRO_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+extern "C" int amro_total_positive(const double* model, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                   int64_t n_sims, int mode, int device,
+                                   int64_t* n_days, int64_t* n_out_cols, double* out) {
+  return guarded([&] {
+    if (n_rows < 1 || n_cols < 1) fail(AMRO_ERUNTIME, "max(): object has no elements");                 // :440
+    double m = model[0];
+    for (int64_t r = 1; r < n_rows; ++r) m = std::max(m, model[r]);
+    if (!(m >= 0.0) || m > 1e7) fail(AMRO_EINVAL, "model_colonized: largest day out of range");
+    const int64_t Dd = (int64_t)m + 1;
+    // :480-481 (mode 1: columns 6 .. 6+n_sims-1)   :503-504 (mode 0: columns 6+n_sims .. n_cols-1)
+    const int64_t c0 = mode == 1 ? 6 : 6 + n_sims, c1 = mode == 1 ? 6 + n_sims - 1 : n_cols - 1;
+    if (c1 >= n_cols || c0 > c1 + 0 || c0 < 0) fail(AMRO_EINDEX, "Mat::cols(): indices out of bounds or incorrectly used");
+    const int64_t nc = c1 - c0 + 1;
+    if (n_days) *n_days = Dd;
+    if (n_out_cols) *n_out_cols = nc;
+    if (!out) return;
+    use_device(device);
+    cudaStream_t st = 0;
+    std::vector<int32_t> cday((size_t)n_rows);
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const double v = model[r];
+      const int64_t i = (v >= 0.0 && v <= (double)(Dd - 1)) ? (int64_t)v : -1;
+      cday[r] = (i >= 0 && (double)i == v) ? (int32_t)i : -1;
+    }
+    DevBuf<double> plane, dout;
+    DevBuf<int32_t> d_day, cnt;
+    upload_matrix(plane, model + c0 * ld, n_rows, nc, ld, st);
+    d_day.upload(cday.data(), cday.size(), st);
+    cnt.alloc((size_t)(Dd * nc));
+    dout.alloc((size_t)(Dd * nc));
+    AMRO_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * Dd * nc, st));
+    gen_count(st, plane.p, n_rows, n_rows, nc, d_day.p, mode == 1 ? 1 : 0, cnt.p, Dd);
+    counts_to_double(st, cnt.p, dout.p, Dd * nc);
+    AMRO_CUDA(cudaGetLastError());
+    AMRO_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * Dd * nc, cudaMemcpyDeviceToHost, st));
+    AMRO_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+extern "C" int amro_summary_of_total_positive(const double* positive, int64_t n_days, int64_t n_sims, int64_t ld,
+                                              const double* quantiles, int64_t n_q, double* out) {
+  return guarded([&] {
+    if (n_days < 0 || n_sims < 0 || n_q < 0) fail(AMRO_EINVAL, "negative size");
+    if (n_days == 0) return;
+    if (n_sims == 0) fail(AMRO_ERUNTIME, "copy into submatrix: incompatible matrix dimensions");
+    std::vector<double> mean(n_days), sd(n_days), y(n_sims);
+    row_mean_sd(positive, n_days, n_sims, ld, mean.data(), sd.data());                       // :534-535
+    // :536-537 arma::quantile = Hyndman & Fan definition 5 (armadillo_bits/glue_quantile_meat.hpp:22-80)
+    const double N = (double)n_sims, pmin = (1.0 - 0.5) / N, pmax = (N - 0.5) / N;
+    for (int64_t d = 0; d < n_days; ++d) {
+      out[d] = (double)d;
+      out[d + n_days] = mean[d];
+      out[d + 2 * n_days] = sd[d];
+      for (int64_t s = 0; s < n_sims; ++s) y[s] = positive[d + ld * s];
+      std::sort(y.begin(), y.end());
+      for (int64_t i = 0; i < n_q; ++i) {
+        const double p = quantiles[i];
+        double v;
+        if (p < pmin) v = (p < 0.0) ? -INFINITY : y.front();
+        else if (p > pmax) v = (p > 1.0) ? INFINITY : y.back();
+        else {
+          const int64_t k = (int64_t)std::floor(N * p + 0.5);
+          const double pk = ((double)k - 0.5) / N;
+          const double wgt = (p - pk) * N;
+          v = ((1.0 - wgt) * y[k - 1]) + (wgt * y[k]);
+        }
+        out[d + (3 + i) * n_days] = v;
+      }
+    }
+  });
+}

@@ -1,0 +1,109 @@
+// Launcher declarations shared by api.cu and the two kernel translation units.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace amro {
+
+// ----------------------------------------------------------------------------------------------------
+// GENERAL path: float64 state planes laid out like the reference's matrix columns (element (row, sim) at
+// plane[row + ld*sim]), any weights / is_new / countdown values.  One launch per phase per day.
+// ----------------------------------------------------------------------------------------------------
+struct GenArgs {
+  double* C;                 // colonised plane  (reference columns 6 .. 6+S-1)
+  double* D;                 // countdown plane  (reference columns 6+S .. 6+2S-1)
+  int64_t ld;
+  const double* h;           // per ORIGINAL row
+  const double* w;
+  int64_t hw_stride;         // element stride of h / w (1)
+  const int64_t* order;      // position -> original row
+  const uint32_t* seg_of_pos;  // position -> absolute segment
+  const int64_t* seg_row_start;
+  const double* seg_N;
+  const double* params;      // [>=S x 6]
+  int64_t p_ld;
+  int64_t S;
+  double* F;                 // scratch [n_segments_of_day x S]: force of infection
+  int ttd;
+  int replay;
+  const double* u_col;       // [rows x S], element (orig row, sim) at u[row + u_ld*sim]
+  const double* u_det;
+  int64_t u_ld;
+  uint64_t seed;
+  uint64_t sim_offset;
+  double* p_out;             // optional [rows x S]
+  int64_t p_out_ld;
+};
+
+void gen_init(cudaStream_t st, double* C, double* D, int64_t ld, int64_t R, int64_t S, int64_t n_init,
+              const double* icp, int64_t icp_rs, int64_t icp_cs, const double* idp, int64_t idp_rs, int64_t idp_cs,
+              int replay, const double* u_icol, const double* u_idet, int64_t ui_ld, uint64_t seed, uint64_t sim_offset);
+void gen_pressure(cudaStream_t st, const GenArgs& a, int64_t seg_begin, int64_t seg_end);
+void gen_update(cudaStream_t st, const GenArgs& a, int64_t row_begin, int64_t row_end, int64_t seg_begin,
+                int test_h, int test_a);
+void gen_propagate(cudaStream_t st, double* C, double* D, int64_t ld, int64_t S, const int64_t* push_src,
+                   const int64_t* push_dst, int64_t n_push, double* tmp);
+// counts[day + ld_out*sim] += #rows of that day with (mode 1: v == 1) or (mode 0: v <= 0)
+void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int64_t S, const int32_t* count_day,
+               int mode, int32_t* counts, int64_t ld_out);
+void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n);
+
+// ----------------------------------------------------------------------------------------------------
+// FAST path: packed int16 state (2*D + C, D = 16383 meaning +inf), 8 simulations (one 16-byte word) per
+// patient-day record and slice; one persistent cooperative kernel runs the initial state and every day.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kSimsPerSlice = 8;
+constexpr int kInfCode = 16383;            // countdown value standing for +inf
+constexpr int kMaxAbsTtd = 16000;          // |time_to_detect| and total_days limits of the packed state
+constexpr int kFastThreads = 256;
+constexpr int kTableSegs = 16;             // ward-day threshold tables resident in shared memory at once
+
+struct FastArgs {
+  // topology (device)
+  const uint32_t* meta_src;
+  const uint32_t* meta_info;
+  const uint32_t* meta_nseg;
+  const uint32_t* init_seg;
+  const int64_t* orig_row;       // nullptr when identity_order
+  const int64_t* day_start;
+  const int64_t* day_seg_start;
+  const int64_t* seg_row_start;
+  const double* seg_N;
+  int64_t R, n_init, n_days, n_seg, max_rows_per_day;
+  // run
+  const double* params; int64_t p_ld;   // [S_pad x 6] device copy, padded rows are zeros
+  const double* icp; int64_t icp_rs, icp_cs;
+  const double* idp; int64_t idp_rs, idp_cs;
+  int64_t S;                     // real simulations
+  int64_t n_slices;              // ceil(S / 8)
+  uint64_t seed, sim_offset;
+  int ttd, tsh_zero_based_unused;
+  uint64_t tsh, tsa;             // schedules converted the way the reference's unsigned % does
+  int ring;                      // 1: two-day ring of state; 0: full trajectory
+  // replay
+  const double* u_col; const double* u_det; int64_t u_ld;
+  const double* u_icol; const double* u_idet; int64_t ui_ld;
+  double* p_out;                 // optional [R x S] (ld = R)
+  // state
+  uint4* state;                  // [n_slices][n_slots] 16-byte words; n_slots = R or 2*max_rows_per_day
+  uint4* init_state;             // [n_slices][n_init]
+  int64_t n_slots;
+  int32_t* pressure;             // [n_slices][n_seg][8]
+  int32_t* counts_col;           // [n_days_out x S_pad8] ld = n_days_out  (zeroed by the caller)
+  int32_t* counts_det;
+  int64_t counts_ld;
+  unsigned int* team_barrier;    // [n_teams] zeroed by the caller
+  int teams, ctas_per_team;
+};
+
+// Returns the number of CTAs of kFastThreads threads that can be co-resident (cooperative launch bound).
+int fast_max_coresident_ctas(int device, bool replay);
+void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int grid);
+
+// state_out[(orig row) + ld*(sim)] = C, state_out[row + ld*(S+sim)] = D for sims [s0, s0+ns) of the run
+void fast_expand(cudaStream_t st, const uint4* state, int64_t n_slots, const int64_t* pos_of, int64_t R,
+                 int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld);
+// pressure_out[seg + ld*sim] = pressure[slice][seg][k]
+void fast_export_pressure(cudaStream_t st, const int32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld);
+
+}  // namespace amro

@@ -1,0 +1,280 @@
+// Host-side topology compiler (see topology.hpp).
+#include "topology.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+#include "common.hpp"
+
+namespace amro {
+namespace {
+
+inline double at(const double* m, int64_t ld, int64_t r, int64_t c) { return m[r + ld * c]; }
+
+// doubles compare equal <=> same key (folds -0.0 onto +0.0; NaN never reaches here)
+inline uint64_t dkey(double x) {
+  x += 0.0;
+  uint64_t u;
+  std::memcpy(&u, &x, 8);
+  return u;
+}
+struct PairHash {
+  size_t operator()(const std::pair<uint64_t, uint64_t>& k) const {
+    uint64_t h = k.first * 0x9E3779B97F4A7C15ull;
+    h ^= (k.second + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+
+constexpr int64_t kMaxDays = 10'000'000;
+
+// integer-valued, in [0, limit] -> the integer; else -1   (the reference compares `col == day` with an
+// unsigned loop counter converted to double, abm_wards.cpp:384,387,447)
+inline int64_t as_day(double v, int64_t limit) {
+  if (!(v >= 0.0) || v > (double)limit) return -1;
+  const int64_t i = (int64_t)v;
+  return ((double)i == v) ? i : -1;
+}
+
+}  // namespace
+
+void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
+                      const double* tp, int64_t K, int64_t t_cols, int64_t t_ld,
+                      int64_t n_init, HostTopology& T) {
+  if (R < 0 || K < 0 || n_init < 0) fail(AMRO_EINVAL, "negative size");
+  // abm_wards.cpp:356  max() of an empty column throws in Armadillo
+  if (K == 0 || t_cols == 0) fail(AMRO_ERUNTIME, "max(): object has no elements");
+  double dmax = at(tp, t_ld, 0, 0);
+  for (int64_t k = 1; k < K; ++k) dmax = std::max(dmax, at(tp, t_ld, k, 0));
+  if (!(dmax >= 0.0) || dmax > (double)kMaxDays)
+    fail(AMRO_EINVAL, "total_patients_per_ward: largest day must be in [0, %lld]", (long long)kMaxDays);
+  // abm_wards.cpp:365  submat(0, 6, n_init-1, ...) needs 1 <= n_init <= R
+  if (n_init < 1 || n_init > R) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
+  // abm_wards.cpp:375  copying ward_matrix into the first 6 columns needs exactly 6 columns
+  if (n_cols != 6) fail(AMRO_ERUNTIME, "copy into submatrix: incompatible matrix dimensions: %lldx6 and %lldx%lld",
+                        (long long)R, (long long)R, (long long)n_cols);
+
+  T = HostTopology();
+  T.R = R;
+  T.n_init = n_init;
+  T.total_days = (int64_t)dmax;
+  const int64_t D = T.total_days + 1;
+
+  // ---- per original row: day, totals day, h, w --------------------------------------------------
+  std::vector<int64_t> row_day(R);
+  T.h.resize(R);
+  T.w.resize(R);
+  T.count_day.assign(R, -1);
+  double cmax = R ? at(wm, ld, 0, 0) : 0.0;
+  for (int64_t r = 0; r < R; ++r) cmax = std::max(cmax, at(wm, ld, r, 0));
+  if (!(cmax >= 0.0) || cmax > (double)kMaxDays)
+    fail(AMRO_EINVAL, "ward_matrix: largest day must be in [0, %lld]", (long long)kMaxDays);
+  T.n_days_out = (int64_t)cmax + 1;
+  bool sorted = true;
+  T.unit_weights = true;
+  T.binary_h = true;
+  int64_t prev_day = -1;
+  double prev_ward = 0.0;
+  bool seen_unstepped = false;
+  for (int64_t r = 0; r < R; ++r) {
+    const double dv = at(wm, ld, r, 0), wv = at(wm, ld, r, 1);
+    const int64_t d = as_day(dv, T.total_days);
+    row_day[r] = d;
+    T.count_day[r] = (int32_t)as_day(dv, T.n_days_out - 1);
+    T.h[r] = at(wm, ld, r, 3);
+    T.w[r] = at(wm, ld, r, 4);
+    if (d >= 0) {
+      if (wv != wv) fail(AMRO_EINVAL, "ward_matrix: NaN ward identifier in row %lld", (long long)r);
+      if (seen_unstepped || d < prev_day || (d == prev_day && wv < prev_ward)) sorted = false;
+      prev_day = d;
+      prev_ward = wv;
+      T.Rp++;
+      if (T.w[r] != 1.0) T.unit_weights = false;
+      if (!(T.h[r] == 0.0 || T.h[r] == 1.0)) T.binary_h = false;
+    } else {
+      seen_unstepped = true;
+    }
+  }
+  T.identity_order = sorted;
+
+  // ---- visiting order: (day, ward, original index), never-stepped rows last ------------------------
+  T.order.resize(R);
+  if (sorted) {
+    std::iota(T.order.begin(), T.order.end(), (int64_t)0);
+  } else {
+    int64_t a = 0, b = T.Rp;
+    for (int64_t r = 0; r < R; ++r) {
+      if (row_day[r] >= 0) T.order[a++] = r; else T.order[b++] = r;
+    }
+    std::stable_sort(T.order.begin(), T.order.begin() + T.Rp, [&](int64_t x, int64_t y) {
+      if (row_day[x] != row_day[y]) return row_day[x] < row_day[y];
+      return at(wm, ld, x, 1) < at(wm, ld, y, 1);
+    });
+  }
+  T.pos_of.resize(R);
+  for (int64_t p = 0; p < R; ++p) T.pos_of[T.order[p]] = p;
+
+  // ---- first tppw row of every (day, ward)   (abm_wards.cpp:384 then :242,249) ---------------------
+  std::unordered_map<std::pair<uint64_t, uint64_t>, int64_t, PairHash> first_row;
+  first_row.reserve((size_t)K * 2);
+  if (t_cols >= 2) {
+    for (int64_t k = 0; k < K; ++k) {
+      const int64_t d = as_day(at(tp, t_ld, k, 0), T.total_days);
+      const double wv = at(tp, t_ld, k, 1);
+      if (d < 0 || wv != wv) continue;
+      first_row.emplace(std::make_pair((uint64_t)d, dkey(wv)), k);
+    }
+  }
+
+  // ---- days and (day, ward) segments ----------------------------------------------------------------
+  T.day_start.assign(D + 1, 0);
+  T.day_seg_start.assign(D + 1, 0);
+  std::vector<uint32_t> seg_of_pos(T.Rp);
+  {
+    int64_t p = 0;
+    for (int64_t d = 0; d < D; ++d) {
+      T.day_start[d] = p;
+      T.day_seg_start[d] = (int64_t)T.seg_N.size();
+      while (p < T.Rp && row_day[T.order[p]] == d) {
+        const double wv = at(wm, ld, T.order[p], 1);
+        const int64_t s0 = p;
+        while (p < T.Rp && row_day[T.order[p]] == d && at(wm, ld, T.order[p], 1) == wv) ++p;
+        auto it = first_row.find(std::make_pair((uint64_t)d, dkey(wv)));
+        if (it == first_row.end() || t_cols < 3)
+          fail(AMRO_EINDEX, "Mat::operator(): index out of bounds (day %lld: ward %g has no row in total_patients_per_ward)",
+               (long long)d, wv);
+        if (T.seg_N.size() >= (size_t)0x7FFFFFF0) fail(AMRO_EINVAL, "too many (day, ward) segments");
+        const uint32_t sid = (uint32_t)T.seg_N.size();
+        for (int64_t q = s0; q < p; ++q) seg_of_pos[q] = sid;
+        T.seg_row_start.push_back(s0);
+        T.seg_N.push_back(at(tp, t_ld, it->second, 2));
+        T.seg_ward.push_back(wv);
+        T.max_seg_rows = std::max(T.max_seg_rows, p - s0);
+      }
+      T.max_rows_per_day = std::max(T.max_rows_per_day, p - T.day_start[d]);
+      T.max_segs_per_day = std::max(T.max_segs_per_day, (int64_t)T.seg_N.size() - T.day_seg_start[d]);
+    }
+    T.day_start[D] = p;
+    T.day_seg_start[D] = (int64_t)T.seg_N.size();
+    T.seg_row_start.push_back(p);
+    T.n_seg = (int64_t)T.seg_N.size();
+  }
+
+  // ---- next_day links: per day the surviving copies; per stepped row its effective predecessor -------
+  // abm_wards.cpp:402-407: after day d, rows of d with next_day > 0 (ascending row order) overwrite the
+  // C/D columns of row trunc(next_day); a later source wins.  A stepped row therefore starts its own day
+  // from the last write made on an EARLIER day (or its initial state), and a write made on its own or a
+  // later day only changes what the returned matrix shows for it.
+  std::vector<int64_t> last_writer(R, -1), seen_stamp(R, -1);
+  std::vector<int64_t> pre_src(T.Rp, -1);  // original row of the effective predecessor
+  T.day_push_start.assign(D + 1, 0);
+  T.simple_final = (T.Rp == R);
+  bool ring = true;
+  std::vector<int64_t> ev;
+  for (int64_t d = 0; d < D; ++d) {
+    const int64_t a = T.day_start[d], b = T.day_start[d + 1];
+    for (int64_t p = a; p < b; ++p) {
+      const int64_t src = last_writer[T.order[p]];
+      pre_src[p] = src;
+      if (src >= 0 && row_day[src] != d - 1) ring = false;
+    }
+    T.day_push_start[d] = (int64_t)T.push_src.size();
+    ev.clear();
+    for (int64_t p = a; p < b; ++p) {
+      const int64_t r = T.order[p];
+      if (at(wm, ld, r, 5) > 0.0) ev.push_back(r);
+    }
+    if (!sorted) std::sort(ev.begin(), ev.end());
+    const size_t base = T.push_src.size();
+    for (size_t i = ev.size(); i-- > 0;) {  // reverse: the last source of a target is its winner
+      const int64_t r = ev[i];
+      const double nd = at(wm, ld, r, 5);
+      if (!(nd < 18446744073709551616.0) || (uint64_t)nd >= (uint64_t)R)
+        fail(AMRO_EINDEX, "Mat::elem(): index out of bounds (row %lld: next_day %g)", (long long)r, nd);
+      const int64_t t = (int64_t)(uint64_t)nd;
+      if (seen_stamp[t] == d) continue;
+      seen_stamp[t] = d;
+      T.push_src.push_back(r);
+      T.push_dst.push_back(t);
+      last_writer[t] = r;
+      if (row_day[t] < 0 || row_day[t] <= d) T.simple_final = false;
+    }
+    std::reverse(T.push_src.begin() + base, T.push_src.end());
+    std::reverse(T.push_dst.begin() + base, T.push_dst.end());
+  }
+  T.day_push_start[D] = (int64_t)T.push_src.size();
+
+  // ---- FAST path encodings ------------------------------------------------------------------------------
+  T.why_not_fast.clear();
+  if (!T.unit_weights) T.why_not_fast = "weights other than 1";
+  else if (!T.binary_h) T.why_not_fast = "is_new values other than 0/1";
+  else if (T.Rp != R) T.why_not_fast = "rows whose day is never stepped";
+  else if (!T.simple_final) T.why_not_fast = "next_day links that point to the same or an earlier day";
+  else if (n_init >= (int64_t)kSrcMask) T.why_not_fast = "too many initial rows";
+  if (T.why_not_fast.empty()) {
+    T.meta_src.resize(T.Rp);
+    T.meta_info.resize(T.Rp);
+    T.meta_nseg.assign(T.Rp, kNone);
+    T.init_seg.assign(n_init, kNone);
+    for (int64_t d = 0; d < D && T.why_not_fast.empty(); ++d) {
+      for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
+        const int64_t r = T.order[p];
+        const uint32_t seg_local = seg_of_pos[p] - (uint32_t)T.day_seg_start[d];
+        T.meta_info[p] = (T.h[r] == 1.0 ? 0x80000000u : 0u) | seg_local;
+        if (pre_src[p] >= 0) {
+          const int64_t pp = T.pos_of[pre_src[p]];
+          const int64_t delta = p - pp;
+          if (delta <= 0 || delta >= (int64_t)kSrcMask) { T.why_not_fast = "predecessor link too long"; break; }
+          T.meta_src[p] = (kSrcPrev << kSrcShift) | (uint32_t)delta;
+          T.meta_nseg[pp] = seg_of_pos[p];
+        } else if (r < n_init) {
+          T.meta_src[p] = (kSrcInit << kSrcShift) | (uint32_t)r;
+          T.init_seg[r] = seg_of_pos[p];
+        } else {
+          T.meta_src[p] = (kSrcNone << kSrcShift);
+        }
+      }
+    }
+  }
+  T.fast_eligible = T.why_not_fast.empty();
+  T.ring_eligible = T.fast_eligible && ring;
+  if (!T.fast_eligible) {
+    T.meta_src.clear(); T.meta_info.clear(); T.meta_nseg.clear(); T.init_seg.clear();
+  }
+}
+
+void compile_day(const double* wm, int64_t n, int64_t n_cols, int64_t ld,
+                 const double* tp, int64_t K, int64_t t_cols, int64_t t_ld, double total_patients,
+                 std::vector<int64_t>& order, std::vector<int64_t>& seg_row_start, std::vector<double>& seg_N) {
+  order.resize(n);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  seg_row_start.clear();
+  seg_N.clear();
+  if (tp == nullptr) {  // ward step: all rows are one ward with the caller's N
+    if (n > 0) { seg_row_start.push_back(0); seg_N.push_back(total_patients); }
+    seg_row_start.push_back(n);
+    return;
+  }
+  if (n == 0) { seg_row_start.push_back(0); return; }  // unique() of an empty column: nothing to do
+  if (n_cols < 2) fail(AMRO_EINDEX, "Mat::col(): index out of bounds");
+  if (t_cols < 2) fail(AMRO_EINDEX, "Mat::col(): index out of bounds");
+  for (int64_t r = 0; r < n; ++r)
+    if (at(wm, ld, r, 1) != at(wm, ld, r, 1)) fail(AMRO_EINVAL, "ward_matrix: NaN ward identifier in row %lld", (long long)r);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return at(wm, ld, x, 1) < at(wm, ld, y, 1); });
+  int64_t p = 0;
+  while (p < n) {
+    const double wv = at(wm, ld, order[p], 1);
+    seg_row_start.push_back(p);
+    while (p < n && at(wm, ld, order[p], 1) == wv) ++p;
+    int64_t hit = -1;
+    for (int64_t k = 0; k < K; ++k) if (at(tp, t_ld, k, 1) == wv) { hit = k; break; }  // :242, first match
+    if (hit < 0 || t_cols < 3) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds (ward %g has no row in total_patients_per_ward)", wv);
+    seg_N.push_back(at(tp, t_ld, hit, 2));
+  }
+  seg_row_start.push_back(n);
+}
+
+}  // namespace amro

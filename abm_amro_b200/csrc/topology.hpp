@@ -1,0 +1,63 @@
+// Host-side topology compiler: turns the reference's ward_matrix / total_patients_per_ward tables into
+// the grouped, link-inverted form the kernels read.  Pure C++ (no CUDA) so it is testable on a CPU box.
+//
+// It replaces the work the reference redoes every day of every run (abm_wards.cpp:235-253 unique/find per
+// ward, :384-388 find per day, :402-407 next_day scatter) by doing it once per hospital.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace amro {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no segment" / "no successor"
+constexpr uint32_t kSrcNone = 0u, kSrcPrev = 1u, kSrcInit = 2u;  // meta_src kind (top 2 bits)
+constexpr uint32_t kSrcShift = 30, kSrcMask = (1u << kSrcShift) - 1u;
+
+struct HostTopology {
+  int64_t R = 0, n_init = 0;
+  int64_t total_days = 0;    // max(tppw[:,0])                      (abm_wards.cpp:356)
+  int64_t n_days_out = 0;    // max(ward_matrix[:,0]) + 1           (abm_wards.cpp:440)
+  int64_t Rp = 0;            // stepped rows: day integer in [0, total_days]
+  int64_t n_seg = 0, max_rows_per_day = 0, max_segs_per_day = 0, max_seg_rows = 0;
+  bool identity_order = false, unit_weights = false, binary_h = false, simple_final = false;
+  bool fast_eligible = false, ring_eligible = false;
+  std::string why_not_fast;
+
+  // position p in [0,R): stepped rows first, sorted by (day, ward, original index) -- the order the
+  // reference visits them (day loop :381, unique() ascending wards :235, find() ascending rows :241);
+  // rows that are never stepped follow in original order.
+  std::vector<int64_t> order;          // [R]  position -> original row
+  std::vector<int64_t> pos_of;         // [R]  original row -> position
+  std::vector<int64_t> day_start;      // [total_days+2] first position of each day
+  std::vector<int64_t> day_seg_start;  // [total_days+2] first segment of each day
+  std::vector<int64_t> seg_row_start;  // [n_seg+1] first position of each (day, ward) segment
+  std::vector<double>  seg_N;          // [n_seg]  N of the first matching tppw row (:242,249)
+  std::vector<double>  seg_ward;       // [n_seg]
+  std::vector<double>  h, w;           // [R] per ORIGINAL row: is_new, weight
+  std::vector<int32_t> count_day;      // [R] per ORIGINAL row: day index for the totals, -1 if none
+
+  // GENERAL path: per day, the surviving (last-writer-wins) next_day copies   (:402-407)
+  std::vector<int64_t> day_push_start; // [total_days+2]
+  std::vector<int64_t> push_src, push_dst;  // original row indices
+
+  // FAST path per position (valid when fast_eligible)
+  std::vector<uint32_t> meta_src;      // [Rp] kind<<30 | (distance to predecessor position | init row)
+  std::vector<uint32_t> meta_info;     // [Rp] h<<31 | segment index within the day
+  std::vector<uint32_t> meta_nseg;     // [Rp] absolute segment of the successor this row feeds, or kNone
+  std::vector<uint32_t> init_seg;      // [n_init] absolute segment of init-sourced stepped rows, or kNone
+};
+
+// Throws amro::Error (AMRO_EINDEX / AMRO_ERUNTIME / AMRO_EINVAL) mirroring what the reference raises.
+void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
+                      const double* tp, int64_t K, int64_t t_cols, int64_t t_ld,
+                      int64_t n_init, HostTopology& T);
+
+// Grouping for the single-day entry points (progress_patients_1_timestep: wards only, no day column
+// match; abm_wards.cpp:235-249).  tp == nullptr: one segment with N = total_patients (ward step, :70).
+void compile_day(const double* wm, int64_t n, int64_t n_cols, int64_t ld,
+                 const double* tp, int64_t K, int64_t t_cols, int64_t t_ld, double total_patients,
+                 std::vector<int64_t>& order, std::vector<int64_t>& seg_row_start, std::vector<double>& seg_N);
+
+}  // namespace amro
