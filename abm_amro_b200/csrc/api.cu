@@ -63,7 +63,7 @@ struct amro_topology {
   // shared / fast path
   DevBuf<int64_t> day_start, day_seg_start, seg_row_start, orig_row, pos_of;
   DevBuf<double> seg_N;
-  DevBuf<uint32_t> meta_src, meta_info, meta_nseg, init_seg;
+  DevBuf<uint32_t> meta_info, meta_next, meta_nseg, init_seg, init_slot;
   // general path (uploaded on first use)
   bool general_ready = false;
   DevBuf<int64_t> order, push_src, push_dst;
@@ -71,8 +71,9 @@ struct amro_topology {
   DevBuf<double> h, w;
   DevBuf<int32_t> count_day;
   // workspace reused across runs (parameter-inference loops call amro_simulate thousands of times)
-  DevBuf<uint4> ws_state, ws_init;
-  DevBuf<int32_t> ws_pressure, ws_counts;
+  DevBuf<uint4> ws_pre, ws_traj;
+  DevBuf<uint32_t> ws_pressure;
+  DevBuf<int32_t> ws_counts;
   DevBuf<unsigned int> ws_barrier;
   DevBuf<double> ws_params;
 
@@ -131,10 +132,11 @@ int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_co
         t->pos_of.upload(H.pos_of.data(), H.pos_of.size());
       }
       if (H.fast_eligible) {
-        t->meta_src.upload(H.meta_src.data(), H.meta_src.size());
         t->meta_info.upload(H.meta_info.data(), H.meta_info.size());
+        t->meta_next.upload(H.meta_next.data(), H.meta_next.size());
         t->meta_nseg.upload(H.meta_nseg.data(), H.meta_nseg.size());
         t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
+        t->init_slot.upload(H.init_slot.data(), H.init_slot.size());
         t->coresident[0] = fast_max_coresident_ctas(device, false);
         t->coresident[1] = fast_max_coresident_ctas(device, true);
       }
@@ -169,7 +171,7 @@ int amro_topology_get_info(const amro_topology* topo, amro_topology_info* info) 
 // Host arrays of a compiled topology, for the CPU tests of the compiler (not part of the public header).
 extern "C" int amro_topology_debug_arrays(const amro_topology* topo, const int64_t** order, const int64_t** day_start,
                                           const int64_t** day_seg_start, const int64_t** seg_row_start,
-                                          const double** seg_N, const uint32_t** meta_src, const uint32_t** meta_info,
+                                          const double** seg_N, const uint32_t** meta_next, const uint32_t** meta_info,
                                           const uint32_t** meta_nseg, const uint32_t** init_seg,
                                           const int64_t** push_src, const int64_t** push_dst, int64_t* n_push) {
   return guarded([&] {
@@ -177,7 +179,7 @@ extern "C" int amro_topology_debug_arrays(const amro_topology* topo, const int64
     const HostTopology& H = topo->H;
     *order = H.order.data(); *day_start = H.day_start.data(); *day_seg_start = H.day_seg_start.data();
     *seg_row_start = H.seg_row_start.data(); *seg_N = H.seg_N.data();
-    *meta_src = H.meta_src.empty() ? nullptr : H.meta_src.data();
+    *meta_next = H.meta_next.empty() ? nullptr : H.meta_next.data();
     *meta_info = H.meta_info.empty() ? nullptr : H.meta_info.data();
     *meta_nseg = H.meta_nseg.empty() ? nullptr : H.meta_nseg.data();
     *init_seg = H.init_seg.empty() ? nullptr : H.init_seg.data();
@@ -204,25 +206,25 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const HostTopology& H = T->H;
   const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
   const int64_t S = A->n_sims, S_pad = (S + 7) / 8 * 8, n_slices = S_pad / 8;
-  if (A->sim_offset % 8 != 0) fail(AMRO_EINVAL, "sim_offset must be a multiple of 8 on the fast path");
-  const bool want_traj = A->keep_trajectory || A->state_out || A->pressure_out;
-  const bool ring = !want_traj && H.ring_eligible;
+  const bool want_traj = A->keep_trajectory || A->state_out;
   const int cap = T->coresident[replay ? 1 : 0];
   if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
+  // Teams of G CTAs per slice of 8 simulations; a CTA wants at least a few warps of records per day.
   int teams, G;
   if (n_slices >= cap) { teams = cap; G = 1; }
   else {
     teams = (int)n_slices;
     G = (int)(cap / n_slices);
-    const int64_t useful = std::max<int64_t>(1, (H.max_rows_per_day + 31) / 32);  // a CTA wants >= one warp of records
-    G = (int)std::min<int64_t>(G, useful);
+    const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kFastThreads));
+    G = (int)std::max<int64_t>(1, std::min<int64_t>(G, useful));
   }
-  const int64_t n_sets = ring ? teams : n_slices;
-  const int64_t n_slots = ring ? 2 * std::max<int64_t>(H.max_rows_per_day, 1) : std::max<int64_t>(H.R, 1);
+  const bool by_team = !A->pressure_out;   // the pressure table is only kept per slice when it is exported
+  const int64_t n_sets = by_team ? teams : n_slices;
+  const int64_t ring = std::max<int64_t>(H.max_rows_per_day, 1);
 
-  ensure_size(T->ws_state, (size_t)(n_sets * n_slots));
-  ensure_size(T->ws_init, (size_t)(n_sets * H.n_init));
-  ensure_size(T->ws_pressure, (size_t)(n_sets * std::max<int64_t>(H.n_seg, 1) * 8));
+  ensure_size(T->ws_pre, (size_t)(n_sets * 2 * ring));
+  if (want_traj) ensure_size(T->ws_traj, (size_t)(n_slices * std::max<int64_t>(H.R, 1)));
+  ensure_size(T->ws_pressure, (size_t)(n_sets * std::max<int64_t>(H.n_seg, 1) * 4));
   ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
   ensure_size(T->ws_barrier, (size_t)teams);
   ensure_size(T->ws_params, (size_t)(S_pad * 6));
@@ -233,11 +235,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
                               S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
 
   FastArgs f{};
-  f.meta_src = T->meta_src.p; f.meta_info = T->meta_info.p; f.meta_nseg = T->meta_nseg.p; f.init_seg = T->init_seg.p;
+  f.meta_info = T->meta_info.p; f.meta_next = T->meta_next.p; f.meta_nseg = T->meta_nseg.p;
+  f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p;
   f.orig_row = H.identity_order ? nullptr : T->orig_row.p;
   f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
   f.seg_N = T->seg_N.p;
-  f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.max_rows_per_day = std::max<int64_t>(H.max_rows_per_day, 1);
+  f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.max_rows_per_day = ring;
   f.params = T->ws_params.p; f.p_ld = S_pad;
   f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
   f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
@@ -245,7 +248,6 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
   f.ttd = A->time_to_detect;
   f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
-  f.ring = ring ? 1 : 0;
   f.u_col = in.u_col; f.u_det = in.u_det; f.u_ld = in.u_ld;
   f.u_icol = in.u_icol; f.u_idet = in.u_idet; f.ui_ld = in.ui_ld;
   DevBuf<double> d_p;
@@ -254,10 +256,10 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     if (on_device) f.p_out = A->p_out;
     else { d_p.alloc((size_t)(H.R * S)); AMRO_CUDA(cudaMemsetAsync(d_p.p, 0xFF, sizeof(double) * H.R * S, st)); f.p_out = d_p.p; }
   }
-  f.state = T->ws_state.p; f.init_state = T->ws_init.p; f.n_slots = n_slots;
+  f.pre = T->ws_pre.p; f.traj = want_traj ? T->ws_traj.p : nullptr;
   f.pressure = T->ws_pressure.p;
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
-  f.team_barrier = T->ws_barrier.p; f.teams = teams; f.ctas_per_team = G;
+  f.team_barrier = T->ws_barrier.p; f.teams = teams; f.ctas_per_team = G; f.sets_by_team = by_team ? 1 : 0;
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
@@ -270,10 +272,10 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
   if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  const int64_t* pos_of = H.identity_order ? nullptr : T->pos_of.p;
   if (A->state_out) {
     if (on_device) {
-      fast_expand(st, f.state, n_slots, H.identity_order ? nullptr : T->pos_of.p, H.R, S, 0, S, A->state_out,
-                  A->state_out + A->so_ld * S, A->so_ld);
+      fast_expand(st, f.traj, pos_of, f.day_start, f.n_days, H.R, S, 0, S, A->state_out, A->state_out + A->so_ld * S, A->so_ld);
       A->launches++;
     } else {
       // expand a block of simulations at a time into the reference's float64 columns, then copy them out
@@ -282,7 +284,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
       buf.alloc((size_t)(2 * H.R * chunk));
       for (int64_t s0 = 0; s0 < S; s0 += chunk) {
         const int64_t ns = std::min(chunk, S - s0);
-        fast_expand(st, f.state, n_slots, H.identity_order ? nullptr : T->pos_of.p, H.R, S, s0, ns, buf.p, buf.p + H.R * chunk, H.R);
+        fast_expand(st, f.traj, pos_of, f.day_start, f.n_days, H.R, S, s0, ns, buf.p, buf.p + H.R * chunk, H.R);
         A->launches++;
         AMRO_CUDA(cudaMemcpy2DAsync(A->state_out + A->so_ld * s0, A->so_ld * sizeof(double), buf.p, H.R * sizeof(double),
                                     H.R * sizeof(double), ns, cudaMemcpyDeviceToHost, st));
@@ -397,8 +399,8 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
       fail(AMRO_EINVAL, "state_out / p_out of %lld x %lld float64 is too large; run a slice of the simulations", (long long)H.R, (long long)S);
 
     int path = A->path;
-    const bool fast_ok = H.fast_eligible && std::abs(A->time_to_detect) <= kMaxAbsTtd && H.total_days <= kMaxAbsTtd &&
-                         (A->sim_offset % 8 == 0);
+    const bool fast_ok = H.fast_eligible && A->time_to_detect >= 0 &&
+                         H.total_days + (int64_t)A->time_to_detect + 2 <= kMaxAbsDay && (A->sim_offset % 8 == 0);
     if (path == AMRO_PATH_AUTO) path = fast_ok ? AMRO_PATH_FAST : AMRO_PATH_GENERAL;
     if (path == AMRO_PATH_FAST && !fast_ok)
       fail(AMRO_EINVAL, "fast path not available: %s", H.fast_eligible ? "time_to_detect / number of days / sim_offset out of range" : H.why_not_fast.c_str());

@@ -49,21 +49,22 @@ void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int6
 void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n);
 
 // ----------------------------------------------------------------------------------------------------
-// FAST path: packed int16 state (2*D + C, D = 16383 meaning +inf), 8 simulations (one 16-byte word) per
-// patient-day record and slice; one persistent cooperative kernel runs the initial state and every day.
+// FAST path: packed 16-bit state, 8 simulations (one 16-byte word) per patient-day record and slice; one
+// persistent cooperative kernel runs the initial state and every day.  See kernels_fast.cu.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kSimsPerSlice = 8;
-constexpr int kInfCode = 16383;            // countdown value standing for +inf
-constexpr int kMaxAbsTtd = 16000;          // |time_to_detect| and total_days limits of the packed state
-constexpr int kFastThreads = 256;
-constexpr int kTableSegs = 16;             // ward-day threshold tables resident in shared memory at once
+constexpr int kMaxAbsDay = 8191;           // 13-bit absolute detection day: total_days + time_to_detect + 2 must fit
+constexpr int kFastThreads = 128;
+constexpr int kFastMinBlocks = 6;          // CTAs per SM the register budget is sized for
+constexpr int kTableSegs = 8;              // ward-day threshold tables resident in shared memory at once
 
 struct FastArgs {
   // topology (device)
-  const uint32_t* meta_src;
   const uint32_t* meta_info;
+  const uint32_t* meta_next;
   const uint32_t* meta_nseg;
   const uint32_t* init_seg;
+  const uint32_t* init_slot;
   const int64_t* orig_row;       // nullptr when identity_order
   const int64_t* day_start;
   const int64_t* day_seg_start;
@@ -77,33 +78,32 @@ struct FastArgs {
   int64_t S;                     // real simulations
   int64_t n_slices;              // ceil(S / 8)
   uint64_t seed, sim_offset;
-  int ttd, tsh_zero_based_unused;
+  int ttd;
   uint64_t tsh, tsa;             // schedules converted the way the reference's unsigned % does
-  int ring;                      // 1: two-day ring of state; 0: full trajectory
   // replay
   const double* u_col; const double* u_det; int64_t u_ld;
   const double* u_icol; const double* u_idet; int64_t ui_ld;
   double* p_out;                 // optional [R x S] (ld = R)
   // state
-  uint4* state;                  // [n_slices][n_slots] 16-byte words; n_slots = R or 2*max_rows_per_day
-  uint4* init_state;             // [n_slices][n_init]
-  int64_t n_slots;
-  int32_t* pressure;             // [n_slices][n_seg][8]
-  int32_t* counts_col;           // [n_days_out x S_pad8] ld = n_days_out  (zeroed by the caller)
+  uint4* pre;                    // [n_sets][2][max_rows_per_day]: pre-step state of the current / next day
+  uint4* traj;                   // nullptr, or [n_slices][R]: post-step state of every record
+  uint32_t* pressure;            // [n_sets][n_seg][4]: 8 x 16-bit colonised counts per ward-day
+  int32_t* counts_col;           // [n_days_out x S_pad8] ld = counts_ld  (zeroed by the caller)
   int32_t* counts_det;
   int64_t counts_ld;
   unsigned int* team_barrier;    // [n_teams] zeroed by the caller
   int teams, ctas_per_team;
+  int sets_by_team;              // 1: pre / pressure indexed by team (reused slice after slice), 0: by slice
 };
 
 // Returns the number of CTAs of kFastThreads threads that can be co-resident (cooperative launch bound).
 int fast_max_coresident_ctas(int device, bool replay);
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int grid);
 
-// state_out[(orig row) + ld*(sim)] = C, state_out[row + ld*(S+sim)] = D for sims [s0, s0+ns) of the run
-void fast_expand(cudaStream_t st, const uint4* state, int64_t n_slots, const int64_t* pos_of, int64_t R,
-                 int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld);
-// pressure_out[seg + ld*sim] = pressure[slice][seg][k]
-void fast_export_pressure(cudaStream_t st, const int32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld);
+// Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run
+void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,
+                 int64_t R, int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld);
+// out[seg + ld*sim] = colonised count the ward-day started with
+void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld);
 
 }  // namespace amro

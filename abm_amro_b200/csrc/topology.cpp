@@ -213,36 +213,42 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   else if (!T.binary_h) T.why_not_fast = "is_new values other than 0/1";
   else if (T.Rp != R) T.why_not_fast = "rows whose day is never stepped";
   else if (!T.simple_final) T.why_not_fast = "next_day links that point to the same or an earlier day";
-  else if (n_init >= (int64_t)kSrcMask) T.why_not_fast = "too many initial rows";
+  else if (!ring) T.why_not_fast = "next_day links that skip a day";
+  else if (T.max_seg_rows > 65535) T.why_not_fast = "a ward-day with more than 65535 records";
+  else if (T.max_rows_per_day >= (int64_t)0xFFFFFFF0u) T.why_not_fast = "too many records in one day";
+  else if (T.max_segs_per_day >= (int64_t)kInfoSegMask) T.why_not_fast = "too many wards in one day";
   if (T.why_not_fast.empty()) {
-    T.meta_src.resize(T.Rp);
     T.meta_info.resize(T.Rp);
+    T.meta_next.assign(T.Rp, kNone);
     T.meta_nseg.assign(T.Rp, kNone);
     T.init_seg.assign(n_init, kNone);
-    for (int64_t d = 0; d < D && T.why_not_fast.empty(); ++d) {
+    T.init_slot.assign(n_init, kNone);
+    T.day_has_init.assign(D, 0);
+    for (int64_t d = 0; d < D; ++d) {
       for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
         const int64_t r = T.order[p];
         const uint32_t seg_local = seg_of_pos[p] - (uint32_t)T.day_seg_start[d];
-        T.meta_info[p] = (T.h[r] == 1.0 ? 0x80000000u : 0u) | seg_local;
+        uint32_t kind = kSrcNone;
         if (pre_src[p] >= 0) {
-          const int64_t pp = T.pos_of[pre_src[p]];
-          const int64_t delta = p - pp;
-          if (delta <= 0 || delta >= (int64_t)kSrcMask) { T.why_not_fast = "predecessor link too long"; break; }
-          T.meta_src[p] = (kSrcPrev << kSrcShift) | (uint32_t)delta;
+          kind = kSrcPrev;
+          const int64_t pp = T.pos_of[pre_src[p]];  // in day d-1 (ring property)
+          T.meta_next[pp] = (uint32_t)(p - T.day_start[d]);
           T.meta_nseg[pp] = seg_of_pos[p];
         } else if (r < n_init) {
-          T.meta_src[p] = (kSrcInit << kSrcShift) | (uint32_t)r;
+          kind = kSrcInit;
+          if (d != 0) T.why_not_fast = "initial-state rows outside day 0";
           T.init_seg[r] = seg_of_pos[p];
-        } else {
-          T.meta_src[p] = (kSrcNone << kSrcShift);
+          T.init_slot[r] = (uint32_t)(p - T.day_start[d]);
+          T.day_has_init[d] = 1;
         }
+        T.meta_info[p] = (T.h[r] == 1.0 ? (1u << kInfoHShift) : 0u) | (kind << kInfoSrcShift) | seg_local;
       }
     }
   }
   T.fast_eligible = T.why_not_fast.empty();
-  T.ring_eligible = T.fast_eligible && ring;
+  T.ring_eligible = T.fast_eligible;
   if (!T.fast_eligible) {
-    T.meta_src.clear(); T.meta_info.clear(); T.meta_nseg.clear(); T.init_seg.clear();
+    T.meta_info.clear(); T.meta_next.clear(); T.meta_nseg.clear(); T.init_seg.clear(); T.init_slot.clear();
   }
 }
 

@@ -12,8 +12,10 @@
 namespace amro {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no segment" / "no successor"
-constexpr uint32_t kSrcNone = 0u, kSrcPrev = 1u, kSrcInit = 2u;  // meta_src kind (top 2 bits)
-constexpr uint32_t kSrcShift = 30, kSrcMask = (1u << kSrcShift) - 1u;
+// meta_info word of a record: bit 31 = is_new, bits 30:29 = where its pre-step state comes from, bits 28:0 = index of
+// its ward-day within the day
+constexpr uint32_t kSrcNone = 0u, kSrcPrev = 1u, kSrcInit = 2u;
+constexpr uint32_t kInfoHShift = 31, kInfoSrcShift = 29, kInfoSegMask = (1u << kInfoSrcShift) - 1u;
 
 struct HostTopology {
   int64_t R = 0, n_init = 0;
@@ -43,10 +45,12 @@ struct HostTopology {
   std::vector<int64_t> push_src, push_dst;  // original row indices
 
   // FAST path per position (valid when fast_eligible)
-  std::vector<uint32_t> meta_src;      // [Rp] kind<<30 | (distance to predecessor position | init row)
-  std::vector<uint32_t> meta_info;     // [Rp] h<<31 | segment index within the day
-  std::vector<uint32_t> meta_nseg;     // [Rp] absolute segment of the successor this row feeds, or kNone
+  std::vector<uint32_t> meta_info;     // [Rp] h<<31 | source kind<<29 | segment index within the day
+  std::vector<uint32_t> meta_next;     // [Rp] position of the successor record within the NEXT day, or kNone
+  std::vector<uint32_t> meta_nseg;     // [Rp] absolute segment of that successor, or kNone
   std::vector<uint32_t> init_seg;      // [n_init] absolute segment of init-sourced stepped rows, or kNone
+  std::vector<uint32_t> init_slot;     // [n_init] position of that row within its day, or kNone
+  std::vector<uint8_t>  day_has_init;  // [total_days+1] 1 if the day holds init-sourced rows
 };
 
 // Throws amro::Error (AMRO_EINDEX / AMRO_ERUNTIME / AMRO_EINVAL) mirroring what the reference raises.

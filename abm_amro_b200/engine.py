@@ -70,7 +70,7 @@ class Topology:
 
     # ---- introspection (host arrays of the compiled form; used by the CPU tests of the compiler) ----
     def debug_arrays(self) -> dict:
-        names = ["order", "day_start", "day_seg_start", "seg_row_start", "seg_N", "meta_src", "meta_info",
+        names = ["order", "day_start", "day_seg_start", "seg_row_start", "seg_N", "meta_next", "meta_info",
                  "meta_nseg", "init_seg", "push_src", "push_dst"]
         ptrs = [C.c_void_p() for _ in names]
         n_push = C.c_int64()
@@ -79,7 +79,7 @@ class Topology:
         D = i.total_days + 1
         shapes = {"order": (i.n_rows, np.int64), "day_start": (D + 1, np.int64), "day_seg_start": (D + 1, np.int64),
                   "seg_row_start": (i.n_segments + 1, np.int64), "seg_N": (i.n_segments, np.float64),
-                  "meta_src": (i.n_rows_stepped, np.uint32), "meta_info": (i.n_rows_stepped, np.uint32),
+                  "meta_next": (i.n_rows_stepped, np.uint32), "meta_info": (i.n_rows_stepped, np.uint32),
                   "meta_nseg": (i.n_rows_stepped, np.uint32), "init_seg": (i.n_init, np.uint32),
                   "push_src": (n_push.value, np.int64), "push_dst": (n_push.value, np.int64)}
         out = {}

@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the ward-level colonisation path (BASELINE.json metric: patient-day-updates/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE full run of the hot path over the workload: every day of the synthetic hospital for every
+ensemble member resident on the GPU (config 2 of BASELINE.json: 30 wards x 10,000 patients x 365 days,
+1,000 members per GPU; weak scaling: every GPU runs its own 1,000 members, Philox counters offset by the
+global member index).  One JSON line is printed by rank 0.
+
+  value        device-resident: parameters already in HBM, per-day counts stay in HBM (CUDA events)
+  e2e          the same run through the host-pointer C ABI call a user makes (amro_simulate with pinned host
+               buffers): parameters copied host->device and the per-(day, member) counts copied back, every step
+  roofline     algorithmic bytes (4 + 20/S_gpu per update) / device time of the fused kernel
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, compiled from the unmodified sources) on the
+               host cores, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (wards, census, days, members per GPU)
+    "cfg1_5w_300p_100d_20s": (5, 300, 100, 20),
+    "cfg2_30w_10kp_365d_1000s": (30, 10_000, 365, 1000),
+    "cfg3_20w_5kp_180d_65536s": (20, 5_000, 180, 65_536),
+}
+DEFAULT_WORKLOAD = "cfg2_30w_10kp_365d_1000s"
+TTD, TSH, TSA, SEED, ICP, IDP = 2, 7, 1, 42, 0.2, 0.2
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes(workload: str):
+    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period_s, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores, bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def truncate_hospital(wm, tp, n_days):
+    keep = wm[:, 0] < n_days
+    w = np.asfortranarray(wm[keep].copy())
+    w[w[:, 5] >= w.shape[0], 5] = -1.0  # links into the removed days
+    t = np.asfortranarray(tp[tp[:, 0] < n_days].copy())
+    return w, t
+
+
+def cpu_sample(workload: str, sample_days: int = 60, sims_per_proc: int = 32, reps: int = 1):
+    """Run the reference CPU path on `procs` host processes, each with its own slice of `sims_per_proc`
+    ensemble members of the first `sample_days` days of the workload.  Returns (updates/s, procs, kind, text)."""
+    from abm_amro_b200 import synth
+    from oracle import ref_runner
+    wards, census, days, _ = WORKLOADS[workload]
+    wm, tp, n_init = synth.make_hospital(wards, census, min(days, sample_days), seed=1)
+    R = wm.shape[0]
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
+    except Exception:
+        avail = 16 << 30
+    per_proc = R * (6 + 2 * sims_per_proc) * 8 * 3
+    procs = max(1, min(ncpu, int(avail * 0.5 / per_proc)))
+    par = synth.tutorial_parameters(sims_per_proc)
+    icp = np.full((n_init, sims_per_proc), ICP, order="F")
+    idp = np.full((n_init, sims_per_proc), IDP, order="F")
+    updates = float(R) * sims_per_proc * procs
+    if ref_runner.available("native"):
+        kind = "reference"
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            fin = os.path.join(td, "in.npz")
+            names = ["icp", "idp", "wm", "tp", "par", "ttd", "tsh", "tsa", "seed"]
+            vals = [icp, idp, wm, tp, par, np.array(TTD), np.array(TSH), np.array(TSA), np.array(SEED)]
+            np.savez(fin, func=np.array("simulate_discrete_model"), argnames=np.array(names), reps=np.array(reps),
+                     **dict(zip(names, vals)))
+            worker = os.path.join(ROOT, "oracle", "_ref_worker.py")
+            ps = [subprocess.Popen([sys.executable, worker, "native", fin, os.path.join(td, f"o{i}.npz")],
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE) for i in range(procs)]
+            for p in ps:
+                _, err = p.communicate()
+                if p.returncode != 0:
+                    raise RuntimeError("reference worker failed: " + err.decode()[-500:])
+            secs = max(float(np.load(os.path.join(td, f"o{i}.npz"))["seconds"]) for i in range(procs))
+    else:
+        kind = "port"
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(procs) as pool:
+            secs = max(pool.map(_port_worker, [(wards, census, min(days, sample_days), sims_per_proc, reps)] * procs))
+    text = (f"{workload}: first {min(days, sample_days)} days ({R} patient-day rows) x {sims_per_proc} members per process, "
+            f"{procs} concurrent single-threaded processes (the reference has no threading), simulate_discrete_model only")
+    return updates / secs, procs, kind, text
+
+
+def _port_worker(spec):
+    wards, census, days, S, reps = spec
+    sys.path.insert(0, ROOT)
+    from abm_amro_b200 import synth
+    from oracle import oracle
+    wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
+    par = synth.tutorial_parameters(S)
+    icp = np.full((n_init, S), ICP, order="F"); idp = np.full((n_init, S), IDP, order="F")
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.simulate_discrete_model(icp, idp, wm, tp, par, TTD, TSH, TSA, SEED)
+    return (time.perf_counter() - t0) / reps
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    ts = []
+    val = procs = kind = text = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        val, procs, kind, text = cpu_sample(args.workload)
+        if i >= args.warmup:
+            ts.append((time.perf_counter() - t0, val))
+    value = float(np.mean([v for _, v in ts]))
+    wards, census, days, S = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "patient-day-updates/sec", "value": value, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([t for t, _ in ts])) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "wards": wards, "census": census, "days": days, "members_per_gpu": S,
+                   "note": "CPU arm: bounded sample of the workload, see cpu_baseline.sample"},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": procs, "kind": kind, "sample": text},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from abm_amro_b200 import capi, engine, ensemble, synth
+
+    wards, census, days, S = WORKLOADS[args.workload]
+    if args.members:
+        S = args.members
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
+    R = wm.shape[0]
+    t0 = time.perf_counter()
+    topo = engine.Topology(wm, tp, n_init, device=local_rank)
+    topo_ms = (time.perf_counter() - t0) * 1e3
+    info = topo.info
+    n_days = info.n_days_out
+    updates_per_step = float(R) * S
+    sim_offset = rank * ((S + 7) // 8 * 8)
+    par_np = synth.tutorial_parameters(S) if not args.workload.startswith("cfg3") else synth.particle_parameters(S)
+
+    # ---- device-resident inputs / outputs ------------------------------------------------------------------
+    par_d = torch.from_numpy(np.ascontiguousarray(par_np.T)).to(dev)            # [6 x S] row-major == [S x 6] column-major
+    icp_d = torch.tensor([ICP], dtype=torch.float64, device=dev)
+    idp_d = torch.tensor([IDP], dtype=torch.float64, device=dev)
+    cc_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)               # == [n_days x S] column-major
+    cd_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        flush.zero_()                                                            # evict L2 between steps
+        r = topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), idp_d.data_ptr(), cc_d.data_ptr(),
+                                 cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset,
+                                 stream=stream.cuda_stream)
+        if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members
+            ensemble.collapse(ensemble.day_moments(cc_d, cd_d), S * world)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches = [], 0
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            r = step_device()
+            kernel_ms.append(r.kernel_ms)
+            launches += r.launches
+        e1.record(stream)
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    path_used = r.path_used
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = updates_per_step * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI call (pinned host buffers) ---------------------------------
+    par_h = torch.empty((6, S), dtype=torch.float64).pin_memory()
+    par_h.copy_(torch.from_numpy(np.ascontiguousarray(par_np.T)))
+    cc_h = torch.empty((S, n_days), dtype=torch.int32).pin_memory()
+    cd_h = torch.empty((S, n_days), dtype=torch.int32).pin_memory()
+    a = capi.SimArgs()
+    a.n_sims, a.sim_offset = S, sim_offset
+    a.time_to_detect, a.testing_schedule_hospitalized, a.testing_schedule_arrivals, a.seed = TTD, TSH, TSA, SEED
+    a.rng_mode, a.path, a.keep_trajectory, a.pointers_on_device = capi.RNG_PHILOX, capi.PATH_AUTO, 0, 0
+    a.parameters, a.p_rows, a.p_ld = par_h.data_ptr(), S, S
+    icp_h, idp_h = np.array([ICP]), np.array([IDP])
+    a.icp, a.idp = icp_h.ctypes.data, idp_h.ctypes.data
+    a.counts_colonized, a.counts_detected = cc_h.data_ptr(), cd_h.data_ptr()
+    import ctypes
+
+    def step_host():
+        flush.zero_()
+        capi.check(capi.lib().amro_simulate(topo._h, ctypes.byref(a)))
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = updates_per_step * world * e2e_steps / e2e_s
+    same = bool(torch.equal(cc_h, cc_d.cpu()) and torch.equal(cd_h, cd_d.cpu()))
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        b_alg = 4.0 + 20.0 / S
+        k_ms = float(np.mean(kernel_ms))
+        achieved = updates_per_step * b_alg / (k_ms * 1e-3) / 1e9
+        traffic = ncu_traffic_bytes(args.workload)
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, procs, kind, text = cpu_sample(args.workload)
+            cpu = {"value": v, "unit": "updates/s", "cores": procs, "kind": kind, "sample": text}
+        line = {
+            "metric": "patient-day-updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 state / u32 Philox / f64 probabilities",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "wards": wards, "census": census, "days": days, "members_per_gpu": S,
+                       "patient_day_rows": R, "updates_per_step_per_gpu": updates_per_step,
+                       "path": "fast" if path_used == capi.PATH_FAST else "general",
+                       "l2": "256 MB buffer written between steps (inside the timed region)",
+                       "topology_compile_ms": topo_ms,
+                       "counts_match_between_device_and_host_api": same},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": b_alg,
+                         "kernel_ms": k_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "updates/s",
+                    "h2d_bytes_per_step": int(S * 6 * 8 + 16), "d2h_bytes_per_step": int(2 * n_days * S * 4),
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    topo.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--members", type=int, default=0, help="override members per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference_arm(args, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else 50
+    args.warmup = args.warmup if args.warmup is not None else 5
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves the way the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
