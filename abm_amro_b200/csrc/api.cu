@@ -247,6 +247,10 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.S = S; f.n_slices = n_slices;
   f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
   f.ttd = A->time_to_detect;
+  for (int r = 0; r < 10; ++r) {
+    f.rk[2 * r] = (uint32_t)f.seed + (uint32_t)r * 0x9E3779B9u;
+    f.rk[2 * r + 1] = (uint32_t)(f.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
   f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
   f.u_col = in.u_col; f.u_det = in.u_det; f.u_ld = in.u_ld;
   f.u_icol = in.u_icol; f.u_idet = in.u_idet; f.ui_ld = in.ui_ld;
@@ -399,8 +403,8 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
       fail(AMRO_EINVAL, "state_out / p_out of %lld x %lld float64 is too large; run a slice of the simulations", (long long)H.R, (long long)S);
 
     int path = A->path;
-    const bool fast_ok = H.fast_eligible && A->time_to_detect >= 0 &&
-                         H.total_days + (int64_t)A->time_to_detect + 2 <= kMaxAbsDay && (A->sim_offset % 8 == 0);
+    const bool fast_ok = H.fast_eligible && A->time_to_detect >= 0 && A->time_to_detect <= kMaxCountdown &&
+                         H.total_days <= kMaxCountdown && (A->sim_offset % 8 == 0);
     if (path == AMRO_PATH_AUTO) path = fast_ok ? AMRO_PATH_FAST : AMRO_PATH_GENERAL;
     if (path == AMRO_PATH_FAST && !fast_ok)
       fail(AMRO_EINVAL, "fast path not available: %s", H.fast_eligible ? "time_to_detect / number of days / sim_offset out of range" : H.why_not_fast.c_str());

@@ -53,7 +53,7 @@ void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64
 // persistent cooperative kernel runs the initial state and every day.  See kernels_fast.cu.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kSimsPerSlice = 8;
-constexpr int kMaxAbsDay = 8191;           // 13-bit absolute detection day: total_days + time_to_detect + 2 must fit
+constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-bit field: days and time_to_detect limits
 constexpr int kFastThreads = 128;
 constexpr int kFastMinBlocks = 6;          // CTAs per SM the register budget is sized for
 constexpr int kTableSegs = 8;              // ward-day threshold tables resident in shared memory at once
@@ -78,6 +78,7 @@ struct FastArgs {
   int64_t S;                     // real simulations
   int64_t n_slices;              // ceil(S / 8)
   uint64_t seed, sim_offset;
+  uint32_t rk[20];               // Philox round keys (key + r*Weyl), consumed straight from the constant bank
   int ttd;
   uint64_t tsh, tsa;             // schedules converted the way the reference's unsigned % does
   // replay

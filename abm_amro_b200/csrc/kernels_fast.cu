@@ -5,16 +5,17 @@
 // with total_positive_colonized/_detected (:435-509), for hospitals with unit weights, is_new in {0,1},
 // time_to_detect >= 0 and next_day links that connect consecutive days.
 //
-// State of one (record, simulation): 16 bits = class << 13 | absolute detection day.
-//   class 0 U   uncolonised                              (reference: C=0, D=inf)
-//         1 A   colonised, no test result coming         (C=1, D=inf)
-//         2 U0  uncolonised with a zero countdown        (C=0, D=0: the initial-state quirk of :372)
-//         3 Pn  colonised, result pending                (C=1, 0 < D <= ttd)
-//         5 B   colonised, detected                      (C=1, D <= 0)
-//   The reference decrements D once per day; here a pending/detected record stores Dabs = D + day, which
-//   does not change from day to day, and the class bit "detected" is refreshed when the state is written.
-//   D of the record of day d after its step is Dabs - d - 1 (fast_expand turns the codes back into C / D).
-//   Bit 13 of a code = colonised, bit 15 = detected: the per-day totals are two shifts and a mask.
+// State of one (record, simulation): a 16-bit code whose top 3 bits are its class.
+//   0x0000        U   uncolonised                              (reference: C=0, D=inf)
+//   0x2000        A   colonised, no test result coming         (C=1, D=inf)
+//   0x4000        U0  uncolonised with a zero countdown        (C=0, D=0: the initial-state quirk of :372)
+//   0x8000 - D        colonised with a finite countdown D: class 3 (0x6000..0x7FFF) while the result is pending
+//                     (0 < D <= ttd), class 4 (0x8000..) once detected (D <= 0).  The reference's daily
+//                     `D -= 1` (:131-132) is `code += 1`, and "pending -> detected" is the carry into bit 15.
+//   Every transition is `new = old + delta` with delta depending only on (class, tested positive today), because the
+//   classes U, A, U0 each have ONE code: U -> A | 0x8000-ttd, A -> A | 0x8000-ttd, U0 -> 0x8001, pending/detected -> +1.
+//   The deltas ride in the low halves of the threshold table entries, so a (record, simulation) update is:
+//   one shared-memory lookup by class, two unsigned compares against the Philox chunk, a select and an add.
 //
 // Data layout (HBM):
 //   pre       [set][2][max records per day]  one 16-byte word = 8 simulations per record; buffer d&1 holds the
@@ -39,12 +40,11 @@
 namespace amro {
 namespace {
 
-constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 5;
+constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 4, kNumCls = 5;
 constexpr uint32_t kClsShift = 13;
-constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, kCodePn = kClsPn << kClsShift,
-                   kCodeB = kClsB << kClsShift;
-constexpr int kSlots = 6, kSlotStride = 9, kRowStride = kSlots * kSlotStride;  // padded: conflict-free lookups
-constexpr int kFlushEvery = 1024;  // row iterations between flushes of the 16-bit packed per-lane counters
+constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, kCodeZero = kClsB << kClsShift;
+constexpr int kTabRow = 8 * (int)kNumCls + 1;  // entries per (ward-day, is_new): [sim][class], +1 pad against bank conflicts
+constexpr int kFlushEvery = 1024;              // row iterations between flushes of the 16-bit packed per-lane counters
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -87,12 +87,26 @@ __device__ __forceinline__ double class_probability(int pc, int h, double F, dou
   return P;
 }
 
+// probability class of a state class: U, U0 -> 0; A, pending -> 1; detected -> 2
+__device__ __forceinline__ int prob_class(uint32_t cls) { return cls == kClsB ? 2 : (cls == kClsA || cls == kClsPn) ? 1 : 0; }
+
+// code delta of a colonised outcome: (class, tested positive today) -> new code - old code  (mod 2^16)
+__device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) {
+  const uint32_t newdet = kCodeZero - (uint32_t)ttd;  // D = ttd after the step (:135 / :147)
+  if (cls == kClsU) return hit ? newdet : kCodeA;      // D = inf (:138 / :150)
+  if (cls == kClsA) return (hit ? newdet : kCodeA) - kCodeA;
+  if (cls == kClsU0) return (kCodeZero + 1u) - kCodeU0;  // D = 0 <= ttd: D -= 1 (:131-132 / :143-144)
+  return 1u;                                            // pending / detected: D -= 1
+}
+
 template <bool REPLAY>
 struct Shared;
 template <>
 struct Shared<false> {
-  uint2 hi[kTableSegs * 2 * kRowStride];    // {T(P) >> 16, T(P*rho) >> 16} at [(seg*2+h)*54 + class*9 + sim]
-  ushort2 lo[kTableSegs * 2 * kRowStride];  // low 16 bits, read only on a tie
+  // x = (T(P) >> 17) << 16 | delta(not tested positive), y = (T(P*rho) >> 17) << 16 | delta(tested positive), at
+  // [(ward-day*2 + is_new)*kTabRow + sim*5 + class]
+  uint2 tab[kTableSegs * 2 * kTabRow];
+  ulonglong2 full[kTableSegs * 2 * kTabRow];  // the 33-bit thresholds {T(P), T(P*rho)}, read only on a tie
   SliceParams par;
   int cnt[16];
 };
@@ -103,82 +117,89 @@ struct Shared<true> {
   int cnt[16];
 };
 
-struct DayConst {        // uniform per day
-  uint32_t newdet;       // code a newly tested-positive record gets: D = ttd after the step
-  uint32_t quirk;        // code of a U0 record that gets colonised: D = -1 after the step
-  uint32_t bump_lim;     // a pending record with Dabs <= bump_lim is detected from tomorrow on
-  bool test_h, test_a;
-};
-
-__device__ __forceinline__ uint32_t next_code(uint32_t v, uint32_t cls, bool col, bool dh, const DayConst& dc, bool has_u0) {
-  const bool keep = v >= kCodePn;                                  // pending / detected: countdown runs on (:131-132)
-  const bool bump = (v - kCodePn) <= dc.bump_lim;                  // pending whose D reaches 0 with this step
-  const uint32_t v2 = v + (bump ? (kCodeB - kCodePn) : 0u);
-  uint32_t r1 = dh ? dc.newdet : kCodeA;                           // :134-138 / :146-150
-  if (has_u0) r1 = (cls == kClsU0) ? dc.quirk : r1;
-  const uint32_t r2 = keep ? v2 : r1;
-  return col ? r2 : 0u;                                            // :153-155
+// Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
+__device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t kx) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a.rk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ a.rk[2 * r + 1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  (void)kx;
+  return make_uint4(c0, c1, c2, c3);
 }
 
-// One record, eight simulations.  Returns the packed post-step codes.
-template <bool REPLAY, bool HAS_U0>
-__device__ __forceinline__ uint4 step_record(const Shared<REPLAY>& sh, const FastArgs& a, const uint4 pre, int ti, int h,
-                                             int64_t orig, uint32_t gslice, int64_t sim0, uint32_t key0, uint32_t key1,
-                                             const DayConst& dc) {
+// Rare path (probability 2^-14 per update): a chunk tied with the upper 15 bits of a threshold.  Redo the record's
+// eight simulations with the full 32-bit uniforms (primary chunk << 16 | refinement chunk) against the 33-bit thresholds.
+__device__ __noinline__ uint4 step_record_exact(const uint2* tab, const ulonglong2* full, const FastArgs& a, uint4 pre,
+                                                uint4 rnd, uint32_t c0, uint32_t c1, uint32_t c2) {
+  const uint4 rf = philox_rk(a, c0, c1, c2, kStreamStep + 1u, 0);
+  const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w}, rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w}, fw[4] = {rf.x, rf.y, rf.z, rf.w};
+  uint32_t postw[4] = {0, 0, 0, 0};
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+    const uint64_t u = (uint64_t)((((rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) << 16) | ((fw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu));
+    const uint32_t cls = v >> kClsShift;
+    const uint2 e = tab[k * kNumCls + cls];
+    const ulonglong2 T = full[k * kNumCls + cls];
+    const bool col = u < T.x, hit = u < T.y;
+    const uint32_t o = col ? ((v + (hit ? e.y : e.x)) & 0xFFFFu) : 0u;
+    postw[k >> 1] |= o << (16 * (k & 1));
+  }
+  return make_uint4(postw[0], postw[1], postw[2], postw[3]);
+}
+
+// One record, eight simulations, free-running mode.
+__device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2* full, const FastArgs& a, const uint4 pre,
+                                             uint32_t c0, uint32_t c1, uint32_t c2) {
+  const uint4 rnd = philox_rk(a, c0, c1, c2, kStreamStep, 0);
+  const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w}, rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+  uint32_t o[8];
+  uint32_t tmin = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t w = prew[k >> 1], r = rw[k >> 1];
+    const uint32_t v = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+    const uint32_t cls = (k & 1) ? (w >> 29) : ((w >> kClsShift) & 7u);
+    const uint2 e = tab[k * kNumCls + cls];
+    // upper 15 bits of the chunk in the upper half, ones below: cw < e.x  <=>  chunk15 < threshold15
+    const uint32_t cw = ((k & 1) ? (r >> 1) : (r << 15)) & 0x7FFF0000u | 0xFFFFu;
+    const bool col = cw < e.x, hit = cw < e.y;
+    tmin = min(tmin, min(cw ^ e.x, cw ^ e.y));           // < 0x10000  <=>  chunk15 == threshold15: a tie
+    o[k] = col ? (v + (hit ? e.y : e.x)) : 0u;           // new code = old + delta (low 16 bits)
+  }
+  if (tmin < 0x10000u) return step_record_exact(tab, full, a, pre, rnd, c0, c1, c2);
+  return make_uint4(__byte_perm(o[0], o[1], 0x5410), __byte_perm(o[2], o[3], 0x5410), __byte_perm(o[4], o[5], 0x5410),
+                    __byte_perm(o[6], o[7], 0x5410));
+}
+
+// One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
+__device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, const FastArgs& a, const uint4 pre, int row, int h,
+                                                    int64_t orig, int64_t sim0, bool flag) {
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w};
-  uint32_t postw[4];
-  if constexpr (!REPLAY) {
-    const uint2* tab = sh.hi + (ti * 2 + h) * kRowStride;
-    const uint4 rnd = philox4x32_10((uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), gslice, kStreamStep, key0, key1);
-    const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-    bool tie = false;
+  uint32_t postw[4] = {0, 0, 0, 0};
+  const double* rho_tab = h ? sh.par.rho_i : sh.par.rho_h;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t v = (k & 1) ? (prew[k >> 1] >> 16) : (prew[k >> 1] & 0xFFFFu);
-      const uint32_t c = (k & 1) ? (rw[k >> 1] >> 16) : (rw[k >> 1] & 0xFFFFu);
-      const uint32_t cls = v >> kClsShift;
-      const uint2 T = tab[cls * kSlotStride + k];
-      tie |= (c == T.x) | (c == T.y);
-      const uint32_t o = next_code(v, cls, c < T.x, c < T.y, dc, HAS_U0);
-      if (k & 1) postw[k >> 1] |= o << 16; else postw[k >> 1] = o;
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+    const uint32_t cls = v >> kClsShift;
+    const int64_t sim = sim0 + k;
+    const double P = sh.P[row][prob_class(cls)][k];
+    bool col = false, hit = false;
+    if (sim < a.S) {
+      if (a.p_out) a.p_out[orig + a.R * sim] = P;
+      col = a.u_col[orig + a.u_ld * sim] < P;                                                  // :116
+      // a finite countdown is always <= ttd here (ttd >= 0), so only U and A reach the test (:131 / :134)
+      if (col && cls <= kClsA && flag) hit = a.u_det[orig + a.u_ld * sim] <= rho_tab[k];       // :134 / :146
     }
-    if (tie) {  // probability 2^-15 per update: redo the record with the refinement chunks (full 32-bit uniforms)
-      const ushort2* tlo = sh.lo + (ti * 2 + h) * kRowStride;
-      const uint4 rf = philox4x32_10((uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), gslice, kStreamStep + 1u, key0, key1);
-      const uint32_t fw[4] = {rf.x, rf.y, rf.z, rf.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-        const uint32_t c = (rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-        const uint32_t f = (fw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-        const uint64_t u = ((uint64_t)c << 16) | f;
-        const uint32_t cls = v >> kClsShift;
-        const uint2 Th = tab[cls * kSlotStride + k];
-        const ushort2 Tl = tlo[cls * kSlotStride + k];
-        const bool col = u < (((uint64_t)Th.x << 16) | Tl.x), dh = u < (((uint64_t)Th.y << 16) | Tl.y);
-        const uint32_t o = next_code(v, cls, col, dh, dc, true);
-        if (k & 1) postw[k >> 1] |= o << 16; else postw[k >> 1] = o;
-      }
-    }
-  } else {
-    const double* rho_tab = h ? sh.par.rho_i : sh.par.rho_h;
-    const bool flag = h ? dc.test_a : dc.test_h;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t v = (k & 1) ? (prew[k >> 1] >> 16) : (prew[k >> 1] & 0xFFFFu);
-      const uint32_t cls = v >> kClsShift;
-      const int pc = (cls == kClsB) ? 2 : (int)(cls & 1u);
-      const int64_t sim = sim0 + k;
-      const double P = sh.P[ti * 2 + h][pc][k];
-      bool col = false, dh = false;
-      if (sim < a.S) {
-        if (a.p_out) a.p_out[orig + a.R * sim] = P;
-        col = a.u_col[orig + a.u_ld * sim] < P;                                              // :116
-        if (col && cls < kClsU0 && flag) dh = a.u_det[orig + a.u_ld * sim] <= rho_tab[k];    // :134 / :146
-      }
-      const uint32_t o = next_code(v, cls, col, dh, dc, true);
-      if (k & 1) postw[k >> 1] |= o << 16; else postw[k >> 1] = o;
-    }
+    const uint32_t o = col ? ((v + code_delta(cls, hit, a.ttd)) & 0xFFFFu) : 0u;               // :153-155
+    postw[k >> 1] |= o << (16 * (k & 1));
   }
   return make_uint4(postw[0], postw[1], postw[2], postw[3]);
 }
@@ -186,7 +207,7 @@ __device__ __forceinline__ uint4 step_record(const Shared<REPLAY>& sh, const Fas
 }  // namespace
 
 template <bool REPLAY>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const FastArgs a) {
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const __grid_constant__ FastArgs a) {
   __shared__ Shared<REPLAY> sh;
   const int tid = threadIdx.x, lane = tid & 31;
   const int team = blockIdx.x / a.ctas_per_team, rank = blockIdx.x % a.ctas_per_team;
@@ -194,7 +215,6 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
   unsigned bar_target = 0;
   unsigned* bar = a.team_barrier + team;
   const int G = a.ctas_per_team;
-  const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
   const int64_t ring = a.max_rows_per_day;
 
   if (tid < 16) sh.cnt[tid] = 0;
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
           // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
           //   uncolonised -> D = 0 (U0);  colonised, flag 0 -> D = 0: detected;  flag 1 -> D = 1: pending if
           //   ttd >= 1, else (1 > ttd) it is neither pending nor detected and gets re-tested like D = inf
-          const uint32_t code = !c0 ? kCodeU0 : (!d0 ? (kCodeB | 0u) : (a.ttd >= 1 ? (kCodePn | 1u) : kCodeA));
+          const uint32_t code = !c0 ? kCodeU0 : (!d0 ? kCodeZero : (a.ttd >= 1 ? kCodeZero - 1u : kCodeA));
           w[k >> 1] |= code << (16 * (k & 1));
           cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
         }
@@ -263,17 +283,15 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
     // ---- day loop (abm_wards.cpp:381) -------------------------------------------------------------------
     for (int64_t d = 0; d < a.n_days; ++d) {
       const int64_t da = a.day_start[d], db = a.day_start[d + 1];
-      const int64_t n = db - da, per = ((n + G - 1) / G + 31) / 32 * 32;
-      const int64_t lo = da + rank * per, hi = min(db, lo + per);
-      DayConst dc;
-      dc.test_h = ((uint64_t)d % a.tsh) == 0;  // :391-392
-      dc.test_a = ((uint64_t)d % a.tsa) == 0;
-      dc.newdet = (a.ttd == 0 ? kCodeB : kCodePn) | (uint32_t)(d + 1 + a.ttd);
-      dc.quirk = kCodeB | (uint32_t)d;
-      dc.bump_lim = (uint32_t)(d + 1);
+      const uint32_t n = (uint32_t)(db - da), per = ((n + G - 1) / G + 31) / 32 * 32;
+      const uint32_t lo = min(n, (uint32_t)rank * per), hi = min(n, lo + per);   // this CTA's records, day-relative
+      const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
       const int64_t seg0 = a.day_seg_start[d];
       const uint4* cur = pre + (d & 1) * ring;
       uint4* nxt = pre + ((d + 1) & 1) * ring;
+      const uint32_t* m_info = a.meta_info + da;
+      const uint32_t* m_next = a.meta_next + da;
+      const uint32_t* m_nseg = a.meta_nseg + da;
       uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
       int since_flush = 0;
 
@@ -295,11 +313,11 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
       };
 
       if (lo < hi) {
-        const int64_t seg_first = seg0 + (a.meta_info[lo] & kInfoSegMask);
-        const int64_t seg_last = seg0 + (a.meta_info[hi - 1] & kInfoSegMask);
+        const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
+        const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
         for (int64_t sb = seg_first; sb <= seg_last; sb += kTableSegs) {
           const int64_t se = min(seg_last + 1, sb + kTableSegs);
-          // ---- threshold tables of ward-days [sb, se) ------------------------------------------------------
+          // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
           __syncthreads();
           for (int t = tid; t < (int)(se - sb) * 16; t += kFastThreads) {
             const int si = t >> 4, h = (t >> 3) & 1, k = t & 7;
@@ -308,57 +326,56 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
             const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
             // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
             const double F = __dmul_rn(__ddiv_rn(sh.par.beta[k], a.seg_N[seg]), (double)cnt);
-            const bool flag = h ? dc.test_a : dc.test_h;
+            const bool flag = h ? test_a : test_h;
             const double rho = h ? sh.par.rho_i[k] : sh.par.rho_h[k];
+            double P[3];
 #pragma unroll
-            for (int pc = 0; pc < 3; ++pc) {
-              const double P = class_probability(pc, h, F, sh.par.alpha[k], sh.par.alpha2[k], sh.par.gamma[k]);
-              if constexpr (REPLAY) {
-                sh.P[si * 2 + h][pc][k] = P;
-              } else {
-                const uint64_t T = threshold33(P);
-                const uint64_t TD = flag ? threshold33(__dmul_rn(clamp01(P), rho)) : 0ull;
-                const uint2 e_test = make_uint2((uint32_t)(T >> 16), (uint32_t)(TD >> 16));
-                const uint2 e_none = make_uint2((uint32_t)(T >> 16), 0u);
-                const ushort2 l_test = make_ushort2((unsigned short)(T & 0xFFFFu), (unsigned short)(TD & 0xFFFFu));
-                const ushort2 l_none = make_ushort2((unsigned short)(T & 0xFFFFu), 0);
-                const int row = (si * 2 + h) * kRowStride + k;
-                // U and A are tested today; U0, Pn and B keep their countdown (no new test)
-                if (pc == 0) { sh.hi[row + kClsU * kSlotStride] = e_test; sh.lo[row + kClsU * kSlotStride] = l_test;
-                               sh.hi[row + kClsU0 * kSlotStride] = e_none; sh.lo[row + kClsU0 * kSlotStride] = l_none; }
-                if (pc == 1) { sh.hi[row + kClsA * kSlotStride] = e_test; sh.lo[row + kClsA * kSlotStride] = l_test;
-                               sh.hi[row + kClsPn * kSlotStride] = e_none; sh.lo[row + kClsPn * kSlotStride] = l_none; }
-                if (pc == 2) { sh.hi[row + kClsB * kSlotStride] = e_none; sh.lo[row + kClsB * kSlotStride] = l_none; }
+            for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, sh.par.alpha[k], sh.par.alpha2[k], sh.par.gamma[k]);
+            if constexpr (REPLAY) {
+#pragma unroll
+              for (int pc = 0; pc < 3; ++pc) sh.P[si * 2 + h][pc][k] = P[pc];
+            } else {
+              const int row = (si * 2 + h) * kTabRow + k * (int)kNumCls;
+#pragma unroll
+              for (uint32_t cls = 0; cls < kNumCls; ++cls) {
+                const double p = P[prob_class(cls)];
+                const uint64_t T = threshold33(p);
+                // U and A are tested today (if it is a testing day); a running countdown is not re-tested
+                const uint64_t TD = (flag && cls <= kClsA) ? threshold33(__dmul_rn(clamp01(p), rho)) : 0ull;
+                sh.tab[row + cls] = make_uint2((uint32_t)(T >> 17) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
+                                               (uint32_t)(TD >> 17) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
+                sh.full[row + cls] = make_ulonglong2(T, TD);
               }
             }
           }
           __syncthreads();
           // ---- the records of those ward-days that belong to this CTA ----------------------------------------
-          const int64_t rb = max(lo, a.seg_row_start[sb]), re = min(hi, a.seg_row_start[se]);
-          for (int64_t base = rb; base < re; base += kFastThreads) {  // CTA-uniform trip count (warp collectives below)
-            const int64_t p = base + tid;
-            const bool valid = p < re;
+          const uint32_t rb = max(lo, (uint32_t)(a.seg_row_start[sb] - da)), re = min(hi, (uint32_t)(a.seg_row_start[se] - da));
+          for (uint32_t base = rb; base < re; base += kFastThreads) {  // CTA-uniform trip count (warp collectives below)
+            const uint32_t i = base + tid;
             uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
             uint32_t nseg = kNone;
-            if (valid) {
-              const uint32_t info = __ldg(&a.meta_info[p]);
-              const uint32_t next = __ldg(&a.meta_next[p]);
-              nseg = __ldg(&a.meta_nseg[p]);
-              uint4 prev = __ldcg(&cur[p - da]);
+            if (i < re) {
+              const uint32_t info = __ldg(&m_info[i]);
+              const uint32_t next = __ldg(&m_next[i]);
+              nseg = __ldg(&m_nseg[i]);
+              uint4 prev = __ldcg(&cur[i]);
+              const int64_t p = da + i;
               const int64_t orig = a.orig_row ? a.orig_row[p] : p;
               const int h = (int)(info >> kInfoHShift);
-              const int ti = (int)((int64_t)(info & kInfoSegMask) + seg0 - sb);
+              const int row = ((int)((int64_t)(info & kInfoSegMask) + seg0 - sb)) * 2 + h;
               if (((info >> kInfoSrcShift) & 3u) == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
               uint4 post;
-              if (d == 0) post = step_record<REPLAY, true>(sh, a, prev, ti, h, orig, gslice, sim0, key0, key1, dc);
-              else post = step_record<REPLAY, false>(sh, a, prev, ti, h, orig, gslice, sim0, key0, key1, dc);
+              if constexpr (REPLAY) post = step_record_replay(sh, a, prev, row, h, orig, sim0, h ? test_a : test_h);
+              else post = step_record(sh.tab + row * kTabRow, sh.full + row * kTabRow, a, prev, (uint32_t)orig,
+                                      (uint32_t)((uint64_t)orig >> 32), gslice);
               if (next != kNone) __stcg(&nxt[next], post);     // :402-407 the successor starts from this state
               if (traj) __stcg(&traj[p], post);
               const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                colw[j] = (pw[j] >> 13) & 0x00010001u;
-                detw[j] = (pw[j] >> 15) & 0x00010001u;
+                detw[j] = (pw[j] >> 15) & 0x00010001u;                       // class 4: D <= 0
+                colw[j] = ((pw[j] >> 13) & 0x00010001u) | detw[j];           // classes 1, 3 (bit 13) and 4
               }
             }
 #pragma unroll
@@ -404,22 +421,14 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const Fas
 
 // ---- packed trajectory -> the reference's float64 columns ------------------------------------------------------
 namespace {
-__global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __restrict__ pos_of,
-                              const int64_t* __restrict__ day_start, int64_t n_days, int64_t R, int64_t S, int64_t s0,
-                              int64_t ns, double* __restrict__ Cout, double* __restrict__ Dout, int64_t ld) {
+__global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __restrict__ pos_of, int64_t R, int64_t S,
+                              int64_t s0, int64_t ns, double* __restrict__ Cout, double* __restrict__ Dout, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n_sl = (ns + 7) / 8;  // s0 is a multiple of 8
   if (i >= R * n_sl) return;
   const int64_t r = i % R, sl = i / R;
   const int64_t slice = s0 / 8 + sl;
   const int64_t p = pos_of ? pos_of[r] : r;
-  // day of the record: last d with day_start[d] <= p
-  int64_t lo = 0, hi = n_days;
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (day_start[mid] <= p) lo = mid; else hi = mid;
-  }
-  const int64_t day = lo;
   const uint4 v = __ldg(&traj[slice * R + p]);
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -428,9 +437,8 @@ __global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __r
     if (s >= ns || s0 + s >= S) break;
     const uint32_t x = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
     const uint32_t cls = x >> kClsShift;
-    const bool finite = cls >= kClsPn;
-    Cout[r + ld * s] = (double)((x >> 13) & 1u);
-    Dout[r + ld * s] = finite ? (double)((int64_t)(x & 0x1FFFu) - day - 1) : __longlong_as_double(0x7FF0000000000000ll);
+    Cout[r + ld * s] = (cls == kClsA || cls >= kClsPn) ? 1.0 : 0.0;
+    Dout[r + ld * s] = (cls >= kClsPn) ? (double)((int)kCodeZero - (int)x) : __longlong_as_double(0x7FF0000000000000ll);
   }
 }
 
@@ -461,9 +469,10 @@ void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int grid) {
 
 void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,
                  int64_t R, int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld) {
+  (void)day_start; (void)n_days;
   const int64_t n = R * ((ns + 7) / 8);
   if (n <= 0) return;
-  k_fast_expand<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(traj, pos_of, day_start, n_days, R, S, s0, ns, Cout, Dout, ld);
+  k_fast_expand<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(traj, pos_of, R, S, s0, ns, Cout, Dout, ld);
 }
 
 void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld) {
