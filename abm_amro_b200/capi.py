@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libamro_b200.so")
+LIB_PATH = os.environ.get("AMRO_B200_LIB") or os.path.join(_PKG, "lib", "libamro_b200.so")  # env override: tuning variants
 
 AMRO_OK, AMRO_EINDEX, AMRO_ERUNTIME, AMRO_EINVAL, AMRO_ECUDA = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_REPLAY = 0, 1

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -210,26 +211,28 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const int cap = T->coresident[replay ? 1 : 0];
   if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
   // Teams of G CTAs per slice of 8 simulations; a CTA wants at least a few warps of records per day.
+  // Teams of G CTAs per GROUP of kGroup slices of 8 simulations; a CTA wants at least a few warps of records per day.
+  const int64_t n_groups = (n_slices + kGroup - 1) / kGroup;
   int teams, G;
-  if (n_slices >= cap) { teams = cap; G = 1; }
+  if (n_groups >= cap) { teams = cap; G = 1; }
   else {
-    teams = (int)n_slices;
-    G = (int)(cap / n_slices);
+    teams = (int)n_groups;
+    G = (int)(cap / n_groups);
     const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kFastThreads));
     G = (int)std::max<int64_t>(1, std::min<int64_t>(G, useful));
   }
   const bool by_team = !A->pressure_out;   // the pressure table is only kept per slice when it is exported
-  const int64_t n_sets = by_team ? teams : n_slices;
+  const int64_t n_sets = (by_team ? (int64_t)teams : n_groups) * kGroup;
   const int64_t ring = std::max<int64_t>(H.max_rows_per_day, 1);
 
   ensure_size(T->ws_pre, (size_t)(n_sets * 2 * ring));
   if (want_traj) ensure_size(T->ws_traj, (size_t)(n_slices * std::max<int64_t>(H.R, 1)));
   ensure_size(T->ws_pressure, (size_t)(n_sets * std::max<int64_t>(H.n_seg, 1) * 4));
   ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
-  ensure_size(T->ws_barrier, (size_t)teams);
+  ensure_size(T->ws_barrier, (size_t)teams * kGroup);
   ensure_size(T->ws_params, (size_t)(S_pad * 6));
   AMRO_CUDA(cudaMemsetAsync(T->ws_counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S_pad, st));
-  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * teams, st));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * teams * kGroup, st));
   AMRO_CUDA(cudaMemsetAsync(T->ws_params.p, 0, sizeof(double) * S_pad * 6, st));
   AMRO_CUDA(cudaMemcpy2DAsync(T->ws_params.p, S_pad * sizeof(double), in.params, in.p_ld * sizeof(double),
                               S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
@@ -264,6 +267,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.pressure = T->ws_pressure.p;
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
   f.team_barrier = T->ws_barrier.p; f.teams = teams; f.ctas_per_team = G; f.sets_by_team = by_team ? 1 : 0;
+  {
+    const char* e = std::getenv("AMRO_STAGGER_CYCLES");
+    const char* m = std::getenv("AMRO_STAGGER_MOD");
+    f.stagger_cycles = e ? std::atoi(e) : 0;
+    f.stagger_mod = m ? std::max(1, std::atoi(m)) : 6;
+  }
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));

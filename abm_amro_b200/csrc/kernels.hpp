@@ -54,8 +54,18 @@ void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64
 // ----------------------------------------------------------------------------------------------------
 constexpr int kSimsPerSlice = 8;
 constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-bit field: days and time_to_detect limits
-constexpr int kFastThreads = 128;
-constexpr int kFastMinBlocks = 6;          // CTAs per SM the register budget is sized for
+#ifndef AMRO_FAST_THREADS
+#define AMRO_FAST_THREADS 128
+#endif
+#ifndef AMRO_FAST_MINBLOCKS
+#define AMRO_FAST_MINBLOCKS 6
+#endif
+constexpr int kFastThreads = AMRO_FAST_THREADS;
+constexpr int kFastMinBlocks = AMRO_FAST_MINBLOCKS;   // CTAs per SM the register budget is sized for
+#ifndef AMRO_FAST_GROUP
+#define AMRO_FAST_GROUP 1
+#endif
+constexpr int kGroup = AMRO_FAST_GROUP;    // slices a team interleaves (hides the team barrier of one behind the other)
 constexpr int kTableSegs = 8;              // ward-day threshold tables resident in shared memory at once
 
 struct FastArgs {
@@ -86,15 +96,16 @@ struct FastArgs {
   const double* u_icol; const double* u_idet; int64_t ui_ld;
   double* p_out;                 // optional [R x S] (ld = R)
   // state
-  uint4* pre;                    // [n_sets][2][max_rows_per_day]: pre-step state of the current / next day
+  uint4* pre;                    // [n_sets][2][max_rows_per_day]: pre-step state of the current / next day (n_sets slices)
   uint4* traj;                   // nullptr, or [n_slices][R]: post-step state of every record
   uint32_t* pressure;            // [n_sets][n_seg][4]: 8 x 16-bit colonised counts per ward-day
   int32_t* counts_col;           // [n_days_out x S_pad8] ld = counts_ld  (zeroed by the caller)
   int32_t* counts_det;
   int64_t counts_ld;
-  unsigned int* team_barrier;    // [n_teams] zeroed by the caller
+  unsigned int* team_barrier;    // [n_teams * kGroup] zeroed by the caller
   int teams, ctas_per_team;
-  int sets_by_team;              // 1: pre / pressure indexed by team (reused slice after slice), 0: by slice
+  int sets_by_team;              // 1: pre / pressure indexed by (team, slot in group), reused group after group; 0: by slice
+  int stagger_cycles, stagger_mod;  // start offset of team t: stagger_cycles * (t % stagger_mod)
 };
 
 // Returns the number of CTAs of kFastThreads threads that can be co-resident (cooperative launch bound).

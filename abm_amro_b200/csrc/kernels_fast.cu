@@ -38,6 +38,14 @@
 #include "topology.hpp"
 
 namespace amro {
+#ifdef AMRO_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[8];   // development only: summed cycles of thread 0 of every CTA per phase
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_ADD(i) do { if (threadIdx.x == 0) { long long _n = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(i) do {} while (0)
+#endif
 namespace {
 
 constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 4, kNumCls = 5;
@@ -46,29 +54,17 @@ constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, k
 constexpr int kTabRow = 8 * (int)kNumCls + 1;  // entries per (ward-day, is_new): [sim][class], +1 pad against bank conflicts
 constexpr int kFlushEvery = 1024;              // row iterations between flushes of the 16-bit packed per-lane counters
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_inc(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Barrier among the CTAs of one team (the pattern of a cooperative-groups grid sync, on a per-team counter).
-// The cooperative launch guarantees the CTAs are co-resident.
-__device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, int ctas) {
-  __syncthreads();
-  if (ctas > 1) {
-    target += (unsigned)ctas;
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(ctr, 1u);
-      while ((int)(ld_acquire(ctr) - target) < 0) {}
-      __threadfence();
-    }
-    __syncthreads();
-  }
 }
 
 struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
@@ -107,14 +103,12 @@ struct Shared<false> {
   // [(ward-day*2 + is_new)*kTabRow + sim*5 + class]
   uint2 tab[kTableSegs * 2 * kTabRow];
   ulonglong2 full[kTableSegs * 2 * kTabRow];  // the 33-bit thresholds {T(P), T(P*rho)}, read only on a tie
-  SliceParams par;
-  int cnt[16];
+  SliceParams par[kGroup];
 };
 template <>
 struct Shared<true> {
   double P[kTableSegs * 2][3][8];
-  SliceParams par;
-  int cnt[16];
+  SliceParams par[kGroup];
 };
 
 // Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
@@ -180,11 +174,11 @@ __device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2*
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
-__device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, const FastArgs& a, const uint4 pre, int row, int h,
+__device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
                                                     int64_t orig, int64_t sim0, bool flag) {
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w};
   uint32_t postw[4] = {0, 0, 0, 0};
-  const double* rho_tab = h ? sh.par.rho_i : sh.par.rho_h;
+  const double* rho_tab = h ? par.rho_i : par.rho_h;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
@@ -206,45 +200,242 @@ __device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, cons
 
 }  // namespace
 
+// Everything a CTA needs to step one slice (8 simulations).  A team interleaves kGroup slices: it works on one while the
+// barrier of the other completes, so no CTA idles waiting for its team mates.
+struct SliceCtx {
+  uint4* pre;
+  uint4* traj;
+  uint32_t* press;
+  unsigned* bar;
+  unsigned bar_target;
+  uint32_t gslice;
+  int64_t sim0;
+  bool valid;
+};
+
+// ---- one day of one slice: the part of the day's records that belongs to this CTA (abm_wards.cpp:384-407) ----------
+template <bool REPLAY>
+__device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& a, const SliceCtx& c, int pslot, int64_t d,
+                                            int rank, int G) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ring = a.max_rows_per_day;
+  const int64_t da = a.day_start[d], db = a.day_start[d + 1];
+  const uint32_t n = (uint32_t)(db - da), per = ((n + G - 1) / G + 31) / 32 * 32;
+  const uint32_t lo = min(n, (uint32_t)rank * per), hi = min(n, lo + per);   // this CTA's records, day-relative
+  const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
+  const int64_t seg0 = a.day_seg_start[d];
+  const uint4* cur = c.pre + (d & 1) * ring;
+  uint4* nxt = c.pre + ((d + 1) & 1) * ring;
+  uint32_t* press = c.press;
+  const uint32_t* m_info = a.meta_info + da;
+  const uint32_t* m_next = a.meta_next + da;
+  const uint32_t* m_nseg = a.meta_nseg + da;
+  const SliceParams& par = sh.par[pslot];
+  uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
+  int since_flush = 0;
+
+  // per-day totals (abm_wards.cpp:445-459 fused): warp-reduce the packed per-lane counters, then one RED per
+  // (simulation, metric) and warp
+  auto flush_counts = [&]() {
+    uint32_t tot[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tot[j] = __reduce_add_sync(0xFFFFFFFFu, ccol[j]);
+      tot[4 + j] = __reduce_add_sync(0xFFFFFFFFu, cdet[j]);
+      ccol[j] = 0;
+      cdet[j] = 0;
+    }
+    if (lane < 16 && d < a.counts_ld) {
+      uint32_t w = tot[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) w = ((lane >> 1) == j) ? tot[j] : w;
+      const uint32_t v = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+      int32_t* dst = (lane < 8) ? a.counts_col : a.counts_det;
+      if (v != 0 && dst) atomicAdd(&dst[d + a.counts_ld * (c.sim0 + (lane & 7))], (int)v);
+    }
+    since_flush = 0;
+  };
+
+  PHASE_T0();
+  if (lo < hi) {
+    const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
+    const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
+    for (int64_t sb = seg_first; sb <= seg_last; sb += kTableSegs) {
+      const int64_t se = min(seg_last + 1, sb + kTableSegs);
+      // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
+      __syncthreads();
+      for (int t = tid; t < (int)(se - sb) * 16; t += kFastThreads) {
+        const int si = t >> 4, h = (t >> 3) & 1, k = t & 7;
+        const int64_t seg = sb + si;
+        const uint32_t pk = __ldcg(&press[seg * 4 + (k >> 1)]);
+        const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
+        // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
+        const double F = __dmul_rn(__ddiv_rn(par.beta[k], a.seg_N[seg]), (double)cnt);
+        const bool flag = h ? test_a : test_h;
+        const double rho = h ? par.rho_i[k] : par.rho_h[k];
+        double P[3];
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, par.alpha[k], par.alpha2[k], par.gamma[k]);
+        if constexpr (REPLAY) {
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc) sh.P[si * 2 + h][pc][k] = P[pc];
+        } else {
+          const int row = (si * 2 + h) * kTabRow + k * (int)kNumCls;
+#pragma unroll
+          for (uint32_t cls = 0; cls < kNumCls; ++cls) {
+            const double p = P[prob_class(cls)];
+            const uint64_t T = threshold33(p);
+            // U and A are tested today (if it is a testing day); a running countdown is not re-tested
+            const uint64_t TD = (flag && cls <= kClsA) ? threshold33(__dmul_rn(clamp01(p), rho)) : 0ull;
+            sh.tab[row + cls] = make_uint2((uint32_t)(T >> 17) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
+                                           (uint32_t)(TD >> 17) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
+            sh.full[row + cls] = make_ulonglong2(T, TD);
+          }
+        }
+      }
+      __syncthreads();
+      PHASE_ADD(0);  // table
+      // ---- the records of those ward-days that belong to this CTA ----------------------------------------
+      const uint32_t rb = max(lo, (uint32_t)(a.seg_row_start[sb] - da)), re = min(hi, (uint32_t)(a.seg_row_start[se] - da));
+      // software pipeline: the loads of the next iteration are in flight while this one computes
+      uint32_t n_info = 0, n_next = kNone, n_nseg = kNone;
+      uint4 n_prev = make_uint4(0u, 0u, 0u, 0u);
+      if (rb + tid < re) {
+        n_info = __ldg(&m_info[rb + tid]); n_next = __ldg(&m_next[rb + tid]); n_nseg = __ldg(&m_nseg[rb + tid]);
+        n_prev = __ldcg(&cur[rb + tid]);
+      }
+      for (uint32_t base = rb; base < re; base += kFastThreads) {  // CTA-uniform trip count (warp collectives below)
+        const uint32_t i = base + tid;
+        const uint32_t info = n_info, next = n_next;
+        uint4 prev = n_prev;
+        uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
+        uint32_t nseg = i < re ? n_nseg : kNone;
+        if (i + kFastThreads < re) {
+          n_info = __ldg(&m_info[i + kFastThreads]); n_next = __ldg(&m_next[i + kFastThreads]);
+          n_nseg = __ldg(&m_nseg[i + kFastThreads]); n_prev = __ldcg(&cur[i + kFastThreads]);
+        }
+        if (i < re) {
+          const int64_t p = da + i;
+          const int64_t orig = a.orig_row ? a.orig_row[p] : p;
+          const int h = (int)(info >> kInfoHShift);
+          const int row = ((int)((int64_t)(info & kInfoSegMask) + seg0 - sb)) * 2 + h;
+          if (((info >> kInfoSrcShift) & 3u) == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
+          uint4 post;
+          if constexpr (REPLAY) post = step_record_replay(sh, par, a, prev, row, h, orig, c.sim0, h ? test_a : test_h);
+          else post = step_record(sh.tab + row * kTabRow, sh.full + row * kTabRow, a, prev, (uint32_t)orig,
+                                  (uint32_t)((uint64_t)orig >> 32), c.gslice);
+          if (next != kNone) __stcg(&nxt[next], post);     // :402-407 the successor starts from this state
+          if (c.traj) __stcg(&c.traj[p], post);
+          const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            detw[j] = (pw[j] >> 15) & 0x00010001u;                       // class 4: D <= 0
+            colw[j] = ((pw[j] >> 13) & 0x00010001u) | detw[j];           // classes 1, 3 (bit 13) and 4
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ccol[j] += colw[j]; cdet[j] += detw[j]; }
+
+        // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
+        // Most lanes of a warp feed the same ward-day: they are summed with a warp reduction and added by one
+        // lane; the rest (transfers) add on their own.
+        const bool has = nseg != kNone;
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, has);
+        if (hm) {
+          const int leader = __ffs(hm) - 1;
+          const uint32_t lseg = __shfl_sync(0xFFFFFFFFu, nseg, leader);
+          const bool mine = nseg == lseg;
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = __reduce_add_sync(0xFFFFFFFFu, mine ? colw[j] : 0u);
+          if (has && (lane == leader || !mine)) {
+            uint32_t* dst = press + (int64_t)nseg * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red_add(dst + j, mine ? v[j] : colw[j]);
+          }
+        }
+        if (++since_flush == kFlushEvery) flush_counts();
+      }
+      PHASE_ADD(1);  // records (thread 0's view)
+    }
+  }
+  flush_counts();
+  PHASE_ADD(2);  // totals
+}
+
+// split-phase team barrier: arrive when this CTA's writes of the phase are done, wait before reading the team's
+__device__ __forceinline__ void team_arrive(SliceCtx& c, int G) {
+  __syncthreads();
+  if (G > 1) {
+    c.bar_target += (unsigned)G;
+    // release: the CTA's state / pressure writes are ordered before thread 0's increment by the bar.sync above
+    if (threadIdx.x == 0) red_release_inc(c.bar);
+  }
+}
+__device__ __forceinline__ void team_wait(const SliceCtx& c, int G) {
+  if (G > 1) {
+    // acquire: poll relaxed, fence once; what another CTA wrote is read afterwards with ld.cg / atomics (L2)
+    if (threadIdx.x == 0) {
+      while ((int)(ld_relaxed(c.bar) - c.bar_target) < 0) {}
+      fence_acquire();
+    }
+    __syncthreads();
+  }
+}
+
 template <bool REPLAY>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const __grid_constant__ FastArgs a) {
   __shared__ Shared<REPLAY> sh;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int team = blockIdx.x / a.ctas_per_team, rank = blockIdx.x % a.ctas_per_team;
   if (team >= a.teams) return;
-  unsigned bar_target = 0;
-  unsigned* bar = a.team_barrier + team;
   const int G = a.ctas_per_team;
   const int64_t ring = a.max_rows_per_day;
+  const int64_t n_groups = (a.n_slices + kGroup - 1) / kGroup;
+  unsigned targets[kGroup];
+#pragma unroll
+  for (int s = 0; s < kGroup; ++s) targets[s] = 0;
 
-  if (tid < 16) sh.cnt[tid] = 0;
+  for (int64_t group = team; group < n_groups; group += a.teams) {
+    SliceCtx ctx[kGroup];
+#pragma unroll
+    for (int s = 0; s < kGroup; ++s) {
+      const int64_t slice = group * kGroup + s;
+      const int64_t set = (a.sets_by_team ? (int64_t)team : group) * kGroup + s;
+      ctx[s].valid = slice < a.n_slices;
+      ctx[s].pre = a.pre + set * 2 * ring;
+      ctx[s].traj = (a.traj && ctx[s].valid) ? a.traj + slice * a.R : nullptr;
+      ctx[s].press = a.pressure + set * a.n_seg * 4;
+      ctx[s].bar = a.team_barrier + team * kGroup + s;
+      ctx[s].bar_target = targets[s];
+      ctx[s].gslice = (uint32_t)((a.sim_offset >> 3) + (uint64_t)slice);
+      ctx[s].sim0 = slice * 8;
+    }
 
-  for (int64_t slice = team; slice < a.n_slices; slice += a.teams) {
-    const int64_t set = a.sets_by_team ? (int64_t)team : slice;
-    uint4* pre = a.pre + set * 2 * ring;
-    uint4* traj = a.traj ? a.traj + slice * a.R : nullptr;
-    uint32_t* press = a.pressure + set * a.n_seg * 4;
-    const uint32_t gslice = (uint32_t)((a.sim_offset >> 3) + (uint64_t)slice);
-    const int64_t sim0 = slice * 8;
-
-    // ---- slice setup: parameters to shared memory, pressure zeroed -----------------------------------------
+    // ---- group setup: parameters to shared memory, pressure zeroed -----------------------------------------
     __syncthreads();
-    if (tid < 48) {
-      const int c = tid >> 3, k = tid & 7;
-      const double v = a.params[(sim0 + k) + a.p_ld * c];
-      double* dst = c == 0 ? sh.par.alpha : c == 1 ? sh.par.beta : c == 2 ? sh.par.gamma : c == 3 ? sh.par.rho_h
-                   : c == 4 ? sh.par.alpha2 : sh.par.rho_i;
+    for (int t = tid; t < 48 * kGroup; t += kFastThreads) {
+      const int s = t / 48, c = (t % 48) >> 3, k = t & 7;
+      if (!ctx[s].valid) continue;
+      const double v = a.params[(ctx[s].sim0 + k) + a.p_ld * c];
+      SliceParams& par = sh.par[s];
+      double* dst = c == 0 ? par.alpha : c == 1 ? par.beta : c == 2 ? par.gamma : c == 3 ? par.rho_h : c == 4 ? par.alpha2 : par.rho_i;
       dst[k] = v;
     }
-    {
+#pragma unroll
+    for (int s = 0; s < kGroup; ++s) {
+      if (!ctx[s].valid) continue;
       const int64_t n = a.n_seg * 4, per = (n + G - 1) / G;
       const int64_t lo = rank * per, hi = min(n, lo + per);
-      for (int64_t i = lo + tid; i < hi; i += kFastThreads) __stcg(&press[i], 0u);
+      for (int64_t i = lo + tid; i < hi; i += kFastThreads) __stcg(&ctx[s].press[i], 0u);
+      team_arrive(ctx[s], G);
     }
-    team_barrier(bar, bar_target, G);
 
     // ---- initial state (abm_wards.cpp:363-372) into the day-0 buffer -----------------------------------------
-    {
+#pragma unroll
+    for (int s = 0; s < kGroup; ++s) {
+      if (!ctx[s].valid) continue;
+      team_wait(ctx[s], G);
       const int64_t n = a.n_init, per = ((n + G - 1) / G + 31) / 32 * 32;
       const int64_t lo = rank * per, hi = min(n, lo + per);
       for (int64_t r = lo + tid; r < hi; r += kFastThreads) {
@@ -253,7 +444,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const __g
         uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int64_t sim = sim0 + k;
+          const int64_t sim = ctx[s].sim0 + k;
           bool c0 = false, d0 = false;
           if (sim < a.S) {
             const double pc = a.icp[r * a.icp_rs + sim * a.icp_cs], pd = a.idp[r * a.idp_rs + sim * a.idp_cs];
@@ -272,149 +463,34 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const __g
           w[k >> 1] |= code << (16 * (k & 1));
           cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
         }
-        __stcg(&pre[slot], make_uint4(w[0], w[1], w[2], w[3]));
+        __stcg(&ctx[s].pre[slot], make_uint4(w[0], w[1], w[2], w[3]));
         const uint32_t iseg = a.init_seg[r];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&press[(int64_t)iseg * 4 + j], cw[j]);
+        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&ctx[s].press[(int64_t)iseg * 4 + j], cw[j]);
+      }
+      team_arrive(ctx[s], G);
+    }
+
+    // ---- day loop (abm_wards.cpp:381): the group's slices alternate, each waits for ITS team barrier of the
+    // previous phase only when it is about to need it ------------------------------------------------------
+    for (int64_t d = 0; d < a.n_days; ++d) {
+#pragma unroll
+      for (int s = 0; s < kGroup; ++s) {
+        if (!ctx[s].valid) continue;
+        { PHASE_T0();
+        team_wait(ctx[s], G);
+        PHASE_ADD(3); }  // team barrier wait
+        process_day<REPLAY>(sh, a, ctx[s], s, d, rank, G);
+        PHASE_T0();
+        team_arrive(ctx[s], G);
+        PHASE_ADD(4);  // arrive
       }
     }
-    team_barrier(bar, bar_target, G);
-
-    // ---- day loop (abm_wards.cpp:381) -------------------------------------------------------------------
-    for (int64_t d = 0; d < a.n_days; ++d) {
-      const int64_t da = a.day_start[d], db = a.day_start[d + 1];
-      const uint32_t n = (uint32_t)(db - da), per = ((n + G - 1) / G + 31) / 32 * 32;
-      const uint32_t lo = min(n, (uint32_t)rank * per), hi = min(n, lo + per);   // this CTA's records, day-relative
-      const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
-      const int64_t seg0 = a.day_seg_start[d];
-      const uint4* cur = pre + (d & 1) * ring;
-      uint4* nxt = pre + ((d + 1) & 1) * ring;
-      const uint32_t* m_info = a.meta_info + da;
-      const uint32_t* m_next = a.meta_next + da;
-      const uint32_t* m_nseg = a.meta_nseg + da;
-      uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
-      int since_flush = 0;
-
-      auto flush_counts = [&]() {
+    // the scratch of this group is reused by the next one: wait until the whole team is done with it
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, ccol[j]);
-          const uint32_t e = __reduce_add_sync(0xFFFFFFFFu, cdet[j]);
-          if (lane == 0) {
-            if (c & 0xFFFFu) atomicAdd(&sh.cnt[2 * j], (int)(c & 0xFFFFu));
-            if (c >> 16) atomicAdd(&sh.cnt[2 * j + 1], (int)(c >> 16));
-            if (e & 0xFFFFu) atomicAdd(&sh.cnt[8 + 2 * j], (int)(e & 0xFFFFu));
-            if (e >> 16) atomicAdd(&sh.cnt[8 + 2 * j + 1], (int)(e >> 16));
-          }
-          ccol[j] = 0;
-          cdet[j] = 0;
-        }
-        since_flush = 0;
-      };
-
-      if (lo < hi) {
-        const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
-        const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
-        for (int64_t sb = seg_first; sb <= seg_last; sb += kTableSegs) {
-          const int64_t se = min(seg_last + 1, sb + kTableSegs);
-          // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
-          __syncthreads();
-          for (int t = tid; t < (int)(se - sb) * 16; t += kFastThreads) {
-            const int si = t >> 4, h = (t >> 3) & 1, k = t & 7;
-            const int64_t seg = sb + si;
-            const uint32_t pk = __ldcg(&press[seg * 4 + (k >> 1)]);
-            const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
-            // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
-            const double F = __dmul_rn(__ddiv_rn(sh.par.beta[k], a.seg_N[seg]), (double)cnt);
-            const bool flag = h ? test_a : test_h;
-            const double rho = h ? sh.par.rho_i[k] : sh.par.rho_h[k];
-            double P[3];
-#pragma unroll
-            for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, sh.par.alpha[k], sh.par.alpha2[k], sh.par.gamma[k]);
-            if constexpr (REPLAY) {
-#pragma unroll
-              for (int pc = 0; pc < 3; ++pc) sh.P[si * 2 + h][pc][k] = P[pc];
-            } else {
-              const int row = (si * 2 + h) * kTabRow + k * (int)kNumCls;
-#pragma unroll
-              for (uint32_t cls = 0; cls < kNumCls; ++cls) {
-                const double p = P[prob_class(cls)];
-                const uint64_t T = threshold33(p);
-                // U and A are tested today (if it is a testing day); a running countdown is not re-tested
-                const uint64_t TD = (flag && cls <= kClsA) ? threshold33(__dmul_rn(clamp01(p), rho)) : 0ull;
-                sh.tab[row + cls] = make_uint2((uint32_t)(T >> 17) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
-                                               (uint32_t)(TD >> 17) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
-                sh.full[row + cls] = make_ulonglong2(T, TD);
-              }
-            }
-          }
-          __syncthreads();
-          // ---- the records of those ward-days that belong to this CTA ----------------------------------------
-          const uint32_t rb = max(lo, (uint32_t)(a.seg_row_start[sb] - da)), re = min(hi, (uint32_t)(a.seg_row_start[se] - da));
-          for (uint32_t base = rb; base < re; base += kFastThreads) {  // CTA-uniform trip count (warp collectives below)
-            const uint32_t i = base + tid;
-            uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
-            uint32_t nseg = kNone;
-            if (i < re) {
-              const uint32_t info = __ldg(&m_info[i]);
-              const uint32_t next = __ldg(&m_next[i]);
-              nseg = __ldg(&m_nseg[i]);
-              uint4 prev = __ldcg(&cur[i]);
-              const int64_t p = da + i;
-              const int64_t orig = a.orig_row ? a.orig_row[p] : p;
-              const int h = (int)(info >> kInfoHShift);
-              const int row = ((int)((int64_t)(info & kInfoSegMask) + seg0 - sb)) * 2 + h;
-              if (((info >> kInfoSrcShift) & 3u) == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
-              uint4 post;
-              if constexpr (REPLAY) post = step_record_replay(sh, a, prev, row, h, orig, sim0, h ? test_a : test_h);
-              else post = step_record(sh.tab + row * kTabRow, sh.full + row * kTabRow, a, prev, (uint32_t)orig,
-                                      (uint32_t)((uint64_t)orig >> 32), gslice);
-              if (next != kNone) __stcg(&nxt[next], post);     // :402-407 the successor starts from this state
-              if (traj) __stcg(&traj[p], post);
-              const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                detw[j] = (pw[j] >> 15) & 0x00010001u;                       // class 4: D <= 0
-                colw[j] = ((pw[j] >> 13) & 0x00010001u) | detw[j];           // classes 1, 3 (bit 13) and 4
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { ccol[j] += colw[j]; cdet[j] += detw[j]; }
-
-            // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
-            // Most lanes of a warp feed the same ward-day: they are summed with a warp reduction and added by one
-            // lane; the rest (transfers) add on their own.
-            const bool has = nseg != kNone;
-            const unsigned hm = __ballot_sync(0xFFFFFFFFu, has);
-            if (hm) {
-              const int leader = __ffs(hm) - 1;
-              const uint32_t lseg = __shfl_sync(0xFFFFFFFFu, nseg, leader);
-              const bool mine = nseg == lseg;
-              uint32_t v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = __reduce_add_sync(0xFFFFFFFFu, mine ? colw[j] : 0u);
-              if (has && (lane == leader || !mine)) {
-                uint32_t* dst = press + (int64_t)nseg * 4;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) red_add(dst + j, mine ? v[j] : colw[j]);
-              }
-            }
-            if (++since_flush == kFlushEvery) flush_counts();
-          }
-        }
-      }
-      // ---- per-day totals of this CTA (abm_wards.cpp:445-459 fused) -------------------------------------------
-      flush_counts();
-      __syncthreads();
-      if (tid < 16) {
-        const int v = sh.cnt[tid];
-        if (v != 0 && d < a.counts_ld) {
-          int32_t* dst = (tid < 8) ? a.counts_col : a.counts_det;
-          if (dst) atomicAdd(&dst[d + a.counts_ld * (sim0 + (tid & 7))], v);
-        }
-        sh.cnt[tid] = 0;
-      }
-      team_barrier(bar, bar_target, G);
+    for (int s = 0; s < kGroup; ++s) {
+      if (ctx[s].valid) team_wait(ctx[s], G);
+      targets[s] = ctx[s].bar_target;
     }
   }
 }
@@ -452,6 +528,13 @@ __global__ void k_fast_export_pressure(const uint32_t* __restrict__ pressure, in
   out[seg + ld * s] = (int32_t)((w >> (16 * (k & 1))) & 0xFFFFu);
 }
 }  // namespace
+
+#ifdef AMRO_PROFILE_PHASES
+extern "C" void amro_debug_phase_cycles(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+}
+#endif
 
 int fast_max_coresident_ctas(int device, bool replay) {
   int per_sm = 0, sms = 0;
