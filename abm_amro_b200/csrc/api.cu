@@ -75,8 +75,8 @@ struct amro_topology {
   DevBuf<uint4> ws_pre, ws_traj;
   DevBuf<uint32_t> ws_pressure;
   DevBuf<int32_t> ws_counts;
-  DevBuf<unsigned int> ws_barrier;
   DevBuf<double> ws_params;
+  DevBuf<unsigned int> ws_barrier;
 
   void ensure_general() {
     if (general_ready) return;
@@ -138,8 +138,6 @@ int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_co
         t->meta_nseg.upload(H.meta_nseg.data(), H.meta_nseg.size());
         t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
         t->init_slot.upload(H.init_slot.data(), H.init_slot.size());
-        t->coresident[0] = fast_max_coresident_ctas(device, false);
-        t->coresident[1] = fast_max_coresident_ctas(device, true);
       }
       AMRO_CUDA(cudaStreamSynchronize(0));
     }
@@ -208,31 +206,31 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
   const int64_t S = A->n_sims, S_pad = (S + 7) / 8 * 8, n_slices = S_pad / 8;
   const bool want_traj = A->keep_trajectory || A->state_out;
-  const int cap = T->coresident[replay ? 1 : 0];
-  if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
-  // Teams of G CTAs per slice of 8 simulations; a CTA wants at least a few warps of records per day.
-  // Teams of G CTAs per GROUP of kGroup slices of 8 simulations; a CTA wants at least a few warps of records per day.
-  const int64_t n_groups = (n_slices + kGroup - 1) / kGroup;
-  int teams, G;
-  if (n_groups >= cap) { teams = cap; G = 1; }
-  else {
-    teams = (int)n_groups;
-    G = (int)(cap / n_groups);
-    const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kFastThreads));
-    G = (int)std::max<int64_t>(1, std::min<int64_t>(G, useful));
+  // Launch shape (kernels_fast.cu): WIDE when there is about a slice per SM or more, else TEAMs of G CTAs per slice.
+  int sms = 0;
+  AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
+  int shape = (n_slices * 4 >= (int64_t)sms * 3) ? kShapeWide : kShapeTeam;
+  if (const char* e = std::getenv("AMRO_FAST_SHAPE")) shape = (e[0] == 'w') ? kShapeWide : kShapeTeam;
+  int G = 1, table_segs;
+  if (shape == kShapeWide) {
+    table_segs = (int)std::max<int64_t>(1, std::min<int64_t>(H.max_segs_per_day, kWideTableSegsMax));
+  } else {
+    table_segs = (int)std::max<int64_t>(1, std::min<int64_t>(H.max_segs_per_day, kTeamTableSegs));
+    const int cap = fast_max_coresident_ctas(T->device, replay, shape, table_segs);
+    if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
+    const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kTeamThreads));  // a CTA wants a few warps of records
+    G = (int)std::max<int64_t>(1, std::min<int64_t>(cap / std::max<int64_t>(n_slices, 1), useful));
+    if (n_slices > cap) G = 1;
   }
-  const bool by_team = !A->pressure_out;   // the pressure table is only kept per slice when it is exported
-  const int64_t n_sets = (by_team ? (int64_t)teams : n_groups) * kGroup;
+  if (const char* e = std::getenv("AMRO_FAST_G")) G = std::max(1, std::atoi(e));
   const int64_t ring = std::max<int64_t>(H.max_rows_per_day, 1);
 
-  ensure_size(T->ws_pre, (size_t)(n_sets * 2 * ring));
+  ensure_size(T->ws_pre, (size_t)(n_slices * 2 * ring));
   if (want_traj) ensure_size(T->ws_traj, (size_t)(n_slices * std::max<int64_t>(H.R, 1)));
-  ensure_size(T->ws_pressure, (size_t)(n_sets * std::max<int64_t>(H.n_seg, 1) * 4));
+  ensure_size(T->ws_pressure, (size_t)(n_slices * std::max<int64_t>(H.n_seg, 1) * 4));
   ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
-  ensure_size(T->ws_barrier, (size_t)teams * kGroup);
   ensure_size(T->ws_params, (size_t)(S_pad * 6));
   AMRO_CUDA(cudaMemsetAsync(T->ws_counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S_pad, st));
-  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * teams * kGroup, st));
   AMRO_CUDA(cudaMemsetAsync(T->ws_params.p, 0, sizeof(double) * S_pad * 6, st));
   AMRO_CUDA(cudaMemcpy2DAsync(T->ws_params.p, S_pad * sizeof(double), in.params, in.p_ld * sizeof(double),
                               S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
@@ -266,17 +264,13 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.pre = T->ws_pre.p; f.traj = want_traj ? T->ws_traj.p : nullptr;
   f.pressure = T->ws_pressure.p;
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
-  f.team_barrier = T->ws_barrier.p; f.teams = teams; f.ctas_per_team = G; f.sets_by_team = by_team ? 1 : 0;
-  {
-    const char* e = std::getenv("AMRO_STAGGER_CYCLES");
-    const char* m = std::getenv("AMRO_STAGGER_MOD");
-    f.stagger_cycles = e ? std::atoi(e) : 0;
-    f.stagger_mod = m ? std::max(1, std::atoi(m)) : 6;
-  }
+  ensure_size(T->ws_barrier, (size_t)n_slices);
+  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_slices, st));
+  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.table_segs = table_segs;
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
-  fast_launch(st, f, replay, teams * G);
+  fast_launch(st, f, replay, shape, (int)(n_slices * G));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
 

@@ -54,19 +54,21 @@ void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64
 // ----------------------------------------------------------------------------------------------------
 constexpr int kSimsPerSlice = 8;
 constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-bit field: days and time_to_detect limits
-#ifndef AMRO_FAST_THREADS
-#define AMRO_FAST_THREADS 128
+#ifndef AMRO_WIDE_THREADS
+#define AMRO_WIDE_THREADS 768
 #endif
-#ifndef AMRO_FAST_MINBLOCKS
-#define AMRO_FAST_MINBLOCKS 6
+#ifndef AMRO_TEAM_THREADS
+#define AMRO_TEAM_THREADS 128
 #endif
-constexpr int kFastThreads = AMRO_FAST_THREADS;
-constexpr int kFastMinBlocks = AMRO_FAST_MINBLOCKS;   // CTAs per SM the register budget is sized for
-#ifndef AMRO_FAST_GROUP
-#define AMRO_FAST_GROUP 1
+#ifndef AMRO_TEAM_MINBLOCKS
+#define AMRO_TEAM_MINBLOCKS 6
 #endif
-constexpr int kGroup = AMRO_FAST_GROUP;    // slices a team interleaves (hides the team barrier of one behind the other)
-constexpr int kTableSegs = 8;              // ward-day threshold tables resident in shared memory at once
+constexpr int kShapeWide = 0, kShapeTeam = 1;
+constexpr int kWideThreads = AMRO_WIDE_THREADS;     // one CTA per SM
+constexpr int kTeamThreads = AMRO_TEAM_THREADS;
+constexpr int kTeamMinBlocks = AMRO_TEAM_MINBLOCKS; // CTAs per SM the team shape's register budget is sized for
+constexpr int kTeamTableSegs = 8;                   // ward-day tables resident in shared memory at once (team shape)
+constexpr int kWideTableSegsMax = 96;               // ... wide shape (a whole day's wards when they fit)
 
 struct FastArgs {
   // topology (device)
@@ -96,21 +98,22 @@ struct FastArgs {
   const double* u_icol; const double* u_idet; int64_t ui_ld;
   double* p_out;                 // optional [R x S] (ld = R)
   // state
-  uint4* pre;                    // [n_sets][2][max_rows_per_day]: pre-step state of the current / next day (n_sets slices)
+  uint4* pre;                    // [n_slices][2][max_rows_per_day]: pre-step state of the current / next day
   uint4* traj;                   // nullptr, or [n_slices][R]: post-step state of every record
-  uint32_t* pressure;            // [n_sets][n_seg][4]: 8 x 16-bit colonised counts per ward-day
+  uint32_t* pressure;            // [n_slices][n_seg][4]: 8 x 16-bit colonised counts per ward-day
   int32_t* counts_col;           // [n_days_out x S_pad8] ld = counts_ld  (zeroed by the caller)
   int32_t* counts_det;
   int64_t counts_ld;
-  unsigned int* team_barrier;    // [n_teams * kGroup] zeroed by the caller
-  int teams, ctas_per_team;
-  int sets_by_team;              // 1: pre / pressure indexed by (team, slot in group), reused group after group; 0: by slice
-  int stagger_cycles, stagger_mod;  // start offset of team t: stagger_cycles * (t % stagger_mod)
+  unsigned int* team_barrier;    // [n_slices] zeroed by the caller
+  int ctas_per_team;             // CTAs that share a slice (1 = no inter-CTA barrier)
+  int table_segs;                // ward-day tables resident in shared memory at once
 };
 
-// Returns the number of CTAs of kFastThreads threads that can be co-resident (cooperative launch bound).
-int fast_max_coresident_ctas(int device, bool replay);
-void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int grid);
+size_t fast_shared_bytes(bool replay, int table_segs);
+int fast_threads(int shape);
+// CTAs of the given launch shape that can be co-resident (bound of a cooperative launch)
+int fast_max_coresident_ctas(int device, bool replay, int shape, int table_segs);
+void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid);
 
 // Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run
 void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,

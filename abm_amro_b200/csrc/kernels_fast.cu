@@ -54,15 +54,6 @@ constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, k
 constexpr int kTabRow = 8 * (int)kNumCls + 1;  // entries per (ward-day, is_new): [sim][class], +1 pad against bank conflicts
 constexpr int kFlushEvery = 1024;              // row iterations between flushes of the 16-bit packed per-lane counters
 
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_inc(unsigned* p) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -95,21 +86,36 @@ __device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) 
   return 1u;                                            // pending / detected: D -= 1
 }
 
+// Shared memory (dynamic): the threshold / delta tables of up to a.table_segs ward-days, then the slice parameters.
+//   free-running: tab  uint2[table_segs*2*kTabRow]       x = (T(P) >> 17) << 16 | delta(not tested positive),
+//                                                         y = (T(P*rho) >> 17) << 16 | delta(tested positive)
+//                      at [(ward-day*2 + is_new)*kTabRow + sim*5 + class]
+//                 full ulonglong2[same]                   the 33-bit thresholds {T(P), T(P*rho)}, read only on a tie
+//   replay:       P    double[table_segs*2][3][8]         the transition probabilities themselves
+struct SharedView {
+  uint2* tab;
+  ulonglong2* full;
+  double* P;
+  SliceParams* par;
+};
+__host__ __device__ inline size_t fast_smem_bytes(bool replay, int table_segs) {
+  const size_t rows = (size_t)table_segs * 2;
+  return (replay ? rows * 24 * sizeof(double) : rows * kTabRow * (sizeof(uint2) + sizeof(ulonglong2))) + sizeof(SliceParams) + 16;
+}
 template <bool REPLAY>
-struct Shared;
-template <>
-struct Shared<false> {
-  // x = (T(P) >> 17) << 16 | delta(not tested positive), y = (T(P*rho) >> 17) << 16 | delta(tested positive), at
-  // [(ward-day*2 + is_new)*kTabRow + sim*5 + class]
-  uint2 tab[kTableSegs * 2 * kTabRow];
-  ulonglong2 full[kTableSegs * 2 * kTabRow];  // the 33-bit thresholds {T(P), T(P*rho)}, read only on a tie
-  SliceParams par[kGroup];
-};
-template <>
-struct Shared<true> {
-  double P[kTableSegs * 2][3][8];
-  SliceParams par[kGroup];
-};
+__device__ __forceinline__ SharedView carve_shared(unsigned char* raw, int table_segs) {
+  SharedView v{};
+  const size_t rows = (size_t)table_segs * 2;
+  if constexpr (REPLAY) {
+    v.P = reinterpret_cast<double*>(raw);
+    v.par = reinterpret_cast<SliceParams*>(raw + rows * 24 * sizeof(double));
+  } else {
+    v.full = reinterpret_cast<ulonglong2*>(raw);
+    v.tab = reinterpret_cast<uint2*>(raw + rows * kTabRow * sizeof(ulonglong2));
+    v.par = reinterpret_cast<SliceParams*>(raw + rows * kTabRow * (sizeof(ulonglong2) + sizeof(uint2)));
+  }
+  return v;
+}
 
 // Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
 __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t kx) {
@@ -174,7 +180,7 @@ __device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2*
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
-__device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
+__device__ __forceinline__ uint4 step_record_replay(const SharedView& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
                                                     int64_t orig, int64_t sim0, bool flag) {
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w};
   uint32_t postw[4] = {0, 0, 0, 0};
@@ -184,7 +190,7 @@ __device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, cons
     const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
     const uint32_t cls = v >> kClsShift;
     const int64_t sim = sim0 + k;
-    const double P = sh.P[row][prob_class(cls)][k];
+    const double P = sh.P[(row * 3 + prob_class(cls)) * 8 + k];
     bool col = false, hit = false;
     if (sim < a.S) {
       if (a.p_out) a.p_out[orig + a.R * sim] = P;
@@ -200,23 +206,18 @@ __device__ __forceinline__ uint4 step_record_replay(const Shared<true>& sh, cons
 
 }  // namespace
 
-// Everything a CTA needs to step one slice (8 simulations).  A team interleaves kGroup slices: it works on one while the
-// barrier of the other completes, so no CTA idles waiting for its team mates.
+// Everything a CTA needs to step its slice (8 simulations).
 struct SliceCtx {
   uint4* pre;
   uint4* traj;
   uint32_t* press;
-  unsigned* bar;
-  unsigned bar_target;
   uint32_t gslice;
   int64_t sim0;
-  bool valid;
 };
 
 // ---- one day of one slice: the part of the day's records that belongs to this CTA (abm_wards.cpp:384-407) ----------
-template <bool REPLAY>
-__device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& a, const SliceCtx& c, int pslot, int64_t d,
-                                            int rank, int G) {
+template <bool REPLAY, int THREADS>
+__device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs& a, const SliceCtx& c, int64_t d, int rank, int G) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t ring = a.max_rows_per_day;
   const int64_t da = a.day_start[d], db = a.day_start[d + 1];
@@ -230,7 +231,8 @@ __device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& 
   const uint32_t* m_info = a.meta_info + da;
   const uint32_t* m_next = a.meta_next + da;
   const uint32_t* m_nseg = a.meta_nseg + da;
-  const SliceParams& par = sh.par[pslot];
+  const SliceParams& par = *sh.par;
+  const int tsegs = a.table_segs;
   uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
   int since_flush = 0;
 
@@ -260,11 +262,11 @@ __device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& 
   if (lo < hi) {
     const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
     const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
-    for (int64_t sb = seg_first; sb <= seg_last; sb += kTableSegs) {
-      const int64_t se = min(seg_last + 1, sb + kTableSegs);
+    for (int64_t sb = seg_first; sb <= seg_last; sb += tsegs) {
+      const int64_t se = min(seg_last + 1, sb + tsegs);
       // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
       __syncthreads();
-      for (int t = tid; t < (int)(se - sb) * 16; t += kFastThreads) {
+      for (int t = tid; t < (int)(se - sb) * 16; t += THREADS) {
         const int si = t >> 4, h = (t >> 3) & 1, k = t & 7;
         const int64_t seg = sb + si;
         const uint32_t pk = __ldcg(&press[seg * 4 + (k >> 1)]);
@@ -278,7 +280,7 @@ __device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& 
         for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, par.alpha[k], par.alpha2[k], par.gamma[k]);
         if constexpr (REPLAY) {
 #pragma unroll
-          for (int pc = 0; pc < 3; ++pc) sh.P[si * 2 + h][pc][k] = P[pc];
+          for (int pc = 0; pc < 3; ++pc) sh.P[((si * 2 + h) * 3 + pc) * 8 + k] = P[pc];
         } else {
           const int row = (si * 2 + h) * kTabRow + k * (int)kNumCls;
 #pragma unroll
@@ -304,15 +306,15 @@ __device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& 
         n_info = __ldg(&m_info[rb + tid]); n_next = __ldg(&m_next[rb + tid]); n_nseg = __ldg(&m_nseg[rb + tid]);
         n_prev = __ldcg(&cur[rb + tid]);
       }
-      for (uint32_t base = rb; base < re; base += kFastThreads) {  // CTA-uniform trip count (warp collectives below)
+      for (uint32_t base = rb; base < re; base += THREADS) {  // CTA-uniform trip count (warp collectives below)
         const uint32_t i = base + tid;
         const uint32_t info = n_info, next = n_next;
         uint4 prev = n_prev;
         uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
         uint32_t nseg = i < re ? n_nseg : kNone;
-        if (i + kFastThreads < re) {
-          n_info = __ldg(&m_info[i + kFastThreads]); n_next = __ldg(&m_next[i + kFastThreads]);
-          n_nseg = __ldg(&m_nseg[i + kFastThreads]); n_prev = __ldcg(&cur[i + kFastThreads]);
+        if (i + THREADS < re) {
+          n_info = __ldg(&m_info[i + THREADS]); n_next = __ldg(&m_next[i + THREADS]);
+          n_nseg = __ldg(&m_nseg[i + THREADS]); n_prev = __ldcg(&cur[i + THREADS]);
         }
         if (i < re) {
           const int64_t p = da + i;
@@ -363,136 +365,120 @@ __device__ __forceinline__ void process_day(Shared<REPLAY>& sh, const FastArgs& 
   PHASE_ADD(2);  // totals
 }
 
-// split-phase team barrier: arrive when this CTA's writes of the phase are done, wait before reading the team's
-__device__ __forceinline__ void team_arrive(SliceCtx& c, int G) {
-  __syncthreads();
-  if (G > 1) {
-    c.bar_target += (unsigned)G;
-    // release: the CTA's state / pressure writes are ordered before thread 0's increment by the bar.sync above
-    if (threadIdx.x == 0) red_release_inc(c.bar);
-  }
+// Split-phase barrier among the CTAs of a team (the pattern of a cooperative-groups grid sync on a per-team counter;
+// the cooperative launch guarantees co-residency).  A team of one CTA only needs __syncthreads.
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ void team_wait(const SliceCtx& c, int G) {
-  if (G > 1) {
-    // acquire: poll relaxed, fence once; what another CTA wrote is read afterwards with ld.cg / atomics (L2)
-    if (threadIdx.x == 0) {
-      while ((int)(ld_relaxed(c.bar) - c.bar_target) < 0) {}
-      fence_acquire();
-    }
+struct TeamBarrier {
+  unsigned* ctr;
+  unsigned target;
+  int G;
+  __device__ __forceinline__ void arrive() {
     __syncthreads();
+    if (G > 1) {
+      target += (unsigned)G;
+      // release: the CTA's state / pressure writes are ordered before thread 0's increment by the bar.sync above
+      if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    }
   }
-}
+  __device__ __forceinline__ void wait() {
+    if (G > 1) {
+      // acquire: poll relaxed, fence once; what another CTA wrote is read afterwards with ld.cg / atomics (L2)
+      if (threadIdx.x == 0) {
+        while ((int)(ld_relaxed(ctr) - target) < 0) {}
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      __syncthreads();
+    }
+  }
+};
 
-template <bool REPLAY>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) k_fast(const __grid_constant__ FastArgs a) {
-  __shared__ Shared<REPLAY> sh;
+template <bool REPLAY, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ FastArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SharedView sh = carve_shared<REPLAY>(smem_raw, a.table_segs);
   const int tid = threadIdx.x;
-  const int team = blockIdx.x / a.ctas_per_team, rank = blockIdx.x % a.ctas_per_team;
-  if (team >= a.teams) return;
   const int G = a.ctas_per_team;
+  const int64_t slice = blockIdx.x / G;                // one team per slice of 8 simulations
+  const int rank = blockIdx.x % G;
+  TeamBarrier bar{a.team_barrier + slice, 0u, G};
   const int64_t ring = a.max_rows_per_day;
-  const int64_t n_groups = (a.n_slices + kGroup - 1) / kGroup;
-  unsigned targets[kGroup];
-#pragma unroll
-  for (int s = 0; s < kGroup; ++s) targets[s] = 0;
 
-  for (int64_t group = team; group < n_groups; group += a.teams) {
-    SliceCtx ctx[kGroup];
-#pragma unroll
-    for (int s = 0; s < kGroup; ++s) {
-      const int64_t slice = group * kGroup + s;
-      const int64_t set = (a.sets_by_team ? (int64_t)team : group) * kGroup + s;
-      ctx[s].valid = slice < a.n_slices;
-      ctx[s].pre = a.pre + set * 2 * ring;
-      ctx[s].traj = (a.traj && ctx[s].valid) ? a.traj + slice * a.R : nullptr;
-      ctx[s].press = a.pressure + set * a.n_seg * 4;
-      ctx[s].bar = a.team_barrier + team * kGroup + s;
-      ctx[s].bar_target = targets[s];
-      ctx[s].gslice = (uint32_t)((a.sim_offset >> 3) + (uint64_t)slice);
-      ctx[s].sim0 = slice * 8;
-    }
+  SliceCtx c;
+  c.pre = a.pre + slice * 2 * ring;
+  c.traj = a.traj ? a.traj + slice * a.R : nullptr;
+  c.press = a.pressure + slice * a.n_seg * 4;
+  c.gslice = (uint32_t)((a.sim_offset >> 3) + (uint64_t)slice);
+  c.sim0 = slice * 8;
 
-    // ---- group setup: parameters to shared memory, pressure zeroed -----------------------------------------
-    __syncthreads();
-    for (int t = tid; t < 48 * kGroup; t += kFastThreads) {
-      const int s = t / 48, c = (t % 48) >> 3, k = t & 7;
-      if (!ctx[s].valid) continue;
-      const double v = a.params[(ctx[s].sim0 + k) + a.p_ld * c];
-      SliceParams& par = sh.par[s];
-      double* dst = c == 0 ? par.alpha : c == 1 ? par.beta : c == 2 ? par.gamma : c == 3 ? par.rho_h : c == 4 ? par.alpha2 : par.rho_i;
-      dst[k] = v;
-    }
-#pragma unroll
-    for (int s = 0; s < kGroup; ++s) {
-      if (!ctx[s].valid) continue;
-      const int64_t n = a.n_seg * 4, per = (n + G - 1) / G;
-      const int64_t lo = rank * per, hi = min(n, lo + per);
-      for (int64_t i = lo + tid; i < hi; i += kFastThreads) __stcg(&ctx[s].press[i], 0u);
-      team_arrive(ctx[s], G);
-    }
+  // ---- slice setup: parameters to shared memory, pressure zeroed ---------------------------------------------
+  if (tid < 48) {
+    const int col = tid >> 3, k = tid & 7;
+    const double v = a.params[(c.sim0 + k) + a.p_ld * col];
+    SliceParams& par = *sh.par;
+    double* dst = col == 0 ? par.alpha : col == 1 ? par.beta : col == 2 ? par.gamma : col == 3 ? par.rho_h
+                 : col == 4 ? par.alpha2 : par.rho_i;
+    dst[k] = v;
+  }
+  {
+    const int64_t n = a.n_seg * 4, per = (n + G - 1) / G;
+    const int64_t lo = rank * per, hi = min(n, lo + per);
+    for (int64_t i = lo + tid; i < hi; i += THREADS) __stcg(&c.press[i], 0u);
+  }
+  bar.arrive();
+  bar.wait();
 
-    // ---- initial state (abm_wards.cpp:363-372) into the day-0 buffer -----------------------------------------
+  // ---- initial state (abm_wards.cpp:363-372) into the day-0 buffer -----------------------------------------
+  {
+    const int64_t n = a.n_init, per = ((n + G - 1) / G + 31) / 32 * 32;
+    const int64_t lo = rank * per, hi = min(n, lo + per);
+    for (int64_t r = lo + tid; r < hi; r += THREADS) {
+      const uint32_t slot = a.init_slot[r];
+      if (slot == kNone) continue;  // overwritten by a predecessor before it is ever read
+      uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int s = 0; s < kGroup; ++s) {
-      if (!ctx[s].valid) continue;
-      team_wait(ctx[s], G);
-      const int64_t n = a.n_init, per = ((n + G - 1) / G + 31) / 32 * 32;
-      const int64_t lo = rank * per, hi = min(n, lo + per);
-      for (int64_t r = lo + tid; r < hi; r += kFastThreads) {
-        const uint32_t slot = a.init_slot[r];
-        if (slot == kNone) continue;  // overwritten by a predecessor before it is ever read
-        uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int64_t sim = ctx[s].sim0 + k;
-          bool c0 = false, d0 = false;
-          if (sim < a.S) {
-            const double pc = a.icp[r * a.icp_rs + sim * a.icp_cs], pd = a.idp[r * a.idp_rs + sim * a.idp_cs];
-            if (REPLAY) {
-              c0 = a.u_icol[r + a.ui_ld * sim] < pc;
-              d0 = a.u_idet[r + a.ui_ld * sim] < pd;
-            } else {
-              c0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitCol) < threshold33(pc);
-              d0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitDet) < threshold33(pd);
-            }
+      for (int k = 0; k < 8; ++k) {
+        const int64_t sim = c.sim0 + k;
+        bool c0 = false, d0 = false;
+        if (sim < a.S) {
+          const double pc = a.icp[r * a.icp_rs + sim * a.icp_cs], pd = a.idp[r * a.idp_rs + sim * a.idp_cs];
+          if (REPLAY) {
+            c0 = a.u_icol[r + a.ui_ld * sim] < pc;
+            d0 = a.u_idet[r + a.ui_ld * sim] < pd;
+          } else {
+            c0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitCol) < threshold33(pc);
+            d0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitDet) < threshold33(pd);
           }
-          // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
-          //   uncolonised -> D = 0 (U0);  colonised, flag 0 -> D = 0: detected;  flag 1 -> D = 1: pending if
-          //   ttd >= 1, else (1 > ttd) it is neither pending nor detected and gets re-tested like D = inf
-          const uint32_t code = !c0 ? kCodeU0 : (!d0 ? kCodeZero : (a.ttd >= 1 ? kCodeZero - 1u : kCodeA));
-          w[k >> 1] |= code << (16 * (k & 1));
-          cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
         }
-        __stcg(&ctx[s].pre[slot], make_uint4(w[0], w[1], w[2], w[3]));
-        const uint32_t iseg = a.init_seg[r];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&ctx[s].press[(int64_t)iseg * 4 + j], cw[j]);
+        // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
+        //   uncolonised -> D = 0 (U0);  colonised, flag 0 -> D = 0: detected;  flag 1 -> D = 1: pending if
+        //   ttd >= 1, else (1 > ttd) it is neither pending nor detected and gets re-tested like D = inf
+        const uint32_t code = !c0 ? kCodeU0 : (!d0 ? kCodeZero : (a.ttd >= 1 ? kCodeZero - 1u : kCodeA));
+        w[k >> 1] |= code << (16 * (k & 1));
+        cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
       }
-      team_arrive(ctx[s], G);
-    }
-
-    // ---- day loop (abm_wards.cpp:381): the group's slices alternate, each waits for ITS team barrier of the
-    // previous phase only when it is about to need it ------------------------------------------------------
-    for (int64_t d = 0; d < a.n_days; ++d) {
+      __stcg(&c.pre[slot], make_uint4(w[0], w[1], w[2], w[3]));
+      const uint32_t iseg = a.init_seg[r];
 #pragma unroll
-      for (int s = 0; s < kGroup; ++s) {
-        if (!ctx[s].valid) continue;
-        { PHASE_T0();
-        team_wait(ctx[s], G);
-        PHASE_ADD(3); }  // team barrier wait
-        process_day<REPLAY>(sh, a, ctx[s], s, d, rank, G);
-        PHASE_T0();
-        team_arrive(ctx[s], G);
-        PHASE_ADD(4);  // arrive
-      }
-    }
-    // the scratch of this group is reused by the next one: wait until the whole team is done with it
-#pragma unroll
-    for (int s = 0; s < kGroup; ++s) {
-      if (ctx[s].valid) team_wait(ctx[s], G);
-      targets[s] = ctx[s].bar_target;
+      for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&c.press[(int64_t)iseg * 4 + j], cw[j]);
     }
   }
+  bar.arrive();
+
+  // ---- day loop (abm_wards.cpp:381): one team barrier per day ----------------------------------------------
+  for (int64_t d = 0; d < a.n_days; ++d) {
+    { PHASE_T0();
+      bar.wait();
+      PHASE_ADD(3); }  // team barrier wait
+    process_day<REPLAY, THREADS>(sh, a, c, d, rank, G);
+    PHASE_T0();
+    bar.arrive();
+    PHASE_ADD(4);  // arrive
+  }
+  bar.wait();
 }
 
 // ---- packed trajectory -> the reference's float64 columns ------------------------------------------------------
@@ -536,18 +522,40 @@ extern "C" void amro_debug_phase_cycles(unsigned long long* out, int reset) {
 }
 #endif
 
-int fast_max_coresident_ctas(int device, bool replay) {
+// Two launch shapes of the same kernel:
+//   WIDE  one big CTA per SM owns a slice by itself (team of 1: only __syncthreads between days); slices beyond the SM
+//         count run in further waves.  For ensembles with at least about one slice per SM.
+//   TEAM  small CTAs, several per SM, cooperate on a slice with one team barrier per day (cooperative launch).  For
+//         few simulations and many records per day.
+namespace {
+template <bool REPLAY>
+const void* kernel_ptr(int shape) {
+  return shape == kShapeWide ? (const void*)k_fast<REPLAY, kWideThreads, 1> : (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks>;
+}
+}  // namespace
+
+size_t fast_shared_bytes(bool replay, int table_segs) { return fast_smem_bytes(replay, table_segs); }
+int fast_threads(int shape) { return shape == kShapeWide ? kWideThreads : kTeamThreads; }
+
+int fast_max_coresident_ctas(int device, bool replay, int shape, int table_segs) {
   int per_sm = 0, sms = 0;
+  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+  const size_t smem = fast_smem_bytes(replay, table_segs);
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  if (replay) AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast<true>, kFastThreads, 0));
-  else AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast<false>, kFastThreads, 0));
+  AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, fast_threads(shape), smem));
   return per_sm * sms;
 }
 
-void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int grid) {
+void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid) {
+  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+  const size_t smem = fast_smem_bytes(replay, a.table_segs);
+  AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
-  if (replay) AMRO_CUDA(cudaLaunchCooperativeKernel((void*)k_fast<true>, dim3(grid), dim3(kFastThreads), params, 0, st));
-  else AMRO_CUDA(cudaLaunchCooperativeKernel((void*)k_fast<false>, dim3(grid), dim3(kFastThreads), params, 0, st));
+  if (a.ctas_per_team > 1)
+    AMRO_CUDA(cudaLaunchCooperativeKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
+  else
+    AMRO_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
 }
 
 void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,
