@@ -155,7 +155,10 @@ __device__ __noinline__ uint4 step_record_exact(const uint2* tab, const ulonglon
   return make_uint4(postw[0], postw[1], postw[2], postw[3]);
 }
 
-// One record, eight simulations, free-running mode.
+// One record, eight simulations, free-running mode.  Per simulation: one 8-byte table read by class, two unsigned
+// compares of the 16-bit Philox chunk (moved to the upper half-word) against the upper halves of the two entries, one
+// select, one add (the code delta rides in the entry's lower half), one select for "not colonised".  The lower halves
+// never disturb the compares except when chunk == threshold16, which is exactly the tie that goes to the exact path.
 __device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2* full, const FastArgs& a, const uint4 pre,
                                              uint32_t c0, uint32_t c1, uint32_t c2) {
   const uint4 rnd = philox_rk(a, c0, c1, c2, kStreamStep, 0);
@@ -165,18 +168,19 @@ __device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2*
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t w = prew[k >> 1], r = rw[k >> 1];
-    const uint32_t v = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
     const uint32_t cls = (k & 1) ? (w >> 29) : ((w >> kClsShift) & 7u);
-    const uint2 e = tab[k * kNumCls + cls];
-    // upper 15 bits of the chunk in the upper half, ones below: cw < e.x  <=>  chunk15 < threshold15
-    const uint32_t cw = ((k & 1) ? (r >> 1) : (r << 15)) & 0x7FFF0000u | 0xFFFFu;
+    const uint2 e = tab[k * (int)kNumCls + cls];
+    const uint32_t cw = (k & 1) ? (r & 0xFFFF0000u) : (r << 16);   // chunk in the upper half, zeros below
     const bool col = cw < e.x, hit = cw < e.y;
-    tmin = min(tmin, min(cw ^ e.x, cw ^ e.y));           // < 0x10000  <=>  chunk15 == threshold15: a tie
-    o[k] = col ? (v + (hit ? e.y : e.x)) : 0u;           // new code = old + delta (low 16 bits)
+    tmin = min(tmin, min(e.x - cw, e.y - cw));             // in [0, 0xFFFF]  <=>  chunk == threshold16: a tie
+    const uint32_t sel = hit ? e.y : e.x;                  // lower half = code delta
+    // new code = old + delta in the half-word where the old code sits; the other half is discarded by the byte permute
+    const uint32_t sum = (k & 1) ? w + (sel << 16) : w + sel;
+    o[k] = col ? sum : 0u;
   }
-  if (tmin < 0x10000u) return step_record_exact(tab, full, a, pre, rnd, c0, c1, c2);
-  return make_uint4(__byte_perm(o[0], o[1], 0x5410), __byte_perm(o[2], o[3], 0x5410), __byte_perm(o[4], o[5], 0x5410),
-                    __byte_perm(o[6], o[7], 0x5410));
+  if (tmin <= 0xFFFFu) return step_record_exact(tab, full, a, pre, rnd, c0, c1, c2);
+  return make_uint4(__byte_perm(o[0], o[1], 0x7610), __byte_perm(o[2], o[3], 0x7610), __byte_perm(o[4], o[5], 0x7610),
+                    __byte_perm(o[6], o[7], 0x7610));
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
@@ -289,8 +293,10 @@ __device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs
             const uint64_t T = threshold33(p);
             // U and A are tested today (if it is a testing day); a running countdown is not re-tested
             const uint64_t TD = (flag && cls <= kClsA) ? threshold33(__dmul_rn(clamp01(p), rho)) : 0ull;
-            sh.tab[row + cls] = make_uint2((uint32_t)(T >> 17) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
-                                           (uint32_t)(TD >> 17) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
+            // upper halves: min(T >> 16, 0xFFFF) -- saturated so that "always" (T = 2^32) still fits; a chunk equal to
+            // the stored half-word is resolved by the exact path
+            sh.tab[row + cls] = make_uint2((uint32_t)min(T >> 16, (uint64_t)0xFFFFu) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
+                                           (uint32_t)min(TD >> 16, (uint64_t)0xFFFFu) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
             sh.full[row + cls] = make_ulonglong2(T, TD);
           }
         }

@@ -6,11 +6,12 @@ cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
        "-cubin", "-o", "/tmp/kf.cubin", src] + sys.argv[1:]
 out = subprocess.run(cmd, capture_output=True, text=True)
 for line in out.stderr.splitlines():
+    if "error" in line: print(line)
     if "k_fastILb0" in line:
         grab = 3
     if "registers" in line or "spill" in line:
         print(line.strip())
-sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4amro6k_fastILb0EEEvNS_8FastArgsE", "/tmp/kf.cubin"], capture_output=True, text=True).stdout
+sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4amro6k_fastILb0ELi768ELi1EEEvNS_8FastArgsE", "/tmp/kf.cubin"], capture_output=True, text=True).stdout
 ins = []
 for l in sass.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
