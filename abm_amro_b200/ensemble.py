@@ -21,9 +21,9 @@ def shard_sims(total_sims: int, world_size: int, rank: int) -> tuple[int, int]:
     tile ``[0, total_sims)`` exactly (trailing ranks may get 0)."""
     groups = math.ceil(total_sims / SIM_ALIGN)
     per = math.ceil(groups / world_size)
-    lo = min(rank * per * SIM_ALIGN, total_sims)
+    lo = rank * per * SIM_ALIGN
     hi = min((rank + 1) * per * SIM_ALIGN, total_sims)
-    return lo, hi - lo
+    return lo, max(hi - lo, 0)
 
 
 def day_moments(counts_col, counts_det):

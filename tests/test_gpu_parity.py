@@ -1,0 +1,277 @@
+"""GPU parity tests (run on the B200 box with `pytest -m gpu`).  Everything goes through the C ABI
+(abm_amro_b200.capi / engine are ctypes over include/amro_b200.h; abm_amro_b200.amro is the pybind11 binding of it).
+
+Gates (BASELINE.json north_star):
+  1. replay: state bookkeeping, per-ward counts and per-day totals bit-exact against the reference (golden vectors
+     generated from the compiled reference) when both consume the same pre-drawn uniforms;
+  2. transition probabilities: max |P_gpu - P_ref| <= 1e-12 (they are in fact bit-identical);
+  3. free running: bit-exact against the oracle's restatement of the Philox stream, and per-day KS tests at
+     alpha = 0.01 against a 512-member ensemble of the reference (>= 95 % of (day, metric) tests must pass).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from abm_amro_b200 import capi, engine, synth
+from oracle import oracle
+from tests import reference_cases
+from tests.helpers import expected_pressure, random_tensors, stream_to_tensors
+
+pytestmark = pytest.mark.gpu
+P_TOL = 1e-12  # north_star: transition probabilities within 1e-12 in fp64
+
+
+@pytest.fixture(params=["auto", "wide", "team"])
+def shape(request, monkeypatch):
+    """Launch shape of the fused kernel (kernels_fast.cu): chosen by the library, or forced."""
+    if request.param != "auto":
+        monkeypatch.setenv("AMRO_FAST_SHAPE", request.param[0])
+    else:
+        monkeypatch.delenv("AMRO_FAST_SHAPE", raising=False)
+    return request.param
+
+
+def _check_against(ref_out, ref_p, got, S):
+    assert np.array_equal(got.state, ref_out[:, 6:]), "C / D columns differ"
+    assert np.array_equal(got.counts_colonized, oracle.total_positive_colonized(ref_out, S))
+    assert np.array_equal(got.counts_detected, oracle.total_positive_detected(ref_out, S))
+    if got.p is not None:
+        m = ~np.isnan(ref_p)
+        assert np.max(np.abs(got.p[m] - ref_p[m]), initial=0.0) <= P_TOL
+        assert np.array_equal(got.p[m], ref_p[m])  # the same IEEE operations in the same order: identical bits
+
+
+# ---- 1 + 2: replay against the reference's golden outputs ----------------------------------------------------------
+@pytest.mark.parametrize("name", ["replay_a", "replay_c"])
+@pytest.mark.parametrize("path", [capi.PATH_FAST, capi.PATH_GENERAL])
+def test_replay_matches_reference_golden(golden, name, path, shape):
+    z = golden(name)
+    ttd, tsh, tsa = (int(x) for x in z["args"])
+    S = z["icp"].shape[1]
+    out, p, t, used = stream_to_tensors(z["icp"], z["idp"], z["wm"], z["tp"], z["par"], ttd, tsh, tsa, z["stream"])
+    assert np.array_equal(out, z["out"])                      # the oracle reproduces the reference's golden output
+    with engine.Topology(z["wm"], z["tp"], z["icp"].shape[0]) as topo:
+        assert topo.info.fast_eligible
+        got = topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, rng_mode=capi.RNG_REPLAY, path=path,
+                            want_state=True, want_p=True, **t)
+        assert got.path_used == path
+        _check_against(z["out"], p, got, S)                   # ... and so does the GPU, from the same uniforms
+
+
+def test_replay_fractional_weights_use_the_general_path(golden):
+    z = golden("replay_b")
+    ttd, tsh, tsa = (int(x) for x in z["args"])
+    out, p, t, _ = stream_to_tensors(z["icp"], z["idp"], z["wm"], z["tp"], z["par"], ttd, tsh, tsa, z["stream"])
+    with engine.Topology(z["wm"], z["tp"], z["icp"].shape[0]) as topo:
+        assert not topo.info.fast_eligible
+        got = topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, rng_mode=capi.RNG_REPLAY, want_state=True, want_p=True, **t)
+        assert got.path_used == capi.PATH_GENERAL
+        _check_against(z["out"], p, got, z["icp"].shape[1])
+        with pytest.raises(ValueError, match="weights"):
+            topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, path=capi.PATH_FAST)
+
+
+CASES = [  # wards, census, days, S, ttd, tsh, tsa
+    (1, 6, 3, 1, 0, 1, 1), (5, 300, 30, 20, 2, 7, 1), (30, 2000, 12, 64, 2, 7, 1), (4, 100, 15, 9, 0, 1, 3),
+    (12, 150, 9, 33, 5, 2, 2), (2, 700, 6, 8, 1, 3, 1)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_replay_and_philox_match_oracle(case, shape):
+    nw, cen, nd, S, ttd, tsh, tsa = case
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=nw + cen)
+    par = synth.particle_parameters(S, seed=3)
+    g = np.random.default_rng(1)
+    icp, idp = g.random((n_init, S)) * 0.6, g.random((n_init, S))
+    t = random_tensors(wm.shape[0], S, n_init, seed=2)
+    ref, refp = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 5, return_p=True,
+                                               rng=oracle.Rng(oracle.RNG_TENSOR, **t))
+    ref_free = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 5, rng=oracle.Rng(oracle.RNG_PHILOX))
+    with engine.Topology(wm, tp, n_init) as topo:
+        for path in (capi.PATH_FAST, capi.PATH_GENERAL):
+            got = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, rng_mode=capi.RNG_REPLAY, path=path, want_state=True,
+                                want_p=True, want_pressure=(path == capi.PATH_FAST), **t)
+            _check_against(ref, refp, got, S)
+            if path == capi.PATH_FAST:   # per-ward colonisation-pressure counts (the reference's sum(W), :99)
+                c0 = (t["u_icol"] < icp).astype(float)
+                assert np.array_equal(got.pressure, expected_pressure(wm, n_init, got.state, c0, topo.debug_arrays()))
+            free = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path, want_state=True)
+            assert np.array_equal(free.state, ref_free[:, 6:])
+            assert np.array_equal(free.counts_colonized, oracle.total_positive_colonized(ref_free, S))
+            summary_only = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path)     # two-day ring, no trajectory
+            assert np.array_equal(summary_only.counts_colonized, free.counts_colonized)
+            assert np.array_equal(summary_only.counts_detected, free.counts_detected)
+
+
+def test_unsorted_rows_and_sharded_ensembles_give_the_same_numbers():
+    wm, tp, n_init = synth.make_hospital(4, 90, 10, seed=8)
+    S = 24
+    par = synth.particle_parameters(S, seed=4)
+    icp, idp = np.full((n_init, S), 0.3), np.full((n_init, S), 0.4)
+    with engine.Topology(wm, tp, n_init) as topo:
+        whole = topo.simulate(par, icp, idp, 2, 7, 1, 11, want_state=True)
+        # an ensemble sharded over "GPUs": global simulation index in the Philox counter -> identical columns
+        for off in (0, 8, 16):
+            part = topo.simulate(par[off:off + 8], icp[:, off:off + 8], idp[:, off:off + 8], 2, 7, 1, 11, sim_offset=off, want_state=True)
+            assert np.array_equal(part.state[:, :8], whole.state[:, off:off + 8])
+            assert np.array_equal(part.state[:, 8:], whole.state[:, S + off:S + off + 8])
+            assert np.array_equal(part.counts_detected, whole.counts_detected[:, off:off + 8])
+    # the same hospital with its rows (after the initial block) shuffled: records keep their identity
+    g = np.random.default_rng(0)
+    perm = np.r_[np.arange(n_init), n_init + g.permutation(wm.shape[0] - n_init)]
+    inv = np.empty_like(perm); inv[perm] = np.arange(perm.size)
+    sh = wm[perm].copy()
+    m = sh[:, 5] > 0
+    sh[m, 5] = inv[sh[m, 5].astype(int)]
+    t = random_tensors(wm.shape[0], S, n_init, seed=6)
+    ts = dict(t, u_col=t["u_col"][perm], u_det=t["u_det"][perm])
+    with engine.Topology(wm, tp, n_init) as a, engine.Topology(sh, tp, n_init) as b:
+        ra = a.simulate(par, icp, idp, 2, 7, 1, 11, rng_mode=capi.RNG_REPLAY, want_state=True, **t)
+        rb = b.simulate(par, icp, idp, 2, 7, 1, 11, rng_mode=capi.RNG_REPLAY, want_state=True, **ts)
+        assert not b.info.identity_order and rb.path_used == capi.PATH_FAST
+        assert np.array_equal(rb.state, ra.state[perm]) and np.array_equal(rb.counts_colonized, ra.counts_colonized)
+        ref = oracle.simulate_discrete_model(icp, idp, sh, tp, par, 2, 7, 1, 11, rng=oracle.Rng(oracle.RNG_PHILOX))
+        assert np.array_equal(b.simulate(par, icp, idp, 2, 7, 1, 11, want_state=True).state, ref[:, 6:])
+
+
+def test_exotic_links_fall_back_to_the_general_path_and_match_the_oracle():
+    wm, tp, n_init = synth.make_hospital(3, 40, 8, seed=12)
+    w2 = wm.copy()
+    src = np.nonzero(w2[:, 5] > 0)[0]
+    w2[src[5], 5] = src[5] + 1            # same-day target
+    w2[src[40], 5] = 3                    # back to day 0
+    w2[src[60], 5] = w2[src[61], 5]       # two sources, one target: the later row wins
+    tp2 = tp[tp[:, 0] < 7]                # the last day is never stepped
+    S = 5
+    par = synth.particle_parameters(S, seed=1)
+    icp, idp = np.full((n_init, S), 0.4), np.full((n_init, S), 0.5)
+    t = random_tensors(wm.shape[0], S, n_init, seed=3)
+    ref, refp = oracle.simulate_discrete_model(icp, idp, w2, tp2, par, 1, 2, 1, 3, return_p=True, rng=oracle.Rng(oracle.RNG_TENSOR, **t))
+    with engine.Topology(w2, tp2, n_init) as topo:
+        assert not topo.info.fast_eligible
+        got = topo.simulate(par, icp, idp, 1, 2, 1, 3, rng_mode=capi.RNG_REPLAY, want_state=True, want_p=True, **t)
+        _check_against(ref, refp, got, S)
+
+
+# ---- the reference's own test-suite through the drop-in module -----------------------------------------------------------
+@pytest.mark.parametrize("case", reference_cases.ALL, ids=lambda f: f.__name__)
+def test_reference_suite_on_the_drop_in_module(case):
+    from abm_amro_b200 import amro
+    case(amro)
+
+
+def test_single_step_entry_points_match_reference_golden(golden):
+    z = golden("ward_step")
+    N, S, ttd, dh, da = z["args"]
+    S, n = int(S), z["wm"].shape[0]
+    # per-(row, sim) uniforms from the flat stream: replay the oracle with recording
+    rng = oracle.Rng(oracle.RNG_STREAM, stream=z["stream"], record_shape=(n, S))
+    assert np.array_equal(oracle.progress_patients_probability_ward_1_timestep(z["wm"], float(N), z["par"], S, int(ttd), int(dh), int(da), rng=rng), z["out"])
+    uc, ud = (np.asfortranarray(np.where(np.isnan(x), 2.0, x)) for x in (rng.rec_col, rng.rec_det))
+    wmat, par = np.asfortranarray(z["wm"].copy()), np.asfortranarray(z["par"])
+    capi.check(capi.lib().amro_progress_patients(wmat.ctypes.data, n, wmat.shape[1], n, None, 0, 0, 0, float(N), par.ctypes.data,
+                                                 par.shape[0], 6, par.shape[0], S, int(ttd), int(dh), int(da), capi.RNG_REPLAY, 0, 0,
+                                                 uc.ctypes.data, ud.ctypes.data, 0, None))
+    assert np.array_equal(wmat, z["out"])                  # the caller's matrix is updated in place, like the reference
+    z = golden("day_step")
+    S, ttd, dh, da = (int(x) for x in z["args"])
+    rng = oracle.Rng(oracle.RNG_STREAM, stream=z["stream"], record_shape=(n, S))
+    oracle.progress_patients_1_timestep(z["wm"], z["tp"], z["par"], S, ttd, dh, da, rng=rng)
+    uc, ud = (np.asfortranarray(np.where(np.isnan(x), 2.0, x)) for x in (rng.rec_col, rng.rec_det))
+    wmat, tpd = np.asfortranarray(z["wm"].copy()), np.asfortranarray(z["tp"])
+    capi.check(capi.lib().amro_progress_patients(wmat.ctypes.data, n, wmat.shape[1], n, tpd.ctypes.data, tpd.shape[0], 3, tpd.shape[0],
+                                                 0.0, par.ctypes.data, par.shape[0], 6, par.shape[0], S, ttd, dh, da, capi.RNG_REPLAY,
+                                                 0, 0, uc.ctypes.data, ud.ctypes.data, 0, None))
+    assert np.array_equal(wmat, z["out"])
+    from abm_amro_b200 import amro
+    borrowed = np.asfortranarray(z["wm"].copy())
+    ret = amro.progress_patients_1_timestep(borrowed, z["tp"], z["par"], S, ttd, dh, da)
+    assert np.array_equal(ret, borrowed) and ret is not borrowed and not np.array_equal(borrowed, z["wm"])
+    with pytest.raises(IndexError):
+        amro.progress_patients_1_timestep(z["wm"].copy(order="F"), z["tp"][z["tp"][:, 1] != 2], z["par"], S, ttd, dh, da)
+
+
+def test_totals_and_collapse_match_reference_golden(golden):
+    from abm_amro_b200 import amro
+    z = golden("summary")
+    S = z["col"].shape[1]
+    assert np.array_equal(amro.total_positive_colonized(z["full"], S), z["col"])
+    assert np.array_equal(amro.total_positive_detected(z["full"], S), z["det"])
+    n_init = int(z["n_init"])
+    bug = amro.simulate_and_collapse(z["wm"], z["tp"], 0.2, 0.3, n_init, .15, .55, .05, .6, .35, .9, 40, 2, 7, 1, 5)
+    fixed = amro.simulate_and_collapse(z["wm"], z["tp"], 0.2, 0.3, n_init, .15, .55, .05, .6, .35, .9, 40, 2, 7, 1, 5, bug_compatible=False)
+    assert bug.shape == z["collapse"].shape == (30, 5) and np.all(bug[:, 3:] == 0) and np.array_equal(bug[:, 0], np.arange(30))
+    assert np.array_equal(bug[:, 1:3], fixed[:, 3:5])                        # the reference's layout bug, reproduced
+    ref = oracle.simulate_and_collapse(z["wm"], z["tp"], 0.2, 0.3, n_init, .15, .55, .05, .6, .35, .9, 40, 2, 7, 1, 5,
+                                       rng=oracle.Rng(oracle.RNG_PHILOX))
+    assert np.array_equal(bug, ref)                                           # same Philox stream, same arithmetic order
+
+
+# ---- 3: free-running ensembles against the reference (statistical) ---------------------------------------------------------
+def test_free_running_ensemble_matches_reference_distribution(golden):
+    from scipy import stats
+    z = golden("ensemble")
+    nw, cen, nd, hseed = (int(x) for x in z["hospital"])
+    ttd, tsh, tsa = (int(x) for x in z["args"])
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=hseed)
+    S = z["col"].shape[1]
+    with engine.Topology(wm, tp, n_init) as topo:
+        got = topo.simulate(synth.tutorial_parameters(S), float(z["init"][0]), float(z["init"][1]), ttd, tsh, tsa, 424242)
+    passed = total = 0
+    for mine, ref in ((got.counts_colonized, z["col"]), (got.counts_detected, z["det"])):
+        for d in range(nd):
+            total += 1
+            passed += stats.ks_2samp(mine[d], ref[d]).pvalue >= 0.01
+        # means and variances within Monte Carlo error of two 512-member ensembles
+        se = np.sqrt(mine.var(1) / S + ref.var(1) / S) + 1e-9
+        assert np.all(np.abs(mine.mean(1) - ref.mean(1)) < 5 * se)
+        assert np.all(np.abs(np.log((mine.var(1) + 1) / (ref.var(1) + 1))) < 0.6)
+    assert passed / total >= 0.95, f"only {passed}/{total} per-day KS tests passed at alpha = 0.01"
+
+
+# ---- full-size properties (BASELINE config 2: 30 wards x 10,000 patients x 365 days, 1,000 members) ---------------------
+def test_full_size_config2_properties():
+    wm, tp, n_init = synth.make_hospital(30, 10_000, 365, seed=1)
+    S = 1000
+    par = synth.tutorial_parameters(S)
+    with engine.Topology(wm, tp, n_init) as topo:
+        assert topo.info.fast_eligible and topo.info.n_rows == 3_650_000
+        a = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)
+        b = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)
+        assert a.path_used == capi.PATH_FAST
+        assert np.array_equal(a.counts_colonized, b.counts_colonized) and np.array_equal(a.counts_detected, b.counts_detected)
+        assert np.all(a.counts_detected <= a.counts_colonized) and np.all(a.counts_colonized <= 10_000) and a.counts_colonized.min() > 0
+        # a slice of the ensemble run on its own (another "GPU") reproduces its columns exactly
+        part = topo.simulate(par[496:560], 0.2, 0.2, 2, 7, 1, 42, sim_offset=496)
+        assert np.array_equal(part.counts_colonized, a.counts_colonized[:, 496:560])
+        assert np.array_equal(part.counts_detected, a.counts_detected[:, 496:560])
+        # another seed gives another ensemble with the same law: day-364 prevalence within 6 standard errors
+        c = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 43)
+        assert not np.array_equal(a.counts_colonized, c.counts_colonized)
+        x, y = a.counts_colonized[-1].astype(float), c.counts_colonized[-1].astype(float)
+        assert abs(x.mean() - y.mean()) < 6 * np.sqrt(x.var() / S + y.var() / S)
+        # the trajectory of 8 members, expanded to the reference's columns, agrees with the fused per-day totals
+        traj = topo.simulate(par[:8], 0.2, 0.2, 2, 7, 1, 42, want_state=True)
+        day = wm[:, 0].astype(int)
+        col = np.stack([np.bincount(day, weights=(traj.state[:, s] == 1), minlength=365) for s in range(8)], 1)
+        det = np.stack([np.bincount(day, weights=(traj.state[:, 8 + s] <= 0), minlength=365) for s in range(8)], 1)
+        assert np.array_equal(col, a.counts_colonized[:, :8]) and np.array_equal(det, a.counts_detected[:, :8])
+
+
+def test_device_pointer_api_matches_host_api():
+    torch = pytest.importorskip("torch")
+    wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=2)
+    S = 40
+    par = synth.tutorial_parameters(S)
+    dev = torch.device("cuda", 0)
+    with engine.Topology(wm, tp, n_init) as topo:
+        host = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 9)
+        par_d = torch.from_numpy(np.ascontiguousarray(par.T)).to(dev)
+        icp_d = torch.tensor([0.2], dtype=torch.float64, device=dev)
+        cc = torch.zeros((S, topo.info.n_days_out), dtype=torch.int32, device=dev); cd = torch.zeros_like(cc)
+        topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), icp_d.data_ptr(), cc.data_ptr(), cd.data_ptr(), S, 2, 7, 1, 9,
+                             stream=torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(cc.cpu().numpy().T, host.counts_colonized) and np.array_equal(cd.cpu().numpy().T, host.counts_detected)
