@@ -64,7 +64,7 @@ struct amro_topology {
   // shared / fast path
   DevBuf<int64_t> day_start, day_seg_start, seg_row_start, orig_row, pos_of;
   DevBuf<double> seg_N;
-  DevBuf<uint32_t> meta_info, meta_next, meta_nseg, init_seg, init_slot;
+  DevBuf<uint32_t> meta_info, meta_next, meta_nseg, init_seg, init_slot, seg_main_next;
   // general path (uploaded on first use)
   bool general_ready = false;
   DevBuf<int64_t> order, push_src, push_dst;
@@ -138,6 +138,7 @@ int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_co
         t->meta_nseg.upload(H.meta_nseg.data(), H.meta_nseg.size());
         t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
         t->init_slot.upload(H.init_slot.data(), H.init_slot.size());
+        t->seg_main_next.upload(H.seg_main_next.data(), H.seg_main_next.size());
       }
       AMRO_CUDA(cudaStreamSynchronize(0));
     }
@@ -237,7 +238,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 
   FastArgs f{};
   f.meta_info = T->meta_info.p; f.meta_next = T->meta_next.p; f.meta_nseg = T->meta_nseg.p;
-  f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p;
+  f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p; f.seg_main_next = T->seg_main_next.p;
   f.orig_row = H.identity_order ? nullptr : T->orig_row.p;
   f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
   f.seg_N = T->seg_N.p;

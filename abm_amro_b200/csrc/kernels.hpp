@@ -75,6 +75,7 @@ struct FastArgs {
   const uint32_t* meta_info;
   const uint32_t* meta_next;
   const uint32_t* meta_nseg;
+  const uint32_t* seg_main_next; // per ward-day: the ward-day most of its records feed (same ward, next day)
   const uint32_t* init_seg;
   const uint32_t* init_slot;
   const int64_t* orig_row;       // nullptr when identity_order

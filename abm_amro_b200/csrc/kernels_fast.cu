@@ -305,24 +305,42 @@ __device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs
       PHASE_ADD(0);  // table
       // ---- the records of those ward-days that belong to this CTA ----------------------------------------
       const uint32_t rb = max(lo, (uint32_t)(a.seg_row_start[sb] - da)), re = min(hi, (uint32_t)(a.seg_row_start[se] - da));
-      // software pipeline: the loads of the next iteration are in flight while this one computes
+      // Each warp owns a contiguous run of 32-record chunks (dealt out evenly): consecutive trips of a warp stay in the
+      // same ward, so what its records add to tomorrow's pressure can be kept in registers across trips.
+      constexpr int kWarps = THREADS / 32;
+      const uint32_t n_chunks = (re - rb + 31) / 32;
+      const uint32_t w0 = min(re, rb + 32u * (uint32_t)(((uint64_t)n_chunks * (tid >> 5)) / kWarps));
+      const uint32_t w1 = min(re, rb + 32u * (uint32_t)(((uint64_t)n_chunks * ((tid >> 5) + 1)) / kWarps));
+      const uint32_t first = w0 + lane, step = 32u, lim = w1, trips_end = w1 + (uint32_t)lane;
+      // software pipeline: the loads of the next trip are in flight while this one computes
       uint32_t n_info = 0, n_next = kNone, n_nseg = kNone;
       uint4 n_prev = make_uint4(0u, 0u, 0u, 0u);
-      if (rb + tid < re) {
-        n_info = __ldg(&m_info[rb + tid]); n_next = __ldg(&m_next[rb + tid]); n_nseg = __ldg(&m_nseg[rb + tid]);
-        n_prev = __ldcg(&cur[rb + tid]);
+      if (first < lim) {
+        n_info = __ldg(&m_info[first]); n_next = __ldg(&m_next[first]); n_nseg = __ldg(&m_nseg[first]);
+        n_prev = __ldcg(&cur[first]);
       }
-      for (uint32_t base = rb; base < re; base += THREADS) {  // CTA-uniform trip count (warp collectives below)
-        const uint32_t i = base + tid;
+      uint32_t pacc[4] = {0, 0, 0, 0}, wmain = kNone, wsegl = 0xFFFFFFFFu;  // wmain / wsegl are warp-uniform
+      auto flush_warp = [&]() {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = __reduce_add_sync(0xFFFFFFFFu, pacc[j]); pacc[j] = 0; }
+        if (lane == 0 && wmain != kNone) {
+          uint32_t* dst = press + (int64_t)wmain * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) red_add(dst + j, v[j]);
+        }
+      };
+
+      for (uint32_t i = first; i < trips_end; i += step) {  // warp-uniform trip count (warp collectives below)
         const uint32_t info = n_info, next = n_next;
         uint4 prev = n_prev;
         uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
-        uint32_t nseg = i < re ? n_nseg : kNone;
-        if (i + THREADS < re) {
-          n_info = __ldg(&m_info[i + THREADS]); n_next = __ldg(&m_next[i + THREADS]);
-          n_nseg = __ldg(&m_nseg[i + THREADS]); n_prev = __ldcg(&cur[i + THREADS]);
+        uint32_t nseg = i < lim ? n_nseg : kNone;
+        if (i + step < lim) {
+          n_info = __ldg(&m_info[i + step]); n_next = __ldg(&m_next[i + step]);
+          n_nseg = __ldg(&m_nseg[i + step]); n_prev = __ldcg(&cur[i + step]);
         }
-        if (i < re) {
+        if (i < lim) {
           const int64_t p = da + i;
           const int64_t orig = a.orig_row ? a.orig_row[p] : p;
           const int h = (int)(info >> kInfoHShift);
@@ -345,25 +363,29 @@ __device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs
         for (int j = 0; j < 4; ++j) { ccol[j] += colw[j]; cdet[j] += detw[j]; }
 
         // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
-        // Most lanes of a warp feed the same ward-day: they are summed with a warp reduction and added by one
-        // lane; the rest (transfers) add on their own.
-        const bool has = nseg != kNone;
-        const unsigned hm = __ballot_sync(0xFFFFFFFFu, has);
-        if (hm) {
-          const int leader = __ffs(hm) - 1;
-          const uint32_t lseg = __shfl_sync(0xFFFFFFFFu, nseg, leader);
-          const bool mine = nseg == lseg;
-          uint32_t v[4];
+        // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
+        // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
+        // records that go elsewhere (transfers) add on their own.
+        {
+          // the ward-day most records of this chunk feed: same ward as the chunk's first record, next day (warp-uniform)
+          const uint32_t segl0 = __shfl_sync(0xFFFFFFFFu, info & kInfoSegMask, 0);
+          if (segl0 != wsegl) {
+            wsegl = segl0;
+            const uint32_t m = __ldg(&a.seg_main_next[seg0 + segl0]);
+            if (m != wmain) { flush_warp(); wmain = m; }
+          }
+          const bool has = nseg != kNone, mine = nseg == wmain;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = __reduce_add_sync(0xFFFFFFFFu, mine ? colw[j] : 0u);
-          if (has && (lane == leader || !mine)) {
+          for (int j = 0; j < 4; ++j) pacc[j] += mine ? colw[j] : 0u;
+          if (has && !mine) {
             uint32_t* dst = press + (int64_t)nseg * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) red_add(dst + j, mine ? v[j] : colw[j]);
+            for (int j = 0; j < 4; ++j) red_add(dst + j, colw[j]);
           }
         }
         if (++since_flush == kFlushEvery) flush_counts();
       }
+      flush_warp();
       PHASE_ADD(1);  // records (thread 0's view)
     }
   }

@@ -224,6 +224,20 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
     T.init_seg.assign(n_init, kNone);
     T.init_slot.assign(n_init, kNone);
     T.day_has_init.assign(D, 0);
+    T.seg_main_next.assign(T.n_seg, kNone);
+    {
+      // same ward on the following day, where it exists
+      std::unordered_map<std::pair<uint64_t, uint64_t>, uint32_t, PairHash> seg_of;
+      seg_of.reserve((size_t)T.n_seg * 2);
+      for (int64_t d = 0; d < D; ++d)
+        for (int64_t sg = T.day_seg_start[d]; sg < T.day_seg_start[d + 1]; ++sg)
+          seg_of.emplace(std::make_pair((uint64_t)d, dkey(T.seg_ward[sg])), (uint32_t)sg);
+      for (int64_t d = 0; d + 1 < D; ++d)
+        for (int64_t sg = T.day_seg_start[d]; sg < T.day_seg_start[d + 1]; ++sg) {
+          auto it = seg_of.find(std::make_pair((uint64_t)(d + 1), dkey(T.seg_ward[sg])));
+          if (it != seg_of.end()) T.seg_main_next[sg] = it->second;
+        }
+    }
     for (int64_t d = 0; d < D; ++d) {
       for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
         const int64_t r = T.order[p];
@@ -248,7 +262,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   T.fast_eligible = T.why_not_fast.empty();
   T.ring_eligible = T.fast_eligible;
   if (!T.fast_eligible) {
-    T.meta_info.clear(); T.meta_next.clear(); T.meta_nseg.clear(); T.init_seg.clear(); T.init_slot.clear();
+    T.meta_info.clear(); T.meta_next.clear(); T.meta_nseg.clear(); T.init_seg.clear(); T.init_slot.clear(); T.seg_main_next.clear();
   }
 }
 

@@ -51,6 +51,7 @@ struct HostTopology {
   std::vector<uint32_t> init_seg;      // [n_init] absolute segment of init-sourced stepped rows, or kNone
   std::vector<uint32_t> init_slot;     // [n_init] position of that row within its day, or kNone
   std::vector<uint8_t>  day_has_init;  // [total_days+1] 1 if the day holds init-sourced rows
+  std::vector<uint32_t> seg_main_next; // [n_seg] the ward-day most of this ward-day's records feed (same ward, next day), or kNone
 };
 
 // Throws amro::Error (AMRO_EINDEX / AMRO_ERUNTIME / AMRO_EINVAL) mirroring what the reference raises.
