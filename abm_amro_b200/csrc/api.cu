@@ -207,10 +207,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
   const int64_t S = A->n_sims, S_pad = (S + 7) / 8 * 8, n_slices = S_pad / 8;
   const bool want_traj = A->keep_trajectory || A->state_out;
-  // Launch shape (kernels_fast.cu): WIDE when there is about a slice per SM or more, else TEAMs of G CTAs per slice.
+  // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, six per SM, G of them per slice) measured equal or better
+  // than WIDE (one 768-thread CTA per slice) on every configuration tried (profiles/sweeps.txt), so it is the default;
+  // AMRO_FAST_SHAPE=w forces WIDE (kept for the tests and for comparison).
   int sms = 0;
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
-  int shape = (n_slices * 4 >= (int64_t)sms * 3) ? kShapeWide : kShapeTeam;
+  int shape = kShapeTeam;
   if (const char* e = std::getenv("AMRO_FAST_SHAPE")) shape = (e[0] == 'w') ? kShapeWide : kShapeTeam;
   int G = 1, table_segs;
   if (shape == kShapeWide) {
@@ -280,6 +282,17 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
   if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  if (A->day_moments) {
+    if (on_device) day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, A->day_moments, H.n_days_out);
+    else {
+      DevBuf<double> dm;
+      dm.alloc((size_t)(4 * H.n_days_out));
+      day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, dm.p, H.n_days_out);
+      AMRO_CUDA(cudaMemcpyAsync(A->day_moments, dm.p, sizeof(double) * 4 * H.n_days_out, cudaMemcpyDeviceToHost, st));
+      AMRO_CUDA(cudaStreamSynchronize(st));
+    }
+    A->launches++;
+  }
   const int64_t* pos_of = H.identity_order ? nullptr : T->pos_of.p;
   if (A->state_out) {
     if (on_device) {
@@ -367,8 +380,15 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     const int64_t pa = H.day_push_start[d], pb = H.day_push_start[d + 1];
     if (pb > pa) { gen_propagate(st, C, Dp, ld, S, T->push_src.p + pa, T->push_dst.p + pa, pb - pa, tmp.p); launches += 2; }
   }
-  if (A->counts_colonized) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
-  if (A->counts_detected) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
+  if (A->counts_colonized || A->day_moments) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
+  if (A->counts_detected || A->day_moments) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
+  DevBuf<double> dm;
+  if (A->day_moments) {
+    double* dst = A->day_moments;
+    if (!on_device) { dm.alloc((size_t)(4 * H.n_days_out)); dst = dm.p; }
+    day_moments(st, counts.p, counts.p + H.n_days_out * S, H.n_days_out, S, H.n_days_out, dst, H.n_days_out);
+    launches++;
+  }
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   AMRO_CUDA(cudaGetLastError());
 
@@ -380,6 +400,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     AMRO_CUDA(cudaMemcpy2DAsync(A->state_out, A->so_ld * sizeof(double), planes.p, R * sizeof(double), R * sizeof(double),
                                 2 * S, cudaMemcpyDeviceToHost, st));
   if (A->p_out && !on_device) AMRO_CUDA(cudaMemcpyAsync(A->p_out, d_p.p, sizeof(double) * R * S, cudaMemcpyDeviceToHost, st));
+  if (A->day_moments && !on_device) AMRO_CUDA(cudaMemcpyAsync(A->day_moments, dm.p, sizeof(double) * 4 * H.n_days_out, cudaMemcpyDeviceToHost, st));
   AMRO_CUDA(cudaStreamSynchronize(st));
   A->kernel_ms = ev.ms();
   A->launches = launches;

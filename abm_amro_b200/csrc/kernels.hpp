@@ -47,6 +47,8 @@ void gen_propagate(cudaStream_t st, double* C, double* D, int64_t ld, int64_t S,
 void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int64_t S, const int32_t* count_day,
                int mode, int32_t* counts, int64_t ld_out);
 void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n);
+// out[day + ld*{0,1,2,3}] = sum / sum of squares over simulations of col[day + ld_c*s], then of det[...]
+void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld);
 
 // ----------------------------------------------------------------------------------------------------
 // FAST path: packed 16-bit state, 8 simulations (one 16-byte word) per patient-day record and slice; one

@@ -167,6 +167,24 @@ __global__ void k_i32_to_f64(const int32_t* __restrict__ in, double* __restrict_
   if (i < n) out[i] = (double)in[i];
 }
 
+// per-day moments over simulations: one warp per day (counts are exact integers in float64 up to 2^53)
+__global__ void k_day_moments(const int32_t* __restrict__ col, const int32_t* __restrict__ det, int64_t n_days, int64_t S,
+                              int64_t ld_c, double* __restrict__ out, int64_t ld) {
+  const int64_t day = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (day >= n_days) return;
+  double a = 0, b = 0, c = 0, d = 0;
+  for (int64_t s = lane; s < S; s += 32) {
+    const double x = (double)col[day + ld_c * s], y = (double)det[day + ld_c * s];
+    a += x; b += x * x; c += y; d += y * y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o); d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+  }
+  if (lane == 0) { out[day] = a; out[day + ld] = b; out[day + 2 * ld] = c; out[day + 3 * ld] = d; }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -200,6 +218,10 @@ void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int6
   if (R * S == 0) return;
   const int64_t n_row_blocks = (R + kThreads - 1) / kThreads;
   k_gen_count<<<(unsigned)(n_row_blocks * S), kThreads, 0, st>>>(plane, ld, R, S, count_day, mode, counts, ld_out);
+}
+void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld) {
+  if (n_days <= 0) return;
+  k_day_moments<<<blocks_for(n_days * 32), kThreads, 0, st>>>(col, det, n_days, S, ld_c, out, ld);
 }
 void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n) {
   if (n <= 0) return;

@@ -35,6 +35,7 @@ class SimResult:
     state: np.ndarray | None              # [R x 2S] float64: C columns then D columns
     p: np.ndarray | None                  # [R x S] transition probabilities (replay / general path)
     pressure: np.ndarray | None           # [n_segments x S] int32 (fast path)
+    moments: np.ndarray | None            # [n_days_out x 4]: sum, sum^2 of colonised counts, sum, sum^2 of detected counts
     path_used: int
     launches: int
     kernel_ms: float
@@ -97,7 +98,7 @@ class Topology:
                  n_sims: int | None = None, sim_offset: int = 0, rng_mode: int = capi.RNG_PHILOX,
                  path: int = capi.PATH_AUTO, keep_trajectory: bool = False, want_counts: bool = True,
                  want_state: bool = False, want_p: bool = False, want_pressure: bool = False,
-                 u_col=None, u_det=None, u_icol=None, u_idet=None) -> SimResult:
+                 want_moments: bool = False, u_col=None, u_det=None, u_icol=None, u_idet=None) -> SimResult:
         i = self.info
         par = _f64(parameters)
         S = int(n_sims if n_sims is not None else par.shape[0])
@@ -123,7 +124,7 @@ class Topology:
             keep += [uc, ud, uic, uid]
             a.u_col, a.u_det, a.u_ld = uc.ctypes.data, ud.ctypes.data, uc.shape[0]
             a.u_icol, a.u_idet, a.ui_ld = uic.ctypes.data, uid.ctypes.data, uic.shape[0]
-        cc = cd = st = p = pr = None
+        cc = cd = st = p = pr = mo = None
         if want_counts:
             cc = np.zeros((i.n_days_out, S), dtype=np.int32, order="F"); cd = np.zeros_like(cc)
             a.counts_colonized, a.counts_detected = cc.ctypes.data, cd.ctypes.data
@@ -133,15 +134,17 @@ class Topology:
             p = np.empty((i.n_rows, S), order="F"); a.p_out = p.ctypes.data
         if want_pressure:
             pr = np.zeros((i.n_segments, S), dtype=np.int32, order="F"); a.pressure_out = pr.ctypes.data
+        if want_moments:
+            mo = np.zeros((i.n_days_out, 4), order="F"); a.day_moments = mo.ctypes.data
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
-        return SimResult(cc, cd, st, p, pr, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        return SimResult(cc, cd, st, p, pr, mo, a.path_used, a.launches, a.kernel_ms, a.total_ms)
 
     # ---- device-resident run (inputs already in HBM; nothing crosses PCIe) ---------------------------------
     def simulate_device(self, parameters_ptr: int, p_rows: int, p_ld: int, icp_ptr: int, idp_ptr: int,
                         counts_col_ptr: int, counts_det_ptr: int, n_sims: int, time_to_detect: int, tsh: int,
                         tsa: int, seed: int, *, sim_offset: int = 0, stream: int = 0,
                         icp_strides=(0, 0), idp_strides=(0, 0), path: int = capi.PATH_AUTO,
-                        keep_trajectory: bool = False) -> SimResult:
+                        keep_trajectory: bool = False, day_moments_ptr: int = 0) -> SimResult:
         a = capi.SimArgs()
         a.n_sims, a.sim_offset = n_sims, sim_offset
         a.time_to_detect, a.testing_schedule_hospitalized, a.testing_schedule_arrivals, a.seed = time_to_detect, tsh, tsa, seed
@@ -150,6 +153,7 @@ class Topology:
         a.icp, a.icp_rs, a.icp_cs = icp_ptr, icp_strides[0], icp_strides[1]
         a.idp, a.idp_rs, a.idp_cs = idp_ptr, idp_strides[0], idp_strides[1]
         a.counts_colonized, a.counts_detected = counts_col_ptr, counts_det_ptr
+        a.day_moments = day_moments_ptr or None
         a.stream = stream
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
-        return SimResult(None, None, None, None, None, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        return SimResult(None, None, None, None, None, None, a.path_used, a.launches, a.kernel_ms, a.total_ms)

@@ -36,7 +36,9 @@ def day_moments(counts_col, counts_det):
 
 
 def collapse(moments, total_sims: int, group=None):
-    """All-reduce the per-rank day moments (the ONE collective of a run) and turn them into the columns of
+    """``moments`` is float64 [n_days x 4] (``day_moments`` above, or the transpose of the C ABI's
+    ``amro_sim_args.day_moments`` buffer, which the fused run fills on the device).
+    All-reduce the per-rank day moments (the ONE collective of a run) and turn them into the columns of
     ``simulate_and_collapse``: mean colonised, mean detected, population sd colonised, population sd
     detected (reference: abm_wards.cpp:617-620, ``stddev(., 1, 1)``).  Returns float64 [n_days x 4]."""
     import torch

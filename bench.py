@@ -243,6 +243,7 @@ def run_ours(args, rank, world, local_rank):
     idp_d = torch.tensor([IDP], dtype=torch.float64, device=dev)
     cc_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)               # == [n_days x S] column-major
     cd_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)
+    mom_d = torch.zeros((4, n_days), dtype=torch.float64, device=dev)            # == [n_days x 4] column-major
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
@@ -250,9 +251,9 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()                                                            # evict L2 between steps
         r = topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), idp_d.data_ptr(), cc_d.data_ptr(),
                                  cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset,
-                                 stream=stream.cuda_stream)
+                                 stream=stream.cuda_stream, day_moments_ptr=mom_d.data_ptr() if world > 1 else 0)
         if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members
-            ensemble.collapse(ensemble.day_moments(cc_d, cd_d), S * world)
+            ensemble.collapse(mom_d.t(), S * world)
         return r
 
     def barrier():

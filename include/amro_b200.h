@@ -113,6 +113,9 @@ typedef struct amro_sim_args {
   double*  state_out;          /* [R x 2S] ld = so_ld: C columns then D columns of the reference matrix   */
   int64_t  so_ld;              /*   (requires keep_trajectory)                                            */
   double*  p_out;              /* [R x S] ld = R: transition probability used for every update            */
+  double*  day_moments;        /* [n_days_out x 4] ld = n_days_out: per day, over this call's simulations: sum and sum
+                                  of squares of the colonised counts, then of the detected counts -- what one
+                                  all-reduce over the GPUs of an ensemble needs for simulate_and_collapse           */
   int32_t* pressure_out;       /* FAST path: [n_segments x S] ld = n_segments: colonised count per
                                   ward-day before its step (the reference's sum(W), :99)                  */
   void*    stream;             /* cudaStream_t when pointers_on_device, else ignored                      */

@@ -100,9 +100,11 @@ def test_replay_and_philox_match_oracle(case, shape):
             free = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path, want_state=True)
             assert np.array_equal(free.state, ref_free[:, 6:])
             assert np.array_equal(free.counts_colonized, oracle.total_positive_colonized(ref_free, S))
-            summary_only = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path)     # two-day ring, no trajectory
+            summary_only = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path, want_moments=True)  # two-day ring, no trajectory
             assert np.array_equal(summary_only.counts_colonized, free.counts_colonized)
             assert np.array_equal(summary_only.counts_detected, free.counts_detected)
+            c, d = free.counts_colonized.astype(float), free.counts_detected.astype(float)   # exact integers in float64
+            assert np.array_equal(summary_only.moments, np.stack([c.sum(1), (c * c).sum(1), d.sum(1), (d * d).sum(1)], 1))
 
 
 def test_unsorted_rows_and_sharded_ensembles_give_the_same_numbers():
