@@ -46,7 +46,7 @@ class SimArgs(C.Structure):
 
 # every entry point include/amro_b200.h declares (tests/test_capi_symbols.py checks this list against the header)
 EXPORTS = ["amro_last_error", "amro_version", "amro_device_count", "amro_topology_create", "amro_topology_destroy",
-           "amro_topology_get_info", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse",
+           "amro_topology_get_info", "amro_topology_cache_clear", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse",
            "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive"]
 
 _lib = None

@@ -183,5 +183,6 @@ PYBIND11_MODULE(amro, m) {
 
   m.def("set_device", [](int d) { g_device = d; }, "CUDA device used by this module (default: $AMRO_DEVICE or 0).");
   m.def("device_count", &amro_device_count);
+  m.def("clear_cache", &amro_topology_cache_clear, "Free the compiled hospitals the one-call functions keep on the device.");
   m.attr("__version__") = amro_version();
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "common.hpp"
@@ -481,10 +482,74 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
 // --------------------------------------------------------------------------------------------------------
 namespace {
 
-struct TopoGuard {
+// ---- topology cache of the one-call entry points ----------------------------------------------------
+// Optimisation loops call amro.simulate_and_collapse thousands of times on ONE hospital with different parameters
+// (tutorials/Test_2024.ipynb:927).  Compiling + uploading the hospital costs far more than a run, so the one-call entry
+// points keep the last few compiled hospitals, keyed by a 128-bit hash of the CONTENT of ward_matrix and
+// total_patients_per_ward (a caller that edits its arrays in place gets a new topology), n_init and the device.
+struct Hash128 { uint64_t a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full; };
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+void hash_bytes(Hash128& h, const void* data, size_t n_bytes) {
+  const uint64_t* p = static_cast<const uint64_t*>(data);  // inputs are arrays of doubles
+  const size_t n = n_bytes / 8;
+  uint64_t a0 = h.a, a1 = h.b, a2 = h.a ^ 0x165667B19E3779F9ull, a3 = h.b ^ 0x27D4EB2F165667C5ull;
+  size_t i = 0;
+  for (; i + 4 <= n; i += 4) {   // four independent multiply-rotate lanes: memory-bound on one core
+    a0 = rotl64(a0 ^ p[i], 27) * 0x9FB21C651E98DF25ull;
+    a1 = rotl64(a1 ^ p[i + 1], 31) * 0xD6E8FEB86659FD93ull;
+    a2 = rotl64(a2 ^ p[i + 2], 33) * 0xA0761D6478BD642Full;
+    a3 = rotl64(a3 ^ p[i + 3], 29) * 0xE7037ED1A0B428DBull;
+  }
+  for (; i < n; ++i) a0 = rotl64(a0 ^ p[i], 27) * 0x9FB21C651E98DF25ull;
+  h.a = rotl64(a0 ^ a2, 17) * 0x9E3779B97F4A7C15ull ^ (a1 + n);
+  h.b = rotl64(a1 ^ a3, 23) * 0xC2B2AE3D27D4EB4Full ^ (a0 + n);
+}
+void hash_matrix(Hash128& h, const double* m, int64_t rows, int64_t cols, int64_t ld) {
+  const int64_t dims[3] = {rows, cols, 0};
+  hash_bytes(h, dims, sizeof dims);
+  if (ld == rows) hash_bytes(h, m, sizeof(double) * (size_t)(rows * cols));
+  else for (int64_t c = 0; c < cols; ++c) hash_bytes(h, m + c * ld, sizeof(double) * (size_t)rows);
+}
+
+struct CachedTopology {
+  Hash128 key;
+  int64_t n_init = 0;
+  int device = -1;
+  uint64_t stamp = 0;
   amro_topology* t = nullptr;
-  ~TopoGuard() { amro_topology_destroy(t); }
 };
+constexpr int kTopoCacheSlots = 4;
+std::mutex g_cache_mutex;
+CachedTopology g_cache[kTopoCacheSlots];
+uint64_t g_cache_clock = 0;
+
+// Returns a topology owned by the cache (valid until evicted; calls are serialised by the mutex the caller holds).
+amro_topology* cached_topology(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K,
+                               int64_t t_cols, int64_t t_ld, int64_t n_init, int device) {
+  Hash128 key;
+  hash_matrix(key, wm, R, w_cols, w_ld);
+  hash_matrix(key, tp, K, t_cols, t_ld);
+  CachedTopology* victim = &g_cache[0];
+  for (auto& c : g_cache) {
+    if (c.t && c.key.a == key.a && c.key.b == key.b && c.n_init == n_init && c.device == device) { c.stamp = ++g_cache_clock; return c.t; }
+    if (c.stamp < victim->stamp) victim = &c;
+  }
+  amro_topology* t = nullptr;
+  int rc = amro_topology_create(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device, &t);
+  if (rc) throw Error(rc, amro_last_error());
+  if (victim->t) amro_topology_destroy(victim->t);
+  *victim = CachedTopology{key, n_init, device, ++g_cache_clock, t};
+  return t;
+}
+
+}  // namespace
+
+extern "C" void amro_topology_cache_clear(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (auto& c : g_cache) { if (c.t) amro_topology_destroy(c.t); c = CachedTopology{}; }
+}
+
+namespace {
 
 // mean(X,1) / stddev(X,1,1) over simulations with Armadillo's operation order
 // (armadillo_bits/op_mean_meat.hpp:105-133, op_var_meat.hpp:85-106,175-219, arrayops_meat.hpp:917-936)
@@ -536,9 +601,9 @@ extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, i
     if (d_rows != i_rows) fail(AMRO_ERUNTIME, "element-wise multiplication: incompatible matrix dimensions: %lldx%lld and %lldx%lld",
                                (long long)d_rows, (long long)S, (long long)i_rows, (long long)S);
     if (p_cols < 6) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");
-    TopoGuard g;
-    int rc = amro_topology_create(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device, &g.t);
-    if (rc) throw Error(rc, amro_last_error());
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    amro_topology* topo = cached_topology(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device);
+    int rc;
     amro_sim_args a{};
     a.n_sims = S; a.sim_offset = 0; a.time_to_detect = time_to_detect;
     a.testing_schedule_hospitalized = tsh; a.testing_schedule_arrivals = tsa; a.seed = seed;
@@ -547,7 +612,7 @@ extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, i
     a.icp = icp; a.icp_rs = 1; a.icp_cs = i_ld;
     a.idp = idp; a.idp_rs = 1; a.idp_cs = d_ld;
     a.state_out = out + 6 * R; a.so_ld = R;
-    rc = amro_simulate(g.t, &a);
+    rc = amro_simulate(topo, &a);
     if (rc) throw Error(rc, amro_last_error());
     for (int64_t c = 0; c < 6; ++c) std::memcpy(out + c * R, ward_matrix + c * w_ld, sizeof(double) * (size_t)R);  // :375
   });
@@ -571,10 +636,10 @@ extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_r
     }
     const int64_t S = n_sims;
     if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
-    TopoGuard g;
-    int rc = amro_topology_create(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device, &g.t);
-    if (rc) throw Error(rc, amro_last_error());
-    const int64_t Dd = g.t->H.n_days_out;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    amro_topology* topo = cached_topology(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device);
+    int rc;
+    const int64_t Dd = topo->H.n_days_out;
     std::vector<double> par((size_t)(S * 6));
     const double v[6] = {alpha, beta, gamma, rho_hospital, alpha2, rho_imported};
     for (int c = 0; c < 6; ++c) for (int64_t s = 0; s < S; ++s) par[s + S * c] = v[c];     // :584-590
@@ -586,7 +651,7 @@ extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_r
     a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
     a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
     a.counts_colonized = cc.data(); a.counts_detected = cd.data();
-    rc = amro_simulate(g.t, &a);
+    rc = amro_simulate(topo, &a);
     if (rc) throw Error(rc, amro_last_error());
     std::vector<double> xc((size_t)(Dd * S)), xd((size_t)(Dd * S)), mc(Dd), md(Dd), sc(Dd), sd(Dd);
     for (size_t i = 0; i < xc.size(); ++i) { xc[i] = (double)cc[i]; xd[i] = (double)cd[i]; }

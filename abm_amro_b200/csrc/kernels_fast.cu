@@ -41,9 +41,13 @@ namespace amro {
 #ifdef AMRO_PROFILE_PHASES
 __device__ unsigned long long g_phase_cycles[8];   // development only: summed cycles of thread 0 of every CTA per phase
 #define PHASE_T0() long long _pt = clock64()
+#define PHASE_DECL long long& _pt,
+#define PHASE_ARG _pt,
 #define PHASE_ADD(i) do { if (threadIdx.x == 0) { long long _n = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
 #else
 #define PHASE_T0() do {} while (0)
+#define PHASE_DECL
+#define PHASE_ARG
 #define PHASE_ADD(i) do {} while (0)
 #endif
 namespace {
@@ -221,7 +225,7 @@ struct SliceCtx {
 
 // ---- one day of one slice: the part of the day's records that belongs to this CTA (abm_wards.cpp:384-407) ----------
 template <bool REPLAY, int THREADS>
-__device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs& a, const SliceCtx& c, int64_t d, int rank, int G) {
+__device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, const FastArgs& a, const SliceCtx& c, int64_t d, int rank, int G) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t ring = a.max_rows_per_day;
   const int64_t da = a.day_start[d], db = a.day_start[d + 1];
@@ -262,7 +266,7 @@ __device__ __forceinline__ void process_day(const SharedView& sh, const FastArgs
     since_flush = 0;
   };
 
-  PHASE_T0();
+  PHASE_ADD(5);  // day set-up
   if (lo < hi) {
     const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
     const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
@@ -497,12 +501,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   bar.arrive();
 
   // ---- day loop (abm_wards.cpp:381): one team barrier per day ----------------------------------------------
+  PHASE_T0();
   for (int64_t d = 0; d < a.n_days; ++d) {
-    { PHASE_T0();
-      bar.wait();
-      PHASE_ADD(3); }  // team barrier wait
-    process_day<REPLAY, THREADS>(sh, a, c, d, rank, G);
-    PHASE_T0();
+    bar.wait();
+    PHASE_ADD(3);  // team barrier wait
+    process_day<REPLAY, THREADS>(PHASE_ARG sh, a, c, d, rank, G);
     bar.arrive();
     PHASE_ADD(4);  // arrive
   }

@@ -133,6 +133,11 @@ int amro_simulate(amro_topology* topo, amro_sim_args* args);
  * One-call equivalents of the reference's Python entry points (host pointers).
  * ---------------------------------------------------------------------------------------------- */
 
+/* The one-call entry points below keep the last few compiled hospitals on the device, keyed by a hash of the CONTENT of
+ * ward_matrix / total_patients_per_ward, so that optimisation loops over the parameters (the use the reference's
+ * tutorial recommends simulate_and_collapse for) do not recompile the hospital every call.  This frees them. */
+void amro_topology_cache_clear(void);
+
 /* amro.simulate_discrete_model (amro.cpp:18-91 -> abm_wards.cpp:322).  out is [R x (6+2S)], ld = R. */
 int amro_simulate_discrete_model(const double* icp, int64_t i_rows, int64_t i_cols, int64_t i_ld,
                                  const double* idp, int64_t d_rows, int64_t d_cols, int64_t d_ld,

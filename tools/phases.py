@@ -15,4 +15,4 @@ for it in range(3):
     L.amro_debug_phase_cycles(buf, 1)
     v = np.array(list(buf), dtype=np.float64)
     n_cta = int(os.environ.get("N_CTA", "125"))
-    print(f"kernel {r.kernel_ms:.3f} ms; per-CTA cycles (thread 0): table {v[0]/n_cta:.0f}  records {v[1]/n_cta:.0f}  flush {v[2]/n_cta:.0f}  wait {v[3]/n_cta:.0f}  arrive {v[4]/n_cta:.0f}  total {v[:5].sum()/n_cta:.0f} (= {v[:5].sum()/n_cta/1.965e6:.2f} ms)")
+    print(f"kernel {r.kernel_ms:.3f} ms; per-CTA cycles (thread 0): table {v[0]/n_cta:.0f}  records {v[1]/n_cta:.0f}  flush {v[2]/n_cta:.0f}  wait {v[3]/n_cta:.0f}  arrive {v[4]/n_cta:.0f}  setup {v[5]/n_cta:.0f}  total {v[:6].sum()/n_cta:.0f} (= {v[:6].sum()/n_cta/1.965e6:.2f} ms)")
