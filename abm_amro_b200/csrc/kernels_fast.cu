@@ -12,10 +12,10 @@
 //   0x8000 - D        colonised with a finite countdown D: class 3 (0x6000..0x7FFF) while the result is pending
 //                     (0 < D <= ttd), class 4 (0x8000..) once detected (D <= 0).  The reference's daily
 //                     `D -= 1` (:131-132) is `code += 1`, and "pending -> detected" is the carry into bit 15.
-//   Every transition is `new = old + delta` with delta depending only on (class, tested positive today), because the
-//   classes U, A, U0 each have ONE code: U -> A | 0x8000-ttd, A -> A | 0x8000-ttd, U0 -> 0x8001, pending/detected -> +1.
-//   The deltas ride in the low halves of the threshold table entries, so a (record, simulation) update is:
-//   one shared-memory lookup by class, two unsigned compares against the Philox chunk, a select and an add.
+//   Two simulations share a 32-bit word and are stepped together (SIMD within a register): class membership, the
+//   Bernoulli compares and the transition are all "add a constant, replicate bit 15 / bit 31 into a half-word mask
+//   (one PRMT), select with LOP3".  U and A have one code each (U -> A | 0x8000-ttd, A -> A | 0x8000-ttd), a running
+//   countdown is `code + 1`, U0 (first day only) steps like D = 0 with the probability of an uncolonised patient.
 //
 // Data layout (HBM):
 //   pre       [set][2][max records per day]  one 16-byte word = 8 simulations per record; buffer d&1 holds the
@@ -55,11 +55,19 @@ namespace {
 constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 4, kNumCls = 5;
 constexpr uint32_t kClsShift = 13;
 constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, kCodeZero = kClsB << kClsShift;
-constexpr int kTabRow = 8 * (int)kNumCls + 1;  // entries per (ward-day, is_new): [sim][class], +1 pad against bank conflicts
+constexpr int kTabRow = 5;                      // 16-byte entries per (ward-day, is_new): see SharedView
 constexpr int kFlushEvery = 1024;              // row iterations between flushes of the 16-bit packed per-lane counters
+constexpr uint32_t kHalves = 0x00010001u;      // one in each half-word
+constexpr uint32_t kCodeA2 = kCodeA * kHalves, kCodeZero2 = kCodeZero * kHalves;
 
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 0xFFFF in every half-word whose top bit (bit 15 / bit 31) is set: PRMT with sign replication of bytes 1 and 3
+__device__ __forceinline__ uint32_t half_mask(uint32_t x) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(x));
+  return m;
 }
 
 struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
@@ -81,7 +89,7 @@ __device__ __forceinline__ double class_probability(int pc, int h, double F, dou
 // probability class of a state class: U, U0 -> 0; A, pending -> 1; detected -> 2
 __device__ __forceinline__ int prob_class(uint32_t cls) { return cls == kClsB ? 2 : (cls == kClsA || cls == kClsPn) ? 1 : 0; }
 
-// code delta of a colonised outcome: (class, tested positive today) -> new code - old code  (mod 2^16)
+// code delta of a colonised outcome: (class, tested positive today) -> new code - old code  (mod 2^16)   [replay mode]
 __device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) {
   const uint32_t newdet = kCodeZero - (uint32_t)ttd;  // D = ttd after the step (:135 / :147)
   if (cls == kClsU) return hit ? newdet : kCodeA;      // D = inf (:138 / :150)
@@ -90,21 +98,23 @@ __device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) 
   return 1u;                                            // pending / detected: D -= 1
 }
 
-// Shared memory (dynamic): the threshold / delta tables of up to a.table_segs ward-days, then the slice parameters.
-//   free-running: tab  uint2[table_segs*2*kTabRow]       x = (T(P) >> 17) << 16 | delta(not tested positive),
-//                                                         y = (T(P*rho) >> 17) << 16 | delta(tested positive)
-//                      at [(ward-day*2 + is_new)*kTabRow + sim*5 + class]
-//                 full ulonglong2[same]                   the 33-bit thresholds {T(P), T(P*rho)}, read only on a tie
+// Shared memory (dynamic): the tables of up to a.table_segs ward-days, then the slice parameters.
+//   free-running: tab  uint4[table_segs*2*kTabRow] at [(ward-day*2 + is_new)*kTabRow + e]; word j of an entry belongs
+//                      to simulations 2j (low half) and 2j+1 (high half); 15-bit Bernoulli thresholds b (rng.cuh):
+//                        e=0  bU               uncolonised:        colonised today  <=>  v15 + bU  >= 0x8000
+//                        e=1  bU ^ bA          A / pending
+//                        e=2  bA ^ bB          detected
+//                        e=3  bUh              uncolonised, tested positive today (0 when nobody is tested)
+//                        e=4  bUh ^ bAh        A
 //   replay:       P    double[table_segs*2][3][8]         the transition probabilities themselves
 struct SharedView {
-  uint2* tab;
-  ulonglong2* full;
+  uint4* tab;
   double* P;
   SliceParams* par;
 };
 __host__ __device__ inline size_t fast_smem_bytes(bool replay, int table_segs) {
   const size_t rows = (size_t)table_segs * 2;
-  return (replay ? rows * 24 * sizeof(double) : rows * kTabRow * (sizeof(uint2) + sizeof(ulonglong2))) + sizeof(SliceParams) + 16;
+  return (replay ? rows * 24 * sizeof(double) : rows * kTabRow * sizeof(uint4)) + sizeof(SliceParams) + 16;
 }
 template <bool REPLAY>
 __device__ __forceinline__ SharedView carve_shared(unsigned char* raw, int table_segs) {
@@ -114,9 +124,8 @@ __device__ __forceinline__ SharedView carve_shared(unsigned char* raw, int table
     v.P = reinterpret_cast<double*>(raw);
     v.par = reinterpret_cast<SliceParams*>(raw + rows * 24 * sizeof(double));
   } else {
-    v.full = reinterpret_cast<ulonglong2*>(raw);
-    v.tab = reinterpret_cast<uint2*>(raw + rows * kTabRow * sizeof(ulonglong2));
-    v.par = reinterpret_cast<SliceParams*>(raw + rows * kTabRow * (sizeof(ulonglong2) + sizeof(uint2)));
+    v.tab = reinterpret_cast<uint4*>(raw);
+    v.par = reinterpret_cast<SliceParams*>(raw + rows * kTabRow * sizeof(uint4));
   }
   return v;
 }
@@ -138,53 +147,47 @@ __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint3
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Rare path (probability 2^-14 per update): a chunk tied with the upper 15 bits of a threshold.  Redo the record's
-// eight simulations with the full 32-bit uniforms (primary chunk << 16 | refinement chunk) against the 33-bit thresholds.
-__device__ __noinline__ uint4 step_record_exact(const uint2* tab, const ulonglong2* full, const FastArgs& a, uint4 pre,
-                                                uint4 rnd, uint32_t c0, uint32_t c1, uint32_t c2) {
-  const uint4 rf = philox_rk(a, c0, c1, c2, kStreamStep + 1u, 0);
-  const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w}, rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w}, fw[4] = {rf.x, rf.y, rf.z, rf.w};
-  uint32_t postw[4] = {0, 0, 0, 0};
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-    const uint64_t u = (uint64_t)((((rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) << 16) | ((fw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu));
-    const uint32_t cls = v >> kClsShift;
-    const uint2 e = tab[k * kNumCls + cls];
-    const ulonglong2 T = full[k * kNumCls + cls];
-    const bool col = u < T.x, hit = u < T.y;
-    const uint32_t o = col ? ((v + (hit ? e.y : e.x)) & 0xFFFFu) : 0u;
-    postw[k >> 1] |= o << (16 * (k & 1));
-  }
-  return make_uint4(postw[0], postw[1], postw[2], postw[3]);
-}
-
-// One record, eight simulations, free-running mode.  Per simulation: one 8-byte table read by class, two unsigned
-// compares of the 16-bit Philox chunk (moved to the upper half-word) against the upper halves of the two entries, one
-// select, one add (the code delta rides in the entry's lower half), one select for "not colonised".  The lower halves
-// never disturb the compares except when chunk == threshold16, which is exactly the tie that goes to the exact path.
-__device__ __forceinline__ uint4 step_record(const uint2* tab, const ulonglong2* full, const FastArgs& a, const uint4 pre,
-                                             uint32_t c0, uint32_t c1, uint32_t c2) {
-  const uint4 rnd = philox_rk(a, c0, c1, c2, kStreamStep, 0);
+// One record, eight simulations, free-running mode; two simulations per 32-bit word, stepped together.
+//   class masks   detected: bit 15 of the code; running countdown: code >= 0x6000; colonised: code >= 0x2000 -- an add
+//                 that moves the boundary to bit 15, then half_mask()
+//   thresholds    b1 = bU ^ (colonised & (bU^bA)) ^ (detected & (bA^bB)),  b2 = bUh ^ (colonised & (bUh^bAh))
+//   draws         colonised today = bit 15 of v15 + b1, tested positive = bit 15 of v15 + b2 (one uniform for both, so
+//                 P(colonised and positive) = P * rho exactly)
+//   transition    countdown: code + 1;  U / A: A, or 0x8000 - ttd when tested positive;  not colonised: 0 (:153-155)
+// FIRST: the record's state may hold U0 (uncolonised, D = 0; day of the initial state only): probability of an uncolonised
+// patient, transition of a countdown at 0.
+// colf[j] gets one bit per half-word: colonised after the step.
+template <bool FIRST>
+__device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, const uint4 pre, const uint4 rnd, uint32_t x2,
+                                             uint32_t (&colf)[4]) {
+  const uint4 tU = tab[0], tXA = tab[1], tXB = tab[2], tUh = tab[3], tXAh = tab[4];
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w}, rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-  uint32_t o[8];
-  uint32_t tmin = 0xFFFFFFFFu;
+  const uint32_t bU[4] = {tU.x, tU.y, tU.z, tU.w}, xA[4] = {tXA.x, tXA.y, tXA.z, tXA.w}, xB[4] = {tXB.x, tXB.y, tXB.z, tXB.w};
+  const uint32_t bH[4] = {tUh.x, tUh.y, tUh.z, tUh.w}, xH[4] = {tXAh.x, tXAh.y, tXAh.z, tXAh.w};
+  uint32_t o[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t w = prew[k >> 1], r = rw[k >> 1];
-    const uint32_t cls = (k & 1) ? (w >> 29) : ((w >> kClsShift) & 7u);
-    const uint2 e = tab[k * (int)kNumCls + cls];
-    const uint32_t cw = (k & 1) ? (r & 0xFFFF0000u) : (r << 16);   // chunk in the upper half, zeros below
-    const bool col = cw < e.x, hit = cw < e.y;
-    tmin = min(tmin, min(e.x - cw, e.y - cw));             // in [0, 0xFFFF]  <=>  chunk == threshold16: a tie
-    const uint32_t sel = hit ? e.y : e.x;                  // lower half = code delta
-    // new code = old + delta in the half-word where the old code sits; the other half is discarded by the byte permute
-    const uint32_t sum = (k & 1) ? w + (sel << 16) : w + sel;
-    o[k] = col ? sum : 0u;
+  for (int j = 0; j < 4; ++j) {
+    uint32_t w = prew[j];
+    const uint32_t av = rw[j] & 0x7FFF7FFFu;
+    const uint32_t mdet = half_mask(w);
+    uint32_t mcnt = half_mask(w + 0x20002000u);      // code >= 0x6000 (codes stay below 0xA000: no carry between halves)
+    uint32_t mcol = half_mask(w + 0x60006000u);      // code >= 0x2000
+    if constexpr (FIRST) {
+      const uint32_t mge4 = half_mask(w + 0x40004000u);
+      const uint32_t mu0 = mge4 & ~mcnt;              // U0 = 0x4000
+      mcol &= ~mu0;
+      w = (w & ~mu0) | (kCodeZero2 & mu0);
+      mcnt = mge4;
+    }
+    const uint32_t b1 = bU[j] ^ (mcol & xA[j]) ^ (mdet & xB[j]);
+    const uint32_t b2 = bH[j] ^ (mcol & xH[j]);
+    const uint32_t m1 = half_mask(av + b1), m2 = half_mask(av + b2);
+    const uint32_t t = m2 & x2 & ~mcnt;                                 // U / A tested positive: A -> 0x8000 - ttd
+    const uint32_t q = (mcnt & (w + kHalves)) | (~mcnt & kCodeA2);      // D -= 1 (:131-132)  |  A
+    o[j] = m1 & (q ^ t);
+    colf[j] = m1 & kHalves;
   }
-  if (tmin <= 0xFFFFu) return step_record_exact(tab, full, a, pre, rnd, c0, c1, c2);
-  return make_uint4(__byte_perm(o[0], o[1], 0x7610), __byte_perm(o[2], o[3], 0x7610), __byte_perm(o[4], o[5], 0x7610),
-                    __byte_perm(o[6], o[7], 0x7610));
+  return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
@@ -243,6 +246,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, con
   const int tsegs = a.table_segs;
   uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
   int since_flush = 0;
+  const uint32_t x2 = kCodeA2 ^ ((kCodeZero - (uint32_t)a.ttd) * kHalves);   // A <-> "D = ttd" (:135 / :147)
 
   // per-day totals (abm_wards.cpp:445-459 fused): warp-reduce the packed per-lane counters, then one RED per
   // (simulation, metric) and warp
@@ -274,8 +278,10 @@ __device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, con
       const int64_t se = min(seg_last + 1, sb + tsegs);
       // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
       __syncthreads();
-      for (int t = tid; t < (int)(se - sb) * 16; t += THREADS) {
-        const int si = t >> 4, h = (t >> 3) & 1, k = t & 7;
+      for (int t0 = 0; t0 < (int)(se - sb) * 16; t0 += THREADS) {   // uniform trip count: the pairing below shuffles
+        const int t = t0 + tid;
+        const bool valid = t < (int)(se - sb) * 16;
+        const int si = valid ? (t >> 4) : 0, h = (t >> 3) & 1, k = t & 7;
         const int64_t seg = sb + si;
         const uint32_t pk = __ldcg(&press[seg * 4 + (k >> 1)]);
         const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
@@ -287,21 +293,30 @@ __device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, con
 #pragma unroll
         for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, par.alpha[k], par.alpha2[k], par.gamma[k]);
         if constexpr (REPLAY) {
+          if (valid) {
 #pragma unroll
-          for (int pc = 0; pc < 3; ++pc) sh.P[((si * 2 + h) * 3 + pc) * 8 + k] = P[pc];
+            for (int pc = 0; pc < 3; ++pc) sh.P[((si * 2 + h) * 3 + pc) * 8 + k] = P[pc];
+          }
         } else {
-          const int row = (si * 2 + h) * kTabRow + k * (int)kNumCls;
+          // dithered 15-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
+          // never re-tested (:131 / :134)
+          const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), c.gslice, kStreamDither,
+                                                     (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
+          uint32_t e[5];
+          e[0] = bernoulli15(P[0], r16);
+          e[1] = bernoulli15(P[1], r16);
+          e[2] = bernoulli15(P[2], r16);
+          e[3] = flag ? bernoulli15(__dmul_rn(clamp01(P[0]), rho), r16) : 0u;
+          e[4] = flag ? bernoulli15(__dmul_rn(clamp01(P[1]), rho), r16) : 0u;
+          // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
 #pragma unroll
-          for (uint32_t cls = 0; cls < kNumCls; ++cls) {
-            const double p = P[prob_class(cls)];
-            const uint64_t T = threshold33(p);
-            // U and A are tested today (if it is a testing day); a running countdown is not re-tested
-            const uint64_t TD = (flag && cls <= kClsA) ? threshold33(__dmul_rn(clamp01(p), rho)) : 0ull;
-            // upper halves: min(T >> 16, 0xFFFF) -- saturated so that "always" (T = 2^32) still fits; a chunk equal to
-            // the stored half-word is resolved by the exact path
-            sh.tab[row + cls] = make_uint2((uint32_t)min(T >> 16, (uint64_t)0xFFFFu) << 16 | (code_delta(cls, false, a.ttd) & 0xFFFFu),
-                                           (uint32_t)min(TD >> 16, (uint64_t)0xFFFFu) << 16 | (code_delta(cls, true, a.ttd) & 0xFFFFu));
-            sh.full[row + cls] = make_ulonglong2(T, TD);
+          for (int q = 0; q < 5; ++q) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
+            e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
+          }
+          if (valid && !(k & 1)) {
+            uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + (si * 2 + h) * kTabRow) + (k >> 1);
+            row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
           }
         }
       }
@@ -349,19 +364,27 @@ __device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, con
           const int64_t orig = a.orig_row ? a.orig_row[p] : p;
           const int h = (int)(info >> kInfoHShift);
           const int row = ((int)((int64_t)(info & kInfoSegMask) + seg0 - sb)) * 2 + h;
-          if (((info >> kInfoSrcShift) & 3u) == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
+          const uint32_t src = (info >> kInfoSrcShift) & 3u;
+          if (src == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
           uint4 post;
-          if constexpr (REPLAY) post = step_record_replay(sh, par, a, prev, row, h, orig, c.sim0, h ? test_a : test_h);
-          else post = step_record(sh.tab + row * kTabRow, sh.full + row * kTabRow, a, prev, (uint32_t)orig,
-                                  (uint32_t)((uint64_t)orig >> 32), c.gslice);
+          if constexpr (REPLAY) {
+            post = step_record_replay(sh, par, a, prev, row, h, orig, c.sim0, h ? test_a : test_h);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t pw = j == 0 ? post.x : j == 1 ? post.y : j == 2 ? post.z : post.w;
+              colw[j] = ((pw >> 13) | (pw >> 15)) & kHalves;             // classes 1, 3 (bit 13) and 4 (bit 15)
+            }
+          } else {
+            // U0 only exists in states that come straight from the initial draw
+            const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice, kStreamStep, 0);
+            if (src == kSrcInit) post = step_record<true>(sh.tab + row * kTabRow, prev, rnd, x2, colw);
+            else post = step_record<false>(sh.tab + row * kTabRow, prev, rnd, x2, colw);
+          }
           if (next != kNone) __stcg(&nxt[next], post);     // :402-407 the successor starts from this state
           if (c.traj) __stcg(&c.traj[p], post);
           const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            detw[j] = (pw[j] >> 15) & 0x00010001u;                       // class 4: D <= 0
-            colw[j] = ((pw[j] >> 13) & 0x00010001u) | detw[j];           // classes 1, 3 (bit 13) and 4
-          }
+          for (int j = 0; j < 4; ++j) detw[j] = (pw[j] >> 15) & kHalves;   // class 4: D <= 0
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) { ccol[j] += colw[j]; cdet[j] += detw[j]; }

@@ -1,18 +1,25 @@
 // Counter-based RNG of the free-running mode (DESIGN.md "RNG spec") and the probability -> threshold map.
 //
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11), hand-written; key = 64-bit seed, counter =
-// (row_lo, row_hi, sim_group, stream).  One call yields 128 bits = eight 16-bit chunks, one per
-// simulation of a group of 8 consecutive simulations, for ONE patient-day record.  A Bernoulli(p) draw
-// compares the 32-bit uniform (primary chunk << 16 | refinement chunk) with T(p) = #{r : r*2^-32 < p};
-// the refinement chunk comes from stream+1 and is only evaluated when the primary chunk ties with the
-// upper half of T (probability 2^-16), so the common case costs one Philox call per 8 updates.
+// (index_lo, index_hi, sim_group, stream).  One call yields 128 bits = eight 16-bit chunks, one per
+// simulation of a group of 8 consecutive simulations.
+//
+// Daily step (stream 0, index = patient-day record): the draw of (record, simulation) is v15 = chunk & 0x7FFF and
+//     Bernoulli(p) fires  <=>  v15 + B(p) >= 2^15,      B(p) = (T31(p) + r16) >> 16  in [0, 2^15],
+// with T31(p) = ceil(p * 2^31) (0 for p <= 0 or NaN, 2^31 for p >= 1) and r16 the DITHER of the record's ward-day:
+// the 16-bit chunk of (stream 6, index = ward-day, simulation).  Rounding the 31-bit threshold to 15 bits with a
+// uniform dither keeps the probability of every draw exact to 2^-31 (E[B(p)] = T31(p) / 2^16; "never" and "always"
+// stay exact) while the kernel compares 15 bits per update; draws of the records of one ward-day and simulation are
+// coupled only through the shared dither, by less than 2^-32 in any joint probability.
+// Initial state (streams 2..5, index = initial row): 32-bit uniform (chunk << 16 | chunk of stream+1) < T(p), T(p) =
+// #{r : r * 2^-32 < p}.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace amro {
 
-constexpr uint32_t kStreamStep = 0, kStreamInitCol = 2, kStreamInitDet = 4;  // +1 = refinement stream
+constexpr uint32_t kStreamStep = 0, kStreamInitCol = 2, kStreamInitDet = 4, kStreamDither = 6;  // init: +1 = low half
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
@@ -45,16 +52,30 @@ __device__ __forceinline__ uint64_t threshold33(double p) {
   return __double2ull_ru(p * 4294967296.0);  // exact product (power of two), rounded up = ceil
 }
 
+// T31(p) and the dithered 15-bit threshold B(p) of the daily step
+__device__ __forceinline__ uint32_t threshold31(double p) {
+  if (!(p > 0.0)) return 0u;
+  if (p >= 1.0) return 1u << 31;
+  return (uint32_t)__double2ull_ru(p * 2147483648.0);  // exact product (power of two), rounded up = ceil
+}
+__device__ __forceinline__ uint32_t bernoulli15(double p, uint32_t r16) { return (threshold31(p) + r16) >> 16; }
+
 __device__ __forceinline__ double clamp01(double p) { return p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p); }
 
-// Full 32-bit uniform of (row, global sim, stream): both chunks.  Used by the general kernels and the
-// initial-state draws; the fast kernel evaluates the refinement lazily.
+// Full 32-bit uniform of (row, global sim, stream): both chunks (initial-state draws).
 __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t row, uint64_t sim, uint32_t stream) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint4 a = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 3), stream, k0, k1);
   const uint4 b = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 3), stream + 1u, k0, k1);
   const int k = (int)(sim & 7u);
   return (chunk16(a, k) << 16) | chunk16(b, k);
+}
+
+// 16-bit chunk of (index, global sim, stream): the daily draw (stream 0, & 0x7FFF) and the ward-day dither (stream 6)
+__device__ __forceinline__ uint32_t philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
+  const uint4 a = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream, (uint32_t)seed,
+                                (uint32_t)(seed >> 32));
+  return chunk16(a, (int)(sim & 7u));
 }
 
 }  // namespace amro

@@ -82,10 +82,28 @@ uint64_t amro_oracle_threshold(double p) {
   return (uint64_t)ceil(p * 4294967296.0);
 }
 
-/* RNG spec: one Philox call serves the 8 simulations of a sim-group (sim >> 3) of one row; simulation
- * k = sim & 7 owns the 16-bit chunk (word[k>>1] >> 16*(k&1)).  The 32-bit uniform of a draw is
- * (primary chunk << 16) | refinement chunk, the refinement coming from the call with stream id + 1
- * (the GPU only evaluates it when the primary chunk ties with the threshold's upper half). */
+/* RNG spec, daily step (abm_amro_b200/csrc/rng.cuh): one Philox call, counter (index_lo, index_hi, sim >> 3, stream),
+ * serves the 8 simulations of a sim-group; simulation k = sim & 7 owns the 16-bit chunk (word[k>>1] >> 16*(k&1)).
+ * The draw of (row, sim) is v15 = chunk(stream 0, row) & 0x7FFF and Bernoulli(p) fires iff v15 + B(p) >= 2^15 with
+ * B(p) = (T31(p) + r16) >> 16, T31(p) = ceil(p * 2^31) clamped to [0, 2^31], r16 = chunk(stream 6, ward-day): the
+ * 31-bit threshold is rounded to 15 bits with a dither shared by the ward-day, so E[B(p)] = T31(p) / 2^16 exactly. */
+uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream};
+  uint32_t a[4];
+  amro_oracle_philox4x32_10(ctr, key, a);
+  unsigned k = (unsigned)(sim & 7u);
+  return (a[k >> 1] >> (16u * (k & 1u))) & 0xFFFFu;
+}
+uint32_t amro_oracle_threshold31(double p) {
+  if (!(p > 0.0)) return 0;
+  if (p >= 1.0) return 1u << 31;
+  return (uint32_t)ceil(p * 2147483648.0);
+}
+uint32_t amro_oracle_bernoulli15(double p, uint32_t r16) { return (amro_oracle_threshold31(p) + r16) >> 16; }
+
+/* RNG spec, initial state: the 32-bit uniform of (row, sim, kind) is (chunk of stream 2*kind) << 16 | chunk of stream
+ * 2*kind + 1, compared with T(p) = #{r : r * 2^-32 < p}. */
 uint32_t amro_oracle_philox_u32(uint64_t seed, uint64_t row, uint64_t sim, uint32_t kind) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 3), 2u * kind};
@@ -153,12 +171,13 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
       const double p = prob[i], h = AT(wm, ld, i, H);
       double* D = &AT(wm, ld, i, dc);
       int col, tie_kind = rng->kind;
-      uint32_t r32 = 0;
+      uint32_t v15 = 0, r16 = 0;
       if (p_out) p_out[gid + p_out_ld * s] = p;
       /* :116-120 colonisation draw, always taken */
       if (tie_kind == AMRO_ORACLE_RNG_PHILOX) {
-        r32 = amro_oracle_philox_u32(rng->seed, gid, rng->sim_offset + s, 0);
-        col = (uint64_t)r32 < amro_oracle_threshold(p);
+        v15 = amro_oracle_philox_chunk(rng->seed, gid, rng->sim_offset + s, 0) & 0x7FFFu;
+        r16 = amro_oracle_philox_chunk(rng->seed, rng->ward_day, rng->sim_offset + s, 6);
+        col = v15 + amro_oracle_bernoulli15(p, r16) >= 0x8000u;
         rng->n_draws++;
       } else {
         double u;
@@ -182,7 +201,7 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
           int hit = 0;
           if (flag) {                                                      /* short-circuit: draw only if testing today */
             if (tie_kind == AMRO_ORACLE_RNG_PHILOX) {
-              hit = (uint64_t)r32 < amro_oracle_threshold(clamp01(p) * rho);
+              hit = v15 + amro_oracle_bernoulli15(clamp01(p) * rho, r16) >= 0x8000u; /* same uniform: P(col and hit) = p*rho */
             } else {
               double u2;
               if (tie_kind == AMRO_ORACLE_RNG_GLIBC) u2 = glibc_randu();
@@ -248,6 +267,7 @@ int amro_oracle_day_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t 
     rc = amro_oracle_ward_step(tmp, n, n_cols, n, N, params, p_rows, p_cols, p_ld, n_sims, ttd,
                                detect_hosp, detect_arr, rng, gids, p_out, p_out_ld);
     if (rc == 0) for (uint64_t c = 0; c < n_cols; ++c) for (uint64_t i = 0; i < n; ++i) AT(wm, ld, idx[i], c) = tmp[i + n * c];
+    rng->ward_day++;
     free(tmp);
   }
   free(wards); free(idx); free(gids);
@@ -287,6 +307,7 @@ int amro_oracle_simulate(const double* icp, uint64_t i_rows, uint64_t i_cols, ui
   const uint64_t S = i_cols, ncol = w_cols + 2 * S, C0 = 6;
   if (rng->kind == AMRO_ORACLE_RNG_GLIBC) srand((unsigned)seed); /* :333 -> arma_rng_cxx03.hpp:48-52 */
   if (rng->kind == AMRO_ORACLE_RNG_PHILOX) rng->seed = (uint64_t)(int64_t)seed;
+  rng->ward_day = 0;
 
   if (t_rows == 0 || t_cols == 0) return fail(AMRO_ORACLE_ERUNTIME, "max(): object has no elements");
   double dmax = AT(tppw, t_ld, 0, 0); /* :356 */

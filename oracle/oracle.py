@@ -27,7 +27,7 @@ class _Rng(C.Structure):
                 ("stream", _dp), ("stream_len", _u64), ("stream_pos", _u64),
                 ("u_col", _dp), ("u_det", _dp), ("u_ld", _u64),
                 ("u_icol", _dp), ("u_idet", _dp), ("ui_ld", _u64),
-                ("seed", _u64), ("sim_offset", _u64), ("n_draws", _u64),
+                ("seed", _u64), ("sim_offset", _u64), ("ward_day", _u64), ("n_draws", _u64),
                 ("rec_col", _dp), ("rec_det", _dp), ("rec_ld", _u64),
                 ("rec_icol", _dp), ("rec_idet", _dp), ("reci_ld", _u64)]
 
