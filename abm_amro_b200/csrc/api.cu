@@ -63,9 +63,10 @@ struct amro_topology {
   double compile_ms = 0.0;
   int coresident[2] = {0, 0};  // cooperative-launch capacity of k_fast<false/true>
   // shared / fast path
-  DevBuf<int64_t> day_start, day_seg_start, seg_row_start, orig_row, pos_of;
+  DevBuf<int64_t> day_start, day_seg_start, seg_row_start, pos_of;
   DevBuf<double> seg_N;
-  DevBuf<uint32_t> meta_info, meta_next, meta_nseg, init_seg, init_slot, seg_main_next;
+  DevBuf<uint4> meta;   // packed per-record words of the fast path (kernels.hpp FastArgs::meta)
+  DevBuf<uint32_t> init_seg, init_slot, seg_main_next;
   // general path (uploaded on first use)
   bool general_ready = false;
   DevBuf<int64_t> order, push_src, push_dst;
@@ -129,14 +130,17 @@ int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_co
       t->day_seg_start.upload(H.day_seg_start.data(), H.day_seg_start.size());
       t->seg_row_start.upload(H.seg_row_start.data(), H.seg_row_start.size());
       t->seg_N.upload(H.seg_N.data(), H.seg_N.size());
-      if (!H.identity_order) {
-        t->orig_row.upload(H.order.data(), (size_t)H.Rp);
-        t->pos_of.upload(H.pos_of.data(), H.pos_of.size());
-      }
+      if (!H.identity_order) t->pos_of.upload(H.pos_of.data(), H.pos_of.size());
       if (H.fast_eligible) {
-        t->meta_info.upload(H.meta_info.data(), H.meta_info.size());
-        t->meta_next.upload(H.meta_next.data(), H.meta_next.size());
-        t->meta_nseg.upload(H.meta_nseg.data(), H.meta_nseg.size());
+        // one 16-byte word per record: what a lane needs about its record comes with ONE load, and the successor's slot
+        // is already the byte offset inside a state-ring buffer laid out [chunk of 32][slice of the team][32]
+        std::vector<uint4> meta((size_t)H.Rp);
+        for (int64_t p = 0; p < H.Rp; ++p) {
+          const uint32_t nx = H.meta_next[p];
+          meta[p] = make_uint4(H.meta_info[p], nx == kNone ? kNone : (uint32_t)(fast_ring_slot(nx) * sizeof(uint4)),
+                               H.meta_nseg[p], (uint32_t)H.order[p]);
+        }
+        t->meta.upload(meta.data(), meta.size());
         t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
         t->init_slot.upload(H.init_slot.data(), H.init_slot.size());
         t->seg_main_next.upload(H.seg_main_next.data(), H.seg_main_next.size());
@@ -206,7 +210,9 @@ uint64_t schedule_u64(int v) { return (uint64_t)(int64_t)v; }  // int -> unsigne
 void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
   const HostTopology& H = T->H;
   const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
-  const int64_t S = A->n_sims, S_pad = (S + 7) / 8 * 8, n_slices = S_pad / 8;
+  constexpr int64_t kTeamSims = kSimsPerSlice * kSlicesPerTeam;
+  const int64_t S = A->n_sims, S_pad = (S + kTeamSims - 1) / kTeamSims * kTeamSims, n_slices = S_pad / kSimsPerSlice;
+  const int64_t n_teams = n_slices / kSlicesPerTeam;   // padded simulations have zero parameters and are never read back
   const bool want_traj = A->keep_trajectory || A->state_out;
   // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, six per SM, G of them per slice) measured equal or better
   // than WIDE (one 768-thread CTA per slice) on every configuration tried (profiles/sweeps.txt), so it is the default;
@@ -215,21 +221,20 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
   int shape = kShapeTeam;
   if (const char* e = std::getenv("AMRO_FAST_SHAPE")) shape = (e[0] == 'w') ? kShapeWide : kShapeTeam;
-  int G = 1, table_segs;
-  if (shape == kShapeWide) {
-    table_segs = (int)std::max<int64_t>(1, std::min<int64_t>(H.max_segs_per_day, kWideTableSegsMax));
-  } else {
-    table_segs = (int)std::max<int64_t>(1, std::min<int64_t>(H.max_segs_per_day, kTeamTableSegs));
-    const int cap = fast_max_coresident_ctas(T->device, replay, shape, table_segs);
+  int G = 1;
+  if (shape == kShapeTeam) {
+    const int cap = fast_max_coresident_ctas(T->device, replay, shape);
     if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
     const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kTeamThreads));  // a CTA wants a few warps of records
-    G = (int)std::max<int64_t>(1, std::min<int64_t>(cap / std::max<int64_t>(n_slices, 1), useful));
-    if (n_slices > cap) G = 1;
+    G = (int)std::max<int64_t>(1, std::min<int64_t>(cap / std::max<int64_t>(n_teams, 1), useful));
+    if (n_teams > cap) G = 1;
   }
   if (const char* e = std::getenv("AMRO_FAST_G")) G = std::max(1, std::atoi(e));
-  const int64_t ring = std::max<int64_t>(H.max_rows_per_day, 1);
+  const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
+  if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
+  if (ring_chunks * 32 * kSlicesPerTeam * (int64_t)sizeof(uint4) >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: day too large for 32-bit slot offsets");
 
-  ensure_size(T->ws_pre, (size_t)(n_slices * 2 * ring));
+  ensure_size(T->ws_pre, (size_t)(n_teams * 2 * ring_chunks * 32 * kSlicesPerTeam));
   if (want_traj) ensure_size(T->ws_traj, (size_t)(n_slices * std::max<int64_t>(H.R, 1)));
   ensure_size(T->ws_pressure, (size_t)(n_slices * std::max<int64_t>(H.n_seg, 1) * 4));
   ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
@@ -240,12 +245,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
                               S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
 
   FastArgs f{};
-  f.meta_info = T->meta_info.p; f.meta_next = T->meta_next.p; f.meta_nseg = T->meta_nseg.p;
+  f.meta = T->meta.p;
   f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p; f.seg_main_next = T->seg_main_next.p;
-  f.orig_row = H.identity_order ? nullptr : T->orig_row.p;
+  f.identity_order = H.identity_order ? 1 : 0;
   f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
   f.seg_N = T->seg_N.p;
-  f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.max_rows_per_day = ring;
+  f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.ring_chunks = ring_chunks;
   f.params = T->ws_params.p; f.p_ld = S_pad;
   f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
   f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
@@ -268,13 +273,13 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.pre = T->ws_pre.p; f.traj = want_traj ? T->ws_traj.p : nullptr;
   f.pressure = T->ws_pressure.p;
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
-  ensure_size(T->ws_barrier, (size_t)n_slices);
-  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_slices, st));
-  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.table_segs = table_segs;
+  ensure_size(T->ws_barrier, (size_t)n_teams);
+  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));
+  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G;
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
-  fast_launch(st, f, replay, shape, (int)(n_slices * G));
+  fast_launch(st, f, replay, shape, (int)(n_teams * G));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
 

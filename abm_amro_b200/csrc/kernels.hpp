@@ -55,37 +55,38 @@ void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_
 // persistent cooperative kernel runs the initial state and every day.  See kernels_fast.cu.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kSimsPerSlice = 8;
+#ifndef AMRO_SLICES_PER_TEAM
+#define AMRO_SLICES_PER_TEAM 2
+#endif
+constexpr int kSlicesPerTeam = AMRO_SLICES_PER_TEAM;           // a team (the CTAs that share one barrier) steps this many slices together
 constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-bit field: days and time_to_detect limits
 #ifndef AMRO_WIDE_THREADS
-#define AMRO_WIDE_THREADS 768
+#define AMRO_WIDE_THREADS 512
 #endif
 #ifndef AMRO_TEAM_THREADS
 #define AMRO_TEAM_THREADS 128
 #endif
 #ifndef AMRO_TEAM_MINBLOCKS
-#define AMRO_TEAM_MINBLOCKS 6
+#define AMRO_TEAM_MINBLOCKS 4
 #endif
 constexpr int kShapeWide = 0, kShapeTeam = 1;
 constexpr int kWideThreads = AMRO_WIDE_THREADS;     // one CTA per SM
 constexpr int kTeamThreads = AMRO_TEAM_THREADS;
 constexpr int kTeamMinBlocks = AMRO_TEAM_MINBLOCKS; // CTAs per SM the team shape's register budget is sized for
-constexpr int kTeamTableSegs = 8;                   // ward-day tables resident in shared memory at once (team shape)
-constexpr int kWideTableSegsMax = 96;               // ... wide shape (a whole day's wards when they fit)
 
 struct FastArgs {
   // topology (device)
-  const uint32_t* meta_info;
-  const uint32_t* meta_next;
-  const uint32_t* meta_nseg;
+  const uint4* meta;             // per record: (is_new | source | ward-day within the day, byte offset of the successor's slot in a
+                                 // state-ring buffer or kNone, successor's ward-day or kNone, original row (low 32 bits))
   const uint32_t* seg_main_next; // per ward-day: the ward-day most of its records feed (same ward, next day)
   const uint32_t* init_seg;
   const uint32_t* init_slot;
-  const int64_t* orig_row;       // nullptr when identity_order
+  int identity_order;            // records are stepped in their original row order (row = position)
   const int64_t* day_start;
   const int64_t* day_seg_start;
   const int64_t* seg_row_start;
   const double* seg_N;
-  int64_t R, n_init, n_days, n_seg, max_rows_per_day;
+  int64_t R, n_init, n_days, n_seg, ring_chunks;   // ring_chunks: 32-record chunks of the fullest day
   // run
   const double* params; int64_t p_ld;   // [S_pad x 6] device copy, padded rows are zeros
   const double* icp; int64_t icp_rs, icp_cs;
@@ -101,21 +102,22 @@ struct FastArgs {
   const double* u_icol; const double* u_idet; int64_t ui_ld;
   double* p_out;                 // optional [R x S] (ld = R)
   // state
-  uint4* pre;                    // [n_slices][2][max_rows_per_day]: pre-step state of the current / next day
-  uint4* traj;                   // nullptr, or [n_slices][R]: post-step state of every record
-  uint32_t* pressure;            // [n_slices][n_seg][4]: 8 x 16-bit colonised counts per ward-day
+  uint4* pre;                    // [n_teams][2][ring_chunks][slices per team][32]: pre-step state of the current / next day
+  uint4* traj;                   // nullptr, or [n_teams][R][slices per team]: post-step state of every record
+  uint32_t* pressure;            // [n_teams][n_seg][slices per team][4]: 8 x 16-bit colonised counts per ward-day and slice
   int32_t* counts_col;           // [n_days_out x S_pad8] ld = counts_ld  (zeroed by the caller)
   int32_t* counts_det;
   int64_t counts_ld;
-  unsigned int* team_barrier;    // [n_slices] zeroed by the caller
+  unsigned int* team_barrier;    // [n_teams] zeroed by the caller
   int ctas_per_team;             // CTAs that share a slice (1 = no inter-CTA barrier)
-  int table_segs;                // ward-day tables resident in shared memory at once
 };
 
-size_t fast_shared_bytes(bool replay, int table_segs);
+// element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
+inline int64_t fast_ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kSlicesPerTeam * 32) + (q & 31u); }
+size_t fast_shared_bytes(bool replay, int shape);
 int fast_threads(int shape);
 // CTAs of the given launch shape that can be co-resident (bound of a cooperative launch)
-int fast_max_coresident_ctas(int device, bool replay, int shape, int table_segs);
+int fast_max_coresident_ctas(int device, bool replay, int shape);
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid);
 
 // Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run

@@ -5,17 +5,18 @@
 // with total_positive_colonized/_detected (:435-509), for hospitals with unit weights, is_new in {0,1},
 // time_to_detect >= 0 and next_day links that connect consecutive days.
 //
-// State of one (record, simulation): a 16-bit code whose top 3 bits are its class.
+// State of one (record, simulation): a 16-bit code.
 //   0x0000        U   uncolonised                              (reference: C=0, D=inf)
-//   0x2000        A   colonised, no test result coming         (C=1, D=inf)
-//   0x4000        U0  uncolonised with a zero countdown        (C=0, D=0: the initial-state quirk of :372)
-//   0x8000 - D        colonised with a finite countdown D: class 3 (0x6000..0x7FFF) while the result is pending
-//                     (0 < D <= ttd), class 4 (0x8000..) once detected (D <= 0).  The reference's daily
-//                     `D -= 1` (:131-132) is `code += 1`, and "pending -> detected" is the carry into bit 15.
-//   Two simulations share a 32-bit word and are stepped together (SIMD within a register): class membership, the
-//   Bernoulli compares and the transition are all "add a constant, replicate bit 15 / bit 31 into a half-word mask
-//   (one PRMT), select with LOP3".  U and A have one code each (U -> A | 0x8000-ttd, A -> A | 0x8000-ttd), a running
-//   countdown is `code + 1`, U0 (first day only) steps like D = 0 with the probability of an uncolonised patient.
+//   0x0800        U0  uncolonised with a zero countdown        (C=0, D=0: the initial-state quirk of :372)
+//   0x1000        A   colonised, no test result coming         (C=1, D=inf)
+//   0x4000 - D        colonised with a finite countdown D: pending (0x20C0..0x3FFF) while 0 < D <= ttd, detected
+//                     (0x4000..0x5F40) once D <= 0.  The reference's daily `D -= 1` (:131-132) is `code + 1`.
+//   Every code is the bit pattern of a finite non-negative fp16 number and integer order = fp16 order, so class tests
+//   (code >= boundary) and the Bernoulli compares run as packed half-precision compares (HSET2: one instruction per TWO
+//   simulations, on the FMA pipe, result a half-word mask or 1.0 per half-word), and the per-lane counters are packed
+//   half adds.  Two simulations share a 32-bit word and are stepped together (SIMD within a register); U and A have
+//   one code each (U -> A | 0x4000-ttd, A -> A | 0x4000-ttd), a running countdown is `code + 1`, U0 (first day only)
+//   steps like D = 0 with the probability of an uncolonised patient.
 //
 // Data layout (HBM):
 //   pre       [set][2][max records per day]  one 16-byte word = 8 simulations per record; buffer d&1 holds the
@@ -52,22 +53,52 @@ __device__ unsigned long long g_phase_cycles[8];   // development only: summed c
 #endif
 namespace {
 
-constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 4, kNumCls = 5;
-constexpr uint32_t kClsShift = 13;
-constexpr uint32_t kCodeA = kClsA << kClsShift, kCodeU0 = kClsU0 << kClsShift, kCodeZero = kClsB << kClsShift;
+constexpr uint32_t kClsU = 0, kClsA = 1, kClsU0 = 2, kClsPn = 3, kClsB = 4;
+constexpr uint32_t kCodeU0 = 0x0800u, kCodeA = 0x1000u, kCodeCnt = 0x2000u, kCodeZero = 0x4000u;  // class boundaries
+static_assert(kCodeZero - kMaxCountdown > kCodeCnt && kCodeZero + kMaxCountdown < 0x7C00u, "codes must stay finite fp16 patterns");
+__host__ __device__ inline uint32_t cls_of(uint32_t code) {
+  return code >= kCodeZero ? kClsB : code >= kCodeCnt ? kClsPn : code >= kCodeA ? kClsA : code >= kCodeU0 ? kClsU0 : kClsU;
+}
 constexpr int kTabRow = 5;                      // 16-byte entries per (ward-day, is_new): see SharedView
 constexpr int kFlushEvery = 1024;              // row iterations between flushes of the 16-bit packed per-lane counters
 constexpr uint32_t kHalves = 0x00010001u;      // one in each half-word
-constexpr uint32_t kCodeA2 = kCodeA * kHalves, kCodeZero2 = kCodeZero * kHalves;
+constexpr uint32_t kCodeA2 = kCodeA * kHalves, kCodeZero2 = kCodeZero * kHalves, kCodeCnt2 = kCodeCnt * kHalves, kCodeU02 = kCodeU0 * kHalves;
+constexpr uint32_t kOne2 = 0x3C003C00u;        // half2 (1.0, 1.0)
 
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 0xFFFF in every half-word whose top bit (bit 15 / bit 31) is set: PRMT with sign replication of bytes 1 and 3
-__device__ __forceinline__ uint32_t half_mask(uint32_t x) {
+// packed half-precision compares / adds on 32-bit registers holding two fp16 patterns
+__device__ __forceinline__ uint32_t h2_ge_mask(uint32_t x, uint32_t y) {  // 0xFFFF per half-word where x >= y
   uint32_t m;
-  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(x));
+  asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
   return m;
+}
+__device__ __forceinline__ uint32_t h2_lt_mask(uint32_t x, uint32_t y) {
+  uint32_t m;
+  asm("set.lt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
+  return m;
+}
+__device__ __forceinline__ uint32_t h2_ge_one(uint32_t x, uint32_t y) {   // 1.0 per half-word where x >= y
+  uint32_t m;
+  asm("set.ge.f16x2.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
+  return m;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t x, uint32_t y) {
+  uint32_t r;
+  asm("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t x, uint32_t y, uint32_t z) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
+  return r;
+}
+// two small non-negative integers held as halves -> packed 16-bit integers
+__device__ __forceinline__ uint32_t h2_to_u16x2(uint32_t x) {
+  uint32_t lo, hi;
+  asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.rni.u32.f16 %0, l; cvt.rni.u32.f16 %1, h; }" : "=r"(lo), "=r"(hi) : "r"(x));
+  return lo | (hi << 16);
 }
 
 struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
@@ -98,35 +129,36 @@ __device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) 
   return 1u;                                            // pending / detected: D -= 1
 }
 
-// Shared memory (dynamic): the tables of up to a.table_segs ward-days, then the slice parameters.
-//   free-running: tab  uint4[table_segs*2*kTabRow] at [(ward-day*2 + is_new)*kTabRow + e]; word j of an entry belongs
-//                      to simulations 2j (low half) and 2j+1 (high half); 15-bit Bernoulli thresholds b (rng.cuh):
-//                        e=0  bU               uncolonised:        colonised today  <=>  v15 + bU  >= 0x8000
+// Shared memory (dynamic): the slice parameters, then for EACH WARP the tables of up to kWarpTableSegs ward-days.
+//   free-running: tab  uint4[kWarpTableSegs*2*kNS*kTabRow] at [((ward-day*2 + is_new)*kNS + slice)*kTabRow + e]; word j of an entry belongs
+//                      to simulations 2j (low half) and 2j+1 (high half); 14-bit Bernoulli thresholds b (rng.cuh):
+//                        e=0  bU               uncolonised:        colonised today  <=>  v14 < bU
 //                        e=1  bU ^ bA          A / pending
 //                        e=2  bA ^ bB          detected
 //                        e=3  bUh              uncolonised, tested positive today (0 when nobody is tested)
 //                        e=4  bUh ^ bAh        A
-//   replay:       P    double[table_segs*2][3][8]         the transition probabilities themselves
-struct SharedView {
+//   replay:       P    double[kWarpTableSegs*2][kNS][3][8] the transition probabilities themselves
+constexpr int kWarpTableSegs = 8;              // ring of ward-day tables per warp (power of two)
+constexpr int kZeroRow = kWarpTableSegs * 2;   // + one all-zero row: lanes without a record step against it
+constexpr int kNS = kSlicesPerTeam;   // slices (of 8 simulations) a team steps together: a thread carries one record x 16 simulations
+// element (uint4) index of slot q of the team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
+__host__ __device__ inline int64_t ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kNS * 32) + (q & 31u); }
+struct WarpShared {
   uint4* tab;
   double* P;
-  SliceParams* par;
 };
-__host__ __device__ inline size_t fast_smem_bytes(bool replay, int table_segs) {
-  const size_t rows = (size_t)table_segs * 2;
-  return (replay ? rows * 24 * sizeof(double) : rows * kTabRow * sizeof(uint4)) + sizeof(SliceParams) + 16;
+__host__ __device__ inline size_t warp_table_bytes(bool replay) {
+  return (size_t)(kWarpTableSegs * 2 + 1) * kNS * (replay ? 24 * sizeof(double) : kTabRow * sizeof(uint4));
+}
+__host__ __device__ inline size_t fast_smem_bytes(bool replay, int threads) {
+  return kNS * sizeof(SliceParams) + (size_t)(threads / 32) * warp_table_bytes(replay);
 }
 template <bool REPLAY>
-__device__ __forceinline__ SharedView carve_shared(unsigned char* raw, int table_segs) {
-  SharedView v{};
-  const size_t rows = (size_t)table_segs * 2;
-  if constexpr (REPLAY) {
-    v.P = reinterpret_cast<double*>(raw);
-    v.par = reinterpret_cast<SliceParams*>(raw + rows * 24 * sizeof(double));
-  } else {
-    v.tab = reinterpret_cast<uint4*>(raw);
-    v.par = reinterpret_cast<SliceParams*>(raw + rows * kTabRow * sizeof(uint4));
-  }
+__device__ __forceinline__ WarpShared carve_shared(unsigned char* raw, int warp) {
+  WarpShared v{};
+  unsigned char* mine = raw + (size_t)warp * warp_table_bytes(REPLAY);
+  if constexpr (REPLAY) v.P = reinterpret_cast<double*>(mine);
+  else v.tab = reinterpret_cast<uint4*>(mine);
   return v;
 }
 
@@ -148,18 +180,15 @@ __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint3
 }
 
 // One record, eight simulations, free-running mode; two simulations per 32-bit word, stepped together.
-//   class masks   detected: bit 15 of the code; running countdown: code >= 0x6000; colonised: code >= 0x2000 -- an add
-//                 that moves the boundary to bit 15, then half_mask()
+//   class masks   detected / running countdown / colonised: packed half compares of the code with the class boundaries
 //   thresholds    b1 = bU ^ (colonised & (bU^bA)) ^ (detected & (bA^bB)),  b2 = bUh ^ (colonised & (bUh^bAh))
-//   draws         colonised today = bit 15 of v15 + b1, tested positive = bit 15 of v15 + b2 (one uniform for both, so
+//   draws         colonised today = v14 < b1, tested positive = v14 < b2 (one uniform for both, so
 //                 P(colonised and positive) = P * rho exactly)
-//   transition    countdown: code + 1;  U / A: A, or 0x8000 - ttd when tested positive;  not colonised: 0 (:153-155)
+//   transition    countdown: code + 1;  U / A: A, or 0x4000 - ttd when tested positive;  not colonised: 0 (:153-155)
 // FIRST: the record's state may hold U0 (uncolonised, D = 0; day of the initial state only): probability of an uncolonised
 // patient, transition of a countdown at 0.
-// colf[j] gets one bit per half-word: colonised after the step.
 template <bool FIRST>
-__device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, const uint4 pre, const uint4 rnd, uint32_t x2,
-                                             uint32_t (&colf)[4]) {
+__device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, const uint4 pre, const uint4 rnd, uint32_t x2) {
   const uint4 tU = tab[0], tXA = tab[1], tXB = tab[2], tUh = tab[3], tXAh = tab[4];
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w}, rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
   const uint32_t bU[4] = {tU.x, tU.y, tU.z, tU.w}, xA[4] = {tXA.x, tXA.y, tXA.z, tXA.w}, xB[4] = {tXB.x, tXB.y, tXB.z, tXB.w};
@@ -168,42 +197,39 @@ __device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, cons
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t w = prew[j];
-    const uint32_t av = rw[j] & 0x7FFF7FFFu;
-    const uint32_t mdet = half_mask(w);
-    uint32_t mcnt = half_mask(w + 0x20002000u);      // code >= 0x6000 (codes stay below 0xA000: no carry between halves)
-    uint32_t mcol = half_mask(w + 0x60006000u);      // code >= 0x2000
+    const uint32_t v = rw[j] & 0x3FFF3FFFu;
+    const uint32_t mdet = h2_ge_mask(w, kCodeZero2);
+    uint32_t mcnt = h2_ge_mask(w, kCodeCnt2);
+    const uint32_t mcol = h2_ge_mask(w, kCodeA2);
     if constexpr (FIRST) {
-      const uint32_t mge4 = half_mask(w + 0x40004000u);
-      const uint32_t mu0 = mge4 & ~mcnt;              // U0 = 0x4000
-      mcol &= ~mu0;
+      const uint32_t mu0 = h2_ge_mask(w, kCodeU02) & ~mcol;
       w = (w & ~mu0) | (kCodeZero2 & mu0);
-      mcnt = mge4;
+      mcnt |= mu0;
     }
     const uint32_t b1 = bU[j] ^ (mcol & xA[j]) ^ (mdet & xB[j]);
     const uint32_t b2 = bH[j] ^ (mcol & xH[j]);
-    const uint32_t m1 = half_mask(av + b1), m2 = half_mask(av + b2);
-    const uint32_t t = m2 & x2 & ~mcnt;                                 // U / A tested positive: A -> 0x8000 - ttd
+    const uint32_t m1 = h2_lt_mask(v, b1), m2 = h2_lt_mask(v, b2);
+    const uint32_t t = m2 & x2 & ~mcnt;                                 // U / A tested positive: A -> 0x4000 - ttd
     const uint32_t q = (mcnt & (w + kHalves)) | (~mcnt & kCodeA2);      // D -= 1 (:131-132)  |  A
     o[j] = m1 & (q ^ t);
-    colf[j] = m1 & kHalves;
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
-__device__ __forceinline__ uint4 step_record_replay(const SharedView& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
-                                                    int64_t orig, int64_t sim0, bool flag) {
+__device__ __forceinline__ uint4 step_record_replay(const WarpShared& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
+                                                    int64_t orig, int64_t sim0, bool flag, bool on) {
   const uint32_t prew[4] = {pre.x, pre.y, pre.z, pre.w};
   uint32_t postw[4] = {0, 0, 0, 0};
   const double* rho_tab = h ? par.rho_i : par.rho_h;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t v = (prew[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-    const uint32_t cls = v >> kClsShift;
+    const uint32_t cls = cls_of(v);
     const int64_t sim = sim0 + k;
     const double P = sh.P[(row * 3 + prob_class(cls)) * 8 + k];
     bool col = false, hit = false;
-    if (sim < a.S) {
+    if (on && sim < a.S) {
       if (a.p_out) a.p_out[orig + a.R * sim] = P;
       col = a.u_col[orig + a.u_ld * sim] < P;                                                  // :116
       // a finite countdown is always <= ttd here (ttd >= 0), so only U and A reach the test (:131 / :134)
@@ -217,211 +243,13 @@ __device__ __forceinline__ uint4 step_record_replay(const SharedView& sh, const 
 
 }  // namespace
 
-// Everything a CTA needs to step its slice (8 simulations).
-struct SliceCtx {
-  uint4* pre;
-  uint4* traj;
-  uint32_t* press;
-  uint32_t gslice;
-  int64_t sim0;
-};
-
-// ---- one day of one slice: the part of the day's records that belongs to this CTA (abm_wards.cpp:384-407) ----------
-template <bool REPLAY, int THREADS>
-__device__ __forceinline__ void process_day(PHASE_DECL const SharedView& sh, const FastArgs& a, const SliceCtx& c, int64_t d, int rank, int G) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t ring = a.max_rows_per_day;
-  const int64_t da = a.day_start[d], db = a.day_start[d + 1];
-  const uint32_t n = (uint32_t)(db - da), per = ((n + G - 1) / G + 31) / 32 * 32;
-  const uint32_t lo = min(n, (uint32_t)rank * per), hi = min(n, lo + per);   // this CTA's records, day-relative
-  const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
-  const int64_t seg0 = a.day_seg_start[d];
-  const uint4* cur = c.pre + (d & 1) * ring;
-  uint4* nxt = c.pre + ((d + 1) & 1) * ring;
-  uint32_t* press = c.press;
-  const uint32_t* m_info = a.meta_info + da;
-  const uint32_t* m_next = a.meta_next + da;
-  const uint32_t* m_nseg = a.meta_nseg + da;
-  const SliceParams& par = *sh.par;
-  const int tsegs = a.table_segs;
-  uint32_t ccol[4] = {0, 0, 0, 0}, cdet[4] = {0, 0, 0, 0};
-  int since_flush = 0;
-  const uint32_t x2 = kCodeA2 ^ ((kCodeZero - (uint32_t)a.ttd) * kHalves);   // A <-> "D = ttd" (:135 / :147)
-
-  // per-day totals (abm_wards.cpp:445-459 fused): warp-reduce the packed per-lane counters, then one RED per
-  // (simulation, metric) and warp
-  auto flush_counts = [&]() {
-    uint32_t tot[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      tot[j] = __reduce_add_sync(0xFFFFFFFFu, ccol[j]);
-      tot[4 + j] = __reduce_add_sync(0xFFFFFFFFu, cdet[j]);
-      ccol[j] = 0;
-      cdet[j] = 0;
-    }
-    if (lane < 16 && d < a.counts_ld) {
-      uint32_t w = tot[0];
-#pragma unroll
-      for (int j = 1; j < 8; ++j) w = ((lane >> 1) == j) ? tot[j] : w;
-      const uint32_t v = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
-      int32_t* dst = (lane < 8) ? a.counts_col : a.counts_det;
-      if (v != 0 && dst) atomicAdd(&dst[d + a.counts_ld * (c.sim0 + (lane & 7))], (int)v);
-    }
-    since_flush = 0;
-  };
-
-  PHASE_ADD(5);  // day set-up
-  if (lo < hi) {
-    const int64_t seg_first = seg0 + (m_info[lo] & kInfoSegMask);
-    const int64_t seg_last = seg0 + (m_info[hi - 1] & kInfoSegMask);
-    for (int64_t sb = seg_first; sb <= seg_last; sb += tsegs) {
-      const int64_t se = min(seg_last + 1, sb + tsegs);
-      // ---- threshold / delta tables of ward-days [sb, se) ------------------------------------------------
-      __syncthreads();
-      for (int t0 = 0; t0 < (int)(se - sb) * 16; t0 += THREADS) {   // uniform trip count: the pairing below shuffles
-        const int t = t0 + tid;
-        const bool valid = t < (int)(se - sb) * 16;
-        const int si = valid ? (t >> 4) : 0, h = (t >> 3) & 1, k = t & 7;
-        const int64_t seg = sb + si;
-        const uint32_t pk = __ldcg(&press[seg * 4 + (k >> 1)]);
-        const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
-        // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
-        const double F = __dmul_rn(__ddiv_rn(par.beta[k], a.seg_N[seg]), (double)cnt);
-        const bool flag = h ? test_a : test_h;
-        const double rho = h ? par.rho_i[k] : par.rho_h[k];
-        double P[3];
-#pragma unroll
-        for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, par.alpha[k], par.alpha2[k], par.gamma[k]);
-        if constexpr (REPLAY) {
-          if (valid) {
-#pragma unroll
-            for (int pc = 0; pc < 3; ++pc) sh.P[((si * 2 + h) * 3 + pc) * 8 + k] = P[pc];
-          }
-        } else {
-          // dithered 15-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
-          // never re-tested (:131 / :134)
-          const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), c.gslice, kStreamDither,
-                                                     (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
-          uint32_t e[5];
-          e[0] = bernoulli15(P[0], r16);
-          e[1] = bernoulli15(P[1], r16);
-          e[2] = bernoulli15(P[2], r16);
-          e[3] = flag ? bernoulli15(__dmul_rn(clamp01(P[0]), rho), r16) : 0u;
-          e[4] = flag ? bernoulli15(__dmul_rn(clamp01(P[1]), rho), r16) : 0u;
-          // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
-#pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
-            e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
-          }
-          if (valid && !(k & 1)) {
-            uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + (si * 2 + h) * kTabRow) + (k >> 1);
-            row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
-          }
-        }
-      }
-      __syncthreads();
-      PHASE_ADD(0);  // table
-      // ---- the records of those ward-days that belong to this CTA ----------------------------------------
-      const uint32_t rb = max(lo, (uint32_t)(a.seg_row_start[sb] - da)), re = min(hi, (uint32_t)(a.seg_row_start[se] - da));
-      // Each warp owns a contiguous run of 32-record chunks (dealt out evenly): consecutive trips of a warp stay in the
-      // same ward, so what its records add to tomorrow's pressure can be kept in registers across trips.
-      constexpr int kWarps = THREADS / 32;
-      const uint32_t n_chunks = (re - rb + 31) / 32;
-      const uint32_t w0 = min(re, rb + 32u * (uint32_t)(((uint64_t)n_chunks * (tid >> 5)) / kWarps));
-      const uint32_t w1 = min(re, rb + 32u * (uint32_t)(((uint64_t)n_chunks * ((tid >> 5) + 1)) / kWarps));
-      const uint32_t first = w0 + lane, step = 32u, lim = w1, trips_end = w1 + (uint32_t)lane;
-      // software pipeline: the loads of the next trip are in flight while this one computes
-      uint32_t n_info = 0, n_next = kNone, n_nseg = kNone;
-      uint4 n_prev = make_uint4(0u, 0u, 0u, 0u);
-      if (first < lim) {
-        n_info = __ldg(&m_info[first]); n_next = __ldg(&m_next[first]); n_nseg = __ldg(&m_nseg[first]);
-        n_prev = __ldcg(&cur[first]);
-      }
-      uint32_t pacc[4] = {0, 0, 0, 0}, wmain = kNone, wsegl = 0xFFFFFFFFu;  // wmain / wsegl are warp-uniform
-      auto flush_warp = [&]() {
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = __reduce_add_sync(0xFFFFFFFFu, pacc[j]); pacc[j] = 0; }
-        if (lane == 0 && wmain != kNone) {
-          uint32_t* dst = press + (int64_t)wmain * 4;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) red_add(dst + j, v[j]);
-        }
-      };
-
-      for (uint32_t i = first; i < trips_end; i += step) {  // warp-uniform trip count (warp collectives below)
-        const uint32_t info = n_info, next = n_next;
-        uint4 prev = n_prev;
-        uint32_t colw[4] = {0, 0, 0, 0}, detw[4] = {0, 0, 0, 0};
-        uint32_t nseg = i < lim ? n_nseg : kNone;
-        if (i + step < lim) {
-          n_info = __ldg(&m_info[i + step]); n_next = __ldg(&m_next[i + step]);
-          n_nseg = __ldg(&m_nseg[i + step]); n_prev = __ldcg(&cur[i + step]);
-        }
-        if (i < lim) {
-          const int64_t p = da + i;
-          const int64_t orig = a.orig_row ? a.orig_row[p] : p;
-          const int h = (int)(info >> kInfoHShift);
-          const int row = ((int)((int64_t)(info & kInfoSegMask) + seg0 - sb)) * 2 + h;
-          const uint32_t src = (info >> kInfoSrcShift) & 3u;
-          if (src == kSrcNone) prev = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
-          uint4 post;
-          if constexpr (REPLAY) {
-            post = step_record_replay(sh, par, a, prev, row, h, orig, c.sim0, h ? test_a : test_h);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t pw = j == 0 ? post.x : j == 1 ? post.y : j == 2 ? post.z : post.w;
-              colw[j] = ((pw >> 13) | (pw >> 15)) & kHalves;             // classes 1, 3 (bit 13) and 4 (bit 15)
-            }
-          } else {
-            // U0 only exists in states that come straight from the initial draw
-            const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice, kStreamStep, 0);
-            if (src == kSrcInit) post = step_record<true>(sh.tab + row * kTabRow, prev, rnd, x2, colw);
-            else post = step_record<false>(sh.tab + row * kTabRow, prev, rnd, x2, colw);
-          }
-          if (next != kNone) __stcg(&nxt[next], post);     // :402-407 the successor starts from this state
-          if (c.traj) __stcg(&c.traj[p], post);
-          const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) detw[j] = (pw[j] >> 15) & kHalves;   // class 4: D <= 0
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { ccol[j] += colw[j]; cdet[j] += detw[j]; }
-
-        // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
-        // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
-        // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
-        // records that go elsewhere (transfers) add on their own.
-        {
-          // the ward-day most records of this chunk feed: same ward as the chunk's first record, next day (warp-uniform)
-          const uint32_t segl0 = __shfl_sync(0xFFFFFFFFu, info & kInfoSegMask, 0);
-          if (segl0 != wsegl) {
-            wsegl = segl0;
-            const uint32_t m = __ldg(&a.seg_main_next[seg0 + segl0]);
-            if (m != wmain) { flush_warp(); wmain = m; }
-          }
-          const bool has = nseg != kNone, mine = nseg == wmain;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pacc[j] += mine ? colw[j] : 0u;
-          if (has && !mine) {
-            uint32_t* dst = press + (int64_t)nseg * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) red_add(dst + j, colw[j]);
-          }
-        }
-        if (++since_flush == kFlushEvery) flush_counts();
-      }
-      flush_warp();
-      PHASE_ADD(1);  // records (thread 0's view)
-    }
-  }
-  flush_counts();
-  PHASE_ADD(2);  // totals
-}
-
-// Split-phase barrier among the CTAs of a team (the pattern of a cooperative-groups grid sync on a per-team counter;
-// the cooperative launch guarantees co-residency).  A team of one CTA only needs __syncthreads.
+// ---- team barrier ------------------------------------------------------------------------------------------------
+// The warps that share a team's slices (all warps of the team's CTAs) meet once per day: a warp may start day d+1 when
+// every warp of the team has finished day d (its successors' states and tomorrow's pressure are then complete).  Arrival
+// is a release increment of the team's counter by lane 0 after __syncwarp (which orders the other lanes' writes before
+// it); waiting is a relaxed poll by lane 0, one acquire fence, __syncwarp.  Nothing in the day loop synchronises a whole
+// CTA, so the latency of one warp's barrier or table build is covered by the other warps of the SM.  A team of one CTA
+// uses the hardware barrier instead.  The cooperative launch guarantees co-residency.
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -430,59 +258,328 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
 struct TeamBarrier {
   unsigned* ctr;
   unsigned target;
-  int G;
+  unsigned n_warps;   // warps of the team
+  bool one_cta;
   __device__ __forceinline__ void arrive() {
-    __syncthreads();
-    if (G > 1) {
-      target += (unsigned)G;
-      // release: the CTA's state / pressure writes are ordered before thread 0's increment by the bar.sync above
-      if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    }
+    if (one_cta) return;
+    __syncwarp();
+    target += n_warps;
+#ifdef AMRO_EXP_NOFENCE   // timing experiment only (breaks the ordering the barrier exists for)
+    if ((threadIdx.x & 31) == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#else
+    if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#endif
   }
   __device__ __forceinline__ void wait() {
-    if (G > 1) {
-      // acquire: poll relaxed, fence once; what another CTA wrote is read afterwards with ld.cg / atomics (L2)
-      if (threadIdx.x == 0) {
-        while ((int)(ld_relaxed(ctr) - target) < 0) {}
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      }
-      __syncthreads();
+    if (one_cta) { __syncthreads(); return; }
+    if ((threadIdx.x & 31) == 0) {
+      while ((int)(ld_relaxed(ctr) - target) < 0) {}
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
+    __syncwarp();
   }
 };
+
+// Everything a warp needs about its team (kNS adjacent slices of 8 simulations; a lane carries one record x 8*kNS sims).
+struct TeamCtx {
+  uint4* pre;          // [2][ring_chunks][kNS][32]
+  uint4* traj;         // [R][kNS] or nullptr
+  uint32_t* press;     // [n_seg][kNS][4]
+  uint32_t gslice0;    // global index of the team's first slice (Philox counter word 2)
+  int64_t sim0;        // first simulation of the team (run-relative)
+};
+
+// ---- tables of the ward-days [b0, b1) (indices within day d), built by ONE warp into its ring of table rows ----------
+// lane -> (slice, is_new, simulation): one ward-day per pass, both slices at once.
+template <bool REPLAY>
+__device__ __forceinline__ void build_tables(const WarpShared& sh, const SliceParams* par, const FastArgs& a, const TeamCtx& c,
+                                             int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
+  const int lane = threadIdx.x & 31;
+  // kNS == 2: the upper half-warp takes the second slice; kNS == 1: it takes the next ward-day
+  const int hi = lane >> 4, s = kNS == 2 ? hi : 0, h = (lane >> 3) & 1, k = lane & 7;
+  constexpr uint32_t kPerPass = kNS == 2 ? 1u : 2u;
+  const SliceParams& p = par[s];
+  const bool flag = h ? test_a : test_h;
+  const double rho = h ? p.rho_i[k] : p.rho_h[k];
+  const double beta = p.beta[k], alpha = p.alpha[k], alpha2 = p.alpha2[k], gamma = p.gamma[k];
+#pragma unroll 2
+  for (uint32_t sl0 = b0; sl0 < b1; sl0 += kPerPass) {
+    const uint32_t sl = kNS == 2 ? sl0 : min(sl0 + (uint32_t)hi, b1 - 1u);   // an odd tail is simply built twice
+    const int64_t seg = seg0 + sl;
+    const int slot = (int)(sl & (kWarpTableSegs - 1));
+    const uint32_t pk = __ldcg(&c.press[(seg * kNS + s) * 4 + (k >> 1)]);
+    const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
+    // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
+    const double F = __dmul_rn(__ddiv_rn(beta, __ldg(&a.seg_N[seg])), (double)cnt);
+    double P[3];
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, alpha, alpha2, gamma);
+    if constexpr (REPLAY) {
+#pragma unroll
+      for (int pc = 0; pc < 3; ++pc) sh.P[(((slot * 2 + h) * kNS + s) * 3 + pc) * 8 + k] = P[pc];
+    } else {
+      // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
+      // never re-tested (:131 / :134)
+      const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), c.gslice0 + (uint32_t)s, kStreamDither,
+                                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
+      uint32_t e[5];
+      e[0] = bernoulli14(P[0], r16);
+      e[1] = bernoulli14(P[1], r16);
+      e[2] = bernoulli14(P[2], r16);
+      e[3] = flag ? bernoulli14(__dmul_rn(clamp01(P[0]), rho), r16) : 0u;
+      e[4] = flag ? bernoulli14(__dmul_rn(clamp01(P[1]), rho), r16) : 0u;
+      // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
+        e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
+      }
+      if (!(k & 1)) {
+        uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + ((slot * 2 + h) * kNS + s) * kTabRow) + (k >> 1);
+        row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
+      }
+    }
+  }
+}
+
+// What a warp does on one day: its run [w0, w1) of the day's records (day-relative) and where they sit.  Static
+// (topology only), so it is computed BEFORE the warp waits for the previous day to complete.
+struct DayPlan {
+  int64_t da;          // first position of the day
+  int64_t seg0;        // first ward-day of the day
+  uint32_t w0, w1;     // the run; w0 is a multiple of 32
+  uint32_t sl_first, sl_last;   // ward-days (within the day) the run touches
+};
+__device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32_t gw, uint32_t n_gw) {
+  DayPlan p{};
+  if (d >= a.n_days) return p;
+  p.da = __ldg(&a.day_start[d]);
+  const uint32_t n = (uint32_t)(__ldg(&a.day_start[d + 1]) - p.da), n_chunks = (n + 31u) / 32u;
+  p.seg0 = __ldg(&a.day_seg_start[d]);
+  // the warp's run of 32-record chunks: consecutive trips stay in one ward for a while, so what the records add to
+  // tomorrow's pressure is kept in registers across trips
+  p.w0 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * gw) / n_gw));
+  p.w1 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * (gw + 1)) / n_gw));
+  if (p.w0 < p.w1) {
+    p.sl_first = __ldg(&a.meta[p.da + p.w0].x) & kInfoSegMask;
+    p.sl_last = __ldg(&a.meta[p.da + p.w1 - 1].x) & kInfoSegMask;
+  }
+  return p;
+}
+
+// ---- one day of the team's slices: the run of the day's records that belongs to this warp (abm_wards.cpp:384-407) ----
+template <bool REPLAY>
+__device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, const SliceParams* par, const FastArgs& a,
+                                            const TeamCtx& c, int64_t d, const DayPlan& pl, TeamBarrier& bar) {
+  const int lane = threadIdx.x & 31;
+  constexpr int kNW = kNS * 4;              // state words of a record: word s*4 + j = simulations 8s + 2j, 8s + 2j + 1
+  uint32_t ccol[kNW], cdet[kNW];            // per-lane day totals, packed halves
+#pragma unroll
+  for (int q = 0; q < kNW; ++q) ccol[q] = cdet[q] = 0;
+
+  // per-day totals (abm_wards.cpp:445-459 fused): per-lane halves -> packed 16-bit integers -> transposing butterfly over
+  // the warp (each step halves the registers and doubles the lanes summed) -> one RED per lane = (slice, metric, simulation)
+  auto flush_counts = [&]() {
+    constexpr int kRegs = kNS * 8;   // 8 or 16 registers of two packed counts
+    static_assert(kRegs == 8 || kRegs == 16, "butterfly sizes");
+    uint32_t r[kRegs];
+#pragma unroll
+    for (int q = 0; q < kNW; ++q) {     // per-lane counts are at most kFlushEvery: exact as halves, no carry between halves
+      r[(q >> 2) * 8 + (q & 3)] = h2_to_u16x2(ccol[q]);
+      r[(q >> 2) * 8 + 4 + (q & 3)] = h2_to_u16x2(cdet[q]);
+      ccol[q] = cdet[q] = 0;
+    }
+#pragma unroll
+    for (int w = kRegs / 2, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+      const bool up = (lane & bit) != 0;
+#pragma unroll
+      for (int q = 0; q < w; ++q) {
+        const uint32_t send = up ? r[q] : r[q + w], keep = up ? r[q + w] : r[q];
+        r[q] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, bit);
+      }
+    }
+#pragma unroll
+    for (int bit = 16 / kRegs; bit >= 1; bit >>= 1) r[0] += __shfl_xor_sync(0xFFFFFFFFu, r[0], bit);
+    // the register a lane ends up with: t = slice(0/1 bit) | metric(1) | word(2); its low / high half = simulations 2*word, 2*word+1
+    const int t = lane >> (kRegs == 16 ? 1 : 2);
+    const int sl = t >> 3, metric = (t >> 2) & 1, k = (t & 3) * 2 + (lane & 1);
+    const uint32_t v = (lane & 1) ? (r[0] >> 16) : (r[0] & 0xFFFFu);
+    int32_t* dst = metric ? a.counts_det : a.counts_col;
+    const bool emit = kRegs == 16 || !(lane & 2);
+    if (emit && v != 0 && dst && d < a.counts_ld) atomicAdd(&dst[d + a.counts_ld * (c.sim0 + sl * 8 + k)], (int)v);
+  };
+
+  if (pl.w0 < pl.w1) {
+    const int64_t ring = a.ring_chunks * (kNS * 32), da = pl.da, seg0 = pl.seg0;
+    const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
+    const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kNS * 32) + lane;   // this lane's slot of the run's first chunk
+    char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
+    const uint4* pm = a.meta + da + pl.w0 + lane;
+    uint4* pt = c.traj ? c.traj + (da + pl.w0 + lane) * kNS : nullptr;
+    const uint32_t x2 = kCodeA2 ^ ((kCodeZero - (uint32_t)a.ttd) * kHalves);   // A <-> "D = ttd" (:135 / :147)
+    int since_flush = 0;
+
+    uint32_t pacc[kNW], wmain = kNone, wsegl = 0xFFFFFFFFu;  // wmain / wsegl are warp-uniform
+#pragma unroll
+    for (int q = 0; q < kNW; ++q) pacc[q] = 0;
+    auto flush_warp = [&]() {
+      uint32_t v[kNW];
+#pragma unroll
+      for (int q = 0; q < kNW; ++q) { v[q] = __reduce_add_sync(0xFFFFFFFFu, h2_to_u16x2(pacc[q])); pacc[q] = 0; }
+      if (lane == 0 && wmain != kNone) {
+        uint32_t* dst = c.press + (int64_t)wmain * kNW;
+#pragma unroll
+        for (int q = 0; q < kNW; ++q) red_add(dst + q, v[q]);
+      }
+    };
+
+    // the ring of table rows holds ward-days [.., built_hi); start with what the run needs first
+    uint32_t built_hi = min(pl.sl_last + 1u, pl.sl_first + (uint32_t)kWarpTableSegs);
+    build_tables<REPLAY>(sh, par, a, c, seg0, pl.sl_first, built_hi, test_h, test_a);
+    __syncwarp();
+    PHASE_ADD(0);  // table
+
+    // software pipeline: the loads of the next trip are in flight while this one computes
+    const uint32_t n_run = pl.w1 - pl.w0;
+    uint4 n_meta = make_uint4(0u, kNone, kNone, 0u), n_prev[kNS];
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) n_prev[s] = make_uint4(0u, 0u, 0u, 0u);
+    if ((uint32_t)lane < n_run) {
+      n_meta = __ldg(pm);
+#pragma unroll
+      for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pc + s * 32);
+    }
+    for (uint32_t i = lane; i < n_run + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
+      const bool active = i < n_run;
+      const uint4 meta = n_meta;
+      uint4 prev[kNS];
+#pragma unroll
+      for (int s = 0; s < kNS; ++s) prev[s] = n_prev[s];
+      pm += 32; pc += kNS * 32;
+      n_meta = make_uint4(0u, kNone, kNone, 0u);
+      if (i + 32u < n_run) {
+        n_meta = __ldg(pm);
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pc + s * 32);
+      }
+      const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
+      const int h = (int)(info >> kInfoHShift);
+      const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
+      const bool any_init = __any_sync(0xFFFFFFFFu, active && src == kSrcInit);   // U0 only comes straight from the initial draw
+      const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, active ? segl : 0u);
+      uint32_t seg_lo = __shfl_sync(0xFFFFFFFFu, segl, 0);                          // lane 0 is active in every trip
+      bool pending = active;
+      for (;;) {   // one pass unless the 32 records span more ward-days than the table ring holds
+        const uint32_t seg_end = min(seg_hi + 1u, seg_lo + (uint32_t)kWarpTableSegs);
+        if (built_hi < seg_end) {
+          __syncwarp();
+          build_tables<REPLAY>(sh, par, a, c, seg0, max(built_hi, seg_lo), seg_end, test_h, test_a);
+          built_hi = seg_end;
+          __syncwarp();
+        }
+        const bool on = pending && segl < seg_end;
+        // lanes that are off step an uncolonised state against the all-zero row: nothing happens, nothing is stored
+        const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * 2 + h) * kNS : kZeroRow * kNS;
+        const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
+        uint32_t colw[kNW], detw[kNW];
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+          uint4 pre = prev[s];
+          if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
+          uint4 post;
+          if constexpr (REPLAY) {
+            post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
+          } else {
+            const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
+            if (any_init) post = step_record<true>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+            else post = step_record<false>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+          }
+          if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
+          if (pt && on) __stcg(pt + s, post);
+          const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                      // 1.0 per half-word: colonised (:477-485), D <= 0 (:500-509)
+            colw[s * 4 + j] = h2_ge_one(pw[j], kCodeA2);
+            detw[s * 4 + j] = h2_ge_one(pw[j], kCodeZero2);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kNW; ++q) { ccol[q] = h2_add(ccol[q], colw[q]); cdet[q] = h2_add(cdet[q], detw[q]); }
+
+        // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
+        // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
+        // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
+        // records that go elsewhere (transfers) add on their own.
+        if (seg_lo != wsegl) {   // seg_lo: the ward of the pass's first record (warp-uniform)
+          wsegl = seg_lo;
+          const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
+          if (m != wmain) { flush_warp(); wmain = m; }
+        }
+        const bool has = nseg != kNone, mine = nseg == wmain;
+        const uint32_t mine2 = mine ? kOne2 : 0u;
+#pragma unroll
+        for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
+        if (has && !mine) {
+          uint32_t* dst = c.press + (int64_t)nseg * kNW;
+#pragma unroll
+          for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> 10) & kHalves);   // 1.0 = 0x3C00 -> 1
+        }
+        pending = pending && !on;
+        if (!__any_sync(0xFFFFFFFFu, pending)) break;
+        seg_lo = __reduce_min_sync(0xFFFFFFFFu, pending ? segl : 0xFFFFFFFFu);
+      }
+      pt = pt ? pt + 32 * kNS : nullptr;
+      if (++since_flush == kFlushEvery) { flush_counts(); since_flush = 0; }
+    }
+    PHASE_ADD(1);  // records (thread 0's view)
+    flush_warp();
+  }
+  bar.arrive();   // tomorrow's pressure and states are out; the day totals below are nobody's input
+  PHASE_ADD(4);
+  flush_counts();
+  PHASE_ADD(2);  // totals
+}
 
 template <bool REPLAY, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SharedView sh = carve_shared<REPLAY>(smem_raw, a.table_segs);
-  const int tid = threadIdx.x;
+  constexpr int kWarps = THREADS / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SliceParams* par = reinterpret_cast<SliceParams*>(smem_raw);   // [kNS]
+  const WarpShared sh = carve_shared<REPLAY>(smem_raw + kNS * sizeof(SliceParams), warp);
   const int G = a.ctas_per_team;
-  const int64_t slice = blockIdx.x / G;                // one team per slice of 8 simulations
+  const int64_t team = blockIdx.x / G;                 // one team per kNS slices of 8 simulations
   const int rank = blockIdx.x % G;
-  TeamBarrier bar{a.team_barrier + slice, 0u, G};
-  const int64_t ring = a.max_rows_per_day;
+  const uint32_t gw = (uint32_t)(rank * kWarps + warp), n_gw = (uint32_t)(G * kWarps);   // this warp within its team
+  TeamBarrier bar{a.team_barrier + team, 0u, n_gw, G == 1};
+  const int64_t ring = a.ring_chunks * (kNS * 32);
 
-  SliceCtx c;
-  c.pre = a.pre + slice * 2 * ring;
-  c.traj = a.traj ? a.traj + slice * a.R : nullptr;
-  c.press = a.pressure + slice * a.n_seg * 4;
-  c.gslice = (uint32_t)((a.sim_offset >> 3) + (uint64_t)slice);
-  c.sim0 = slice * 8;
+  TeamCtx c;
+  c.pre = a.pre + team * 2 * ring;
+  c.traj = a.traj ? a.traj + team * a.R * kNS : nullptr;
+  c.press = a.pressure + team * a.n_seg * (kNS * 4);
+  c.gslice0 = (uint32_t)((a.sim_offset >> 3) + (uint64_t)team * kNS);
+  c.sim0 = team * (kNS * 8);
 
-  // ---- slice setup: parameters to shared memory, pressure zeroed ---------------------------------------------
-  if (tid < 48) {
-    const int col = tid >> 3, k = tid & 7;
-    const double v = a.params[(c.sim0 + k) + a.p_ld * col];
-    SliceParams& par = *sh.par;
-    double* dst = col == 0 ? par.alpha : col == 1 ? par.beta : col == 2 ? par.gamma : col == 3 ? par.rho_h
-                 : col == 4 ? par.alpha2 : par.rho_i;
+  // ---- team setup: parameters and the all-zero table row to shared memory, pressure zeroed -----------------------
+  if (tid < 48 * kNS) {
+    const int s = tid / 48, col = (tid % 48) >> 3, k = tid & 7;
+    const double v = a.params[(c.sim0 + s * 8 + k) + a.p_ld * col];
+    SliceParams& p = par[s];
+    double* dst = col == 0 ? p.alpha : col == 1 ? p.beta : col == 2 ? p.gamma : col == 3 ? p.rho_h : col == 4 ? p.alpha2 : p.rho_i;
     dst[k] = v;
   }
+  if constexpr (REPLAY) {
+    for (int q = lane; q < kNS * 24; q += 32) sh.P[kZeroRow * kNS * 24 + q] = 0.0;
+  } else {
+    for (int q = lane; q < kNS * kTabRow; q += 32) sh.tab[kZeroRow * kNS * kTabRow + q] = make_uint4(0u, 0u, 0u, 0u);
+  }
   {
-    const int64_t n = a.n_seg * 4, per = (n + G - 1) / G;
+    const int64_t n = a.n_seg * (kNS * 4), per = (n + G - 1) / G;
     const int64_t lo = rank * per, hi = min(n, lo + per);
     for (int64_t i = lo + tid; i < hi; i += THREADS) __stcg(&c.press[i], 0u);
   }
+  __syncthreads();   // parameters visible to every warp of the CTA
   bar.arrive();
   bar.wait();
 
@@ -493,46 +590,48 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
     for (int64_t r = lo + tid; r < hi; r += THREADS) {
       const uint32_t slot = a.init_slot[r];
       if (slot == kNone) continue;  // overwritten by a predecessor before it is ever read
-      uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
+#pragma unroll 1
+      for (int s = 0; s < kNS; ++s) {
+        uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int64_t sim = c.sim0 + k;
-        bool c0 = false, d0 = false;
-        if (sim < a.S) {
-          const double pc = a.icp[r * a.icp_rs + sim * a.icp_cs], pd = a.idp[r * a.idp_rs + sim * a.idp_cs];
-          if (REPLAY) {
-            c0 = a.u_icol[r + a.ui_ld * sim] < pc;
-            d0 = a.u_idet[r + a.ui_ld * sim] < pd;
-          } else {
-            c0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitCol) < threshold33(pc);
-            d0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitDet) < threshold33(pd);
+        for (int k = 0; k < 8; ++k) {
+          const int64_t sim = c.sim0 + s * 8 + k;
+          bool c0 = false, d0 = false;
+          if (sim < a.S) {
+            const double pc = a.icp[r * a.icp_rs + sim * a.icp_cs], pd = a.idp[r * a.idp_rs + sim * a.idp_cs];
+            if (REPLAY) {
+              c0 = a.u_icol[r + a.ui_ld * sim] < pc;
+              d0 = a.u_idet[r + a.ui_ld * sim] < pd;
+            } else {
+              c0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitCol) < threshold33(pc);
+              d0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitDet) < threshold33(pd);
+            }
           }
+          // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
+          //   uncolonised -> D = 0 (U0);  colonised, flag 0 -> D = 0: detected;  flag 1 -> D = 1: pending if
+          //   ttd >= 1, else (1 > ttd) it is neither pending nor detected and gets re-tested like D = inf
+          const uint32_t code = !c0 ? kCodeU0 : (!d0 ? kCodeZero : (a.ttd >= 1 ? kCodeZero - 1u : kCodeA));
+          w[k >> 1] |= code << (16 * (k & 1));
+          cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
         }
-        // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
-        //   uncolonised -> D = 0 (U0);  colonised, flag 0 -> D = 0: detected;  flag 1 -> D = 1: pending if
-        //   ttd >= 1, else (1 > ttd) it is neither pending nor detected and gets re-tested like D = inf
-        const uint32_t code = !c0 ? kCodeU0 : (!d0 ? kCodeZero : (a.ttd >= 1 ? kCodeZero - 1u : kCodeA));
-        w[k >> 1] |= code << (16 * (k & 1));
-        cw[k >> 1] |= (c0 ? 1u : 0u) << (16 * (k & 1));
-      }
-      __stcg(&c.pre[slot], make_uint4(w[0], w[1], w[2], w[3]));
-      const uint32_t iseg = a.init_seg[r];
+        __stcg(&c.pre[ring_slot(slot) + s * 32], make_uint4(w[0], w[1], w[2], w[3]));
+        const uint32_t iseg = a.init_seg[r];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&c.press[(int64_t)iseg * 4 + j], cw[j]);
+        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&c.press[((int64_t)iseg * kNS + s) * 4 + j], cw[j]);
+      }
     }
   }
   bar.arrive();
 
   // ---- day loop (abm_wards.cpp:381): one team barrier per day ----------------------------------------------
   PHASE_T0();
+  DayPlan plan = plan_day(a, 0, gw, n_gw);
   for (int64_t d = 0; d < a.n_days; ++d) {
     bar.wait();
     PHASE_ADD(3);  // team barrier wait
-    process_day<REPLAY, THREADS>(PHASE_ARG sh, a, c, d, rank, G);
-    bar.arrive();
-    PHASE_ADD(4);  // arrive
+    process_day<REPLAY>(PHASE_ARG sh, par, a, c, d, plan, bar);
+    plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
   }
-  bar.wait();
 }
 
 // ---- packed trajectory -> the reference's float64 columns ------------------------------------------------------
@@ -543,18 +642,17 @@ __global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __r
   const int64_t n_sl = (ns + 7) / 8;  // s0 is a multiple of 8
   if (i >= R * n_sl) return;
   const int64_t r = i % R, sl = i / R;
-  const int64_t slice = s0 / 8 + sl;
+  const int64_t slice = s0 / 8 + sl, team = slice / kNS, in_team = slice % kNS;
   const int64_t p = pos_of ? pos_of[r] : r;
-  const uint4 v = __ldg(&traj[slice * R + p]);
+  const uint4 v = __ldg(&traj[(team * R + p) * kNS + in_team]);
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int64_t s = sl * 8 + k;
     if (s >= ns || s0 + s >= S) break;
     const uint32_t x = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-    const uint32_t cls = x >> kClsShift;
-    Cout[r + ld * s] = (cls == kClsA || cls >= kClsPn) ? 1.0 : 0.0;
-    Dout[r + ld * s] = (cls >= kClsPn) ? (double)((int)kCodeZero - (int)x) : __longlong_as_double(0x7FF0000000000000ll);
+    Cout[r + ld * s] = (x >= kCodeA) ? 1.0 : 0.0;
+    Dout[r + ld * s] = (x >= kCodeCnt) ? (double)((int)kCodeZero - (int)x) : __longlong_as_double(0x7FF0000000000000ll);
   }
 }
 
@@ -564,7 +662,8 @@ __global__ void k_fast_export_pressure(const uint32_t* __restrict__ pressure, in
   if (i >= n_seg * S) return;
   const int64_t seg = i % n_seg, s = i / n_seg;
   const int k = (int)(s & 7);
-  const uint32_t w = pressure[((s >> 3) * n_seg + seg) * 4 + (k >> 1)];
+  const int64_t slice = s >> 3, team = slice / kNS, in_team = slice % kNS;
+  const uint32_t w = pressure[((team * n_seg + seg) * kNS + in_team) * 4 + (k >> 1)];
   out[seg + ld * s] = (int32_t)((w >> (16 * (k & 1))) & 0xFFFFu);
 }
 }  // namespace
@@ -588,13 +687,13 @@ const void* kernel_ptr(int shape) {
 }
 }  // namespace
 
-size_t fast_shared_bytes(bool replay, int table_segs) { return fast_smem_bytes(replay, table_segs); }
 int fast_threads(int shape) { return shape == kShapeWide ? kWideThreads : kTeamThreads; }
+size_t fast_shared_bytes(bool replay, int shape) { return fast_smem_bytes(replay, fast_threads(shape)); }
 
-int fast_max_coresident_ctas(int device, bool replay, int shape, int table_segs) {
+int fast_max_coresident_ctas(int device, bool replay, int shape) {
   int per_sm = 0, sms = 0;
   const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
-  const size_t smem = fast_smem_bytes(replay, table_segs);
+  const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, fast_threads(shape), smem));
@@ -603,7 +702,7 @@ int fast_max_coresident_ctas(int device, bool replay, int shape, int table_segs)
 
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid) {
   const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
-  const size_t smem = fast_smem_bytes(replay, a.table_segs);
+  const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
   if (a.ctas_per_team > 1)

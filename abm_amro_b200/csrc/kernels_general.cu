@@ -91,13 +91,13 @@ __global__ void k_gen_update(GenArgs a, int64_t row_begin, int64_t row_end, int6
   if (a.p_out) a.p_out[r + a.p_out_ld * s] = P;
 
   bool col;
-  uint32_t v15 = 0, r16 = 0;
+  uint32_t v14 = 0, r16 = 0;
   if (a.replay) {
     col = a.u_col[r + a.u_ld * s] < P;                                                 // :116
-  } else {  // rng.cuh: 15-bit draw against the threshold dithered per (ward-day, simulation)
-    v15 = philox_chunk(a.seed, (uint64_t)r, a.sim_offset + s, kStreamStep) & 0x7FFFu;
+  } else {  // rng.cuh: 14-bit draw against the threshold dithered per (ward-day, simulation)
+    v14 = philox_chunk(a.seed, (uint64_t)r, a.sim_offset + s, kStreamStep) & 0x3FFFu;
     r16 = philox_chunk(a.seed, (uint64_t)a.seg_of_pos[p], a.sim_offset + s, kStreamDither);
-    col = v15 + bernoulli15(P, r16) >= 0x8000u;
+    col = v14 < bernoulli14(P, r16);
   }
   const bool h0 = (h == 0.0), h1 = (h == 1.0);
   if (col && (h0 || h1)) {                                                             // :129 / :141
@@ -109,7 +109,7 @@ __global__ void k_gen_update(GenArgs a, int64_t row_begin, int64_t row_end, int6
       bool hit = false;
       if (flag) {
         if (a.replay) hit = a.u_det[r + a.u_ld * s] <= rho;                            // :134 / :146
-        else hit = v15 + bernoulli15(__dmul_rn(clamp01(P), rho), r16) >= 0x8000u;
+        else hit = v14 < bernoulli14(__dmul_rn(clamp01(P), rho), r16);
       }
       d = hit ? (double)a.ttd : dinf();                                                // :135,138
     }

@@ -4,13 +4,14 @@
 // (index_lo, index_hi, sim_group, stream).  One call yields 128 bits = eight 16-bit chunks, one per
 // simulation of a group of 8 consecutive simulations.
 //
-// Daily step (stream 0, index = patient-day record): the draw of (record, simulation) is v15 = chunk & 0x7FFF and
-//     Bernoulli(p) fires  <=>  v15 + B(p) >= 2^15,      B(p) = (T31(p) + r16) >> 16  in [0, 2^15],
-// with T31(p) = ceil(p * 2^31) (0 for p <= 0 or NaN, 2^31 for p >= 1) and r16 the DITHER of the record's ward-day:
-// the 16-bit chunk of (stream 6, index = ward-day, simulation).  Rounding the 31-bit threshold to 15 bits with a
-// uniform dither keeps the probability of every draw exact to 2^-31 (E[B(p)] = T31(p) / 2^16; "never" and "always"
-// stay exact) while the kernel compares 15 bits per update; draws of the records of one ward-day and simulation are
-// coupled only through the shared dither, by less than 2^-32 in any joint probability.
+// Daily step (stream 0, index = patient-day record): the draw of (record, simulation) is v14 = chunk & 0x3FFF and
+//     Bernoulli(p) fires  <=>  v14 < B(p),      B(p) = (T30(p) + r16) >> 16  in [0, 2^14],
+// with T30(p) = ceil(p * 2^30) (0 for p <= 0 or NaN, 2^30 for p >= 1) and r16 the DITHER of the record's ward-day:
+// the 16-bit chunk of (stream 6, index = ward-day, simulation).  Rounding the 30-bit threshold to 14 bits with a
+// uniform dither keeps the probability of every draw exact to 2^-30 (E[B(p)] = T30(p) / 2^16; "never" and "always"
+// stay exact) while the kernel compares 14 bits per update -- as packed fp16 compares: every 14-bit pattern is a finite
+// non-negative half whose order is the integer order.  Draws of the records of one ward-day and simulation are coupled
+// only through the shared dither, by less than 2^-30 in any joint probability.
 // Initial state (streams 2..5, index = initial row): 32-bit uniform (chunk << 16 | chunk of stream+1) < T(p), T(p) =
 // #{r : r * 2^-32 < p}.
 #pragma once
@@ -52,13 +53,13 @@ __device__ __forceinline__ uint64_t threshold33(double p) {
   return __double2ull_ru(p * 4294967296.0);  // exact product (power of two), rounded up = ceil
 }
 
-// T31(p) and the dithered 15-bit threshold B(p) of the daily step
-__device__ __forceinline__ uint32_t threshold31(double p) {
+// T30(p) and the dithered 14-bit threshold B(p) of the daily step
+__device__ __forceinline__ uint32_t threshold30(double p) {
   if (!(p > 0.0)) return 0u;
-  if (p >= 1.0) return 1u << 31;
-  return (uint32_t)__double2ull_ru(p * 2147483648.0);  // exact product (power of two), rounded up = ceil
+  if (p >= 1.0) return 1u << 30;
+  return (uint32_t)__double2ull_ru(p * 1073741824.0);  // exact product (power of two), rounded up = ceil
 }
-__device__ __forceinline__ uint32_t bernoulli15(double p, uint32_t r16) { return (threshold31(p) + r16) >> 16; }
+__device__ __forceinline__ uint32_t bernoulli14(double p, uint32_t r16) { return (threshold30(p) + r16) >> 16; }
 
 __device__ __forceinline__ double clamp01(double p) { return p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p); }
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t row, uint
   return (chunk16(a, k) << 16) | chunk16(b, k);
 }
 
-// 16-bit chunk of (index, global sim, stream): the daily draw (stream 0, & 0x7FFF) and the ward-day dither (stream 6)
+// 16-bit chunk of (index, global sim, stream): the daily draw (stream 0, & 0x3FFF) and the ward-day dither (stream 6)
 __device__ __forceinline__ uint32_t philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
   const uint4 a = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream, (uint32_t)seed,
                                 (uint32_t)(seed >> 32));

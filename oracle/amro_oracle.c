@@ -84,9 +84,9 @@ uint64_t amro_oracle_threshold(double p) {
 
 /* RNG spec, daily step (abm_amro_b200/csrc/rng.cuh): one Philox call, counter (index_lo, index_hi, sim >> 3, stream),
  * serves the 8 simulations of a sim-group; simulation k = sim & 7 owns the 16-bit chunk (word[k>>1] >> 16*(k&1)).
- * The draw of (row, sim) is v15 = chunk(stream 0, row) & 0x7FFF and Bernoulli(p) fires iff v15 + B(p) >= 2^15 with
- * B(p) = (T31(p) + r16) >> 16, T31(p) = ceil(p * 2^31) clamped to [0, 2^31], r16 = chunk(stream 6, ward-day): the
- * 31-bit threshold is rounded to 15 bits with a dither shared by the ward-day, so E[B(p)] = T31(p) / 2^16 exactly. */
+ * The draw of (row, sim) is v14 = chunk(stream 0, row) & 0x3FFF and Bernoulli(p) fires iff v14 < B(p) with
+ * B(p) = (T30(p) + r16) >> 16, T30(p) = ceil(p * 2^30) clamped to [0, 2^30], r16 = chunk(stream 6, ward-day): the
+ * 30-bit threshold is rounded to 14 bits with a dither shared by the ward-day, so E[B(p)] = T30(p) / 2^16 exactly. */
 uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream};
@@ -95,12 +95,12 @@ uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, u
   unsigned k = (unsigned)(sim & 7u);
   return (a[k >> 1] >> (16u * (k & 1u))) & 0xFFFFu;
 }
-uint32_t amro_oracle_threshold31(double p) {
+uint32_t amro_oracle_threshold30(double p) {
   if (!(p > 0.0)) return 0;
-  if (p >= 1.0) return 1u << 31;
-  return (uint32_t)ceil(p * 2147483648.0);
+  if (p >= 1.0) return 1u << 30;
+  return (uint32_t)ceil(p * 1073741824.0);
 }
-uint32_t amro_oracle_bernoulli15(double p, uint32_t r16) { return (amro_oracle_threshold31(p) + r16) >> 16; }
+uint32_t amro_oracle_bernoulli14(double p, uint32_t r16) { return (amro_oracle_threshold30(p) + r16) >> 16; }
 
 /* RNG spec, initial state: the 32-bit uniform of (row, sim, kind) is (chunk of stream 2*kind) << 16 | chunk of stream
  * 2*kind + 1, compared with T(p) = #{r : r * 2^-32 < p}. */
@@ -171,13 +171,13 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
       const double p = prob[i], h = AT(wm, ld, i, H);
       double* D = &AT(wm, ld, i, dc);
       int col, tie_kind = rng->kind;
-      uint32_t v15 = 0, r16 = 0;
+      uint32_t v14 = 0, r16 = 0;
       if (p_out) p_out[gid + p_out_ld * s] = p;
       /* :116-120 colonisation draw, always taken */
       if (tie_kind == AMRO_ORACLE_RNG_PHILOX) {
-        v15 = amro_oracle_philox_chunk(rng->seed, gid, rng->sim_offset + s, 0) & 0x7FFFu;
+        v14 = amro_oracle_philox_chunk(rng->seed, gid, rng->sim_offset + s, 0) & 0x3FFFu;
         r16 = amro_oracle_philox_chunk(rng->seed, rng->ward_day, rng->sim_offset + s, 6);
-        col = v15 + amro_oracle_bernoulli15(p, r16) >= 0x8000u;
+        col = v14 < amro_oracle_bernoulli14(p, r16);
         rng->n_draws++;
       } else {
         double u;
@@ -201,7 +201,7 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
           int hit = 0;
           if (flag) {                                                      /* short-circuit: draw only if testing today */
             if (tie_kind == AMRO_ORACLE_RNG_PHILOX) {
-              hit = v15 + amro_oracle_bernoulli15(clamp01(p) * rho, r16) >= 0x8000u; /* same uniform: P(col and hit) = p*rho */
+              hit = v14 < amro_oracle_bernoulli14(clamp01(p) * rho, r16); /* same uniform: P(col and hit) = p*rho */
             } else {
               double u2;
               if (tie_kind == AMRO_ORACLE_RNG_GLIBC) u2 = glibc_randu();

@@ -68,10 +68,10 @@ void     amro_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2],
 uint64_t amro_oracle_threshold(double p);
 /* the 32-bit uniform integer the spec assigns to (row, global sim, draw kind 0=step 1=init-col 2=init-det) */
 uint32_t amro_oracle_philox_u32(uint64_t seed, uint64_t row, uint64_t sim, uint32_t kind);
-/* daily step: 16-bit chunk of (index, sim, stream), 31-bit threshold and its dithered 15-bit rounding */
+/* daily step: 16-bit chunk of (index, sim, stream), 30-bit threshold and its dithered 14-bit rounding */
 uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream);
-uint32_t amro_oracle_threshold31(double p);
-uint32_t amro_oracle_bernoulli15(double p, uint32_t r16);
+uint32_t amro_oracle_threshold30(double p);
+uint32_t amro_oracle_bernoulli14(double p, uint32_t r16);
 
 /* reference progress_patients_probability_ward_1_timestep, abm_wards.cpp:70-159.
  * row_ids[i] = global row index of local row i (NULL = identity); p_out (optional) receives the

@@ -1,7 +1,9 @@
-"""Development: per-phase cycle breakdown of the fast kernel (needs the `phases` variant)."""
+"""Development: per-phase cycle breakdown of the fast kernel (needs a variant built with -DAMRO_PROFILE_PHASES;
+AMRO_B200_LIB selects it, default lib_variants/phases)."""
 import ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["AMRO_B200_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "abm_amro_b200/lib_variants/phases/libamro_b200.so")
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root)
+os.environ.setdefault("AMRO_B200_LIB", os.path.join(root, "abm_amro_b200/lib_variants/phases/libamro_b200.so"))
 import numpy as np
 from abm_amro_b200 import capi, engine, synth
 wm, tp, n_init = synth.make_hospital(30, 10000, 365, seed=1)
