@@ -103,6 +103,10 @@ __device__ __forceinline__ uint32_t h2_to_u16x2(uint32_t x) {
 
 struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
   double alpha[8], beta[8], gamma[8], rho_h[8], alpha2[8], rho_i[8];
+  // 30-bit thresholds that do not depend on the ward-day (finite force of infection), [kind][is_new][simulation]:
+  // kind 0: stays colonised, undetected (1 - alpha + gamma h); 1: stays colonised, detected (1 - alpha2 + gamma h);
+  // 2: kind 0 and tested positive (clamp(P) * rho)
+  uint32_t t30[3][2][8];
 };
 
 // Transition probability for unit weight (W = C), force of infection F -- the reference's expression order, one
@@ -216,6 +220,11 @@ __device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, cons
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// first day only (U0 present): out of line, the record loop stays small
+__device__ __forceinline__ uint4 step_record_first(const uint4* __restrict__ tab, const uint4 pre, const uint4 rnd, uint32_t x2) {
+  return step_record<true>(tab, pre, rnd, x2);
+}
+
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
 __device__ __forceinline__ uint4 step_record_replay(const WarpShared& sh, const SliceParams& par, const FastArgs& a, const uint4 pre, int row, int h,
                                                     int64_t orig, int64_t sim0, bool flag, bool on) {
@@ -291,9 +300,13 @@ struct TeamCtx {
 
 // ---- tables of the ward-days [b0, b1) (indices within day d), built by ONE warp into its ring of table rows ----------
 // lane -> (slice, is_new, simulation): one ward-day per pass, both slices at once.
+
+// The probabilities of colonised patients (:103-112 with W = 1) do not depend on the ward's pressure unless the force of
+// infection is not finite (N = 0): their 30-bit thresholds are evaluated once per run (SliceParams::t30) and only the
+// ward-day's dither is added here; a non-finite force takes the general expression.
 template <bool REPLAY>
-__device__ __forceinline__ void build_tables(const WarpShared& sh, const SliceParams* par, const FastArgs& a, const TeamCtx& c,
-                                             int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
+__device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* par, const FastArgs& a, const uint32_t* press, uint32_t gslice0,
+                                          int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
   const int lane = threadIdx.x & 31;
   // kNS == 2: the upper half-warp takes the second slice; kNS == 1: it takes the next ward-day
   const int hi = lane >> 4, s = kNS == 2 ? hi : 0, h = (lane >> 3) & 1, k = lane & 7;
@@ -302,32 +315,40 @@ __device__ __forceinline__ void build_tables(const WarpShared& sh, const SlicePa
   const bool flag = h ? test_a : test_h;
   const double rho = h ? p.rho_i[k] : p.rho_h[k];
   const double beta = p.beta[k], alpha = p.alpha[k], alpha2 = p.alpha2[k], gamma = p.gamma[k];
-#pragma unroll 2
+#pragma unroll 1
   for (uint32_t sl0 = b0; sl0 < b1; sl0 += kPerPass) {
     const uint32_t sl = kNS == 2 ? sl0 : min(sl0 + (uint32_t)hi, b1 - 1u);   // an odd tail is simply built twice
     const int64_t seg = seg0 + sl;
     const int slot = (int)(sl & (kWarpTableSegs - 1));
-    const uint32_t pk = __ldcg(&c.press[(seg * kNS + s) * 4 + (k >> 1)]);
+    const uint32_t pk = __ldcg(&press[(seg * kNS + s) * 4 + (k >> 1)]);
     const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
     // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
     const double F = __dmul_rn(__ddiv_rn(beta, __ldg(&a.seg_N[seg])), (double)cnt);
-    double P[3];
-#pragma unroll
-    for (int pc = 0; pc < 3; ++pc) P[pc] = class_probability(pc, h, F, alpha, alpha2, gamma);
+    const bool finite = fabs(F) <= 1.7976931348623157e308;
     if constexpr (REPLAY) {
 #pragma unroll
-      for (int pc = 0; pc < 3; ++pc) sh.P[(((slot * 2 + h) * kNS + s) * 3 + pc) * 8 + k] = P[pc];
+      for (int pc = 0; pc < 3; ++pc) sh.P[(((slot * 2 + h) * kNS + s) * 3 + pc) * 8 + k] = class_probability(pc, h, F, alpha, alpha2, gamma);
     } else {
       // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
       // never re-tested (:131 / :134)
-      const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), c.gslice0 + (uint32_t)s, kStreamDither,
+      const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gslice0 + (uint32_t)s, kStreamDither,
                                                  (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
+      const double P0 = class_probability(0, h, F, alpha, alpha2, gamma);
+      uint32_t t30[5];
+      t30[0] = threshold30(P0);
+      t30[3] = threshold30(__dmul_rn(clamp01(P0), rho));
+      if (finite) {
+        t30[1] = p.t30[0][h][k]; t30[2] = p.t30[1][h][k]; t30[4] = p.t30[2][h][k];
+      } else {
+        const double P1 = class_probability(1, h, F, alpha, alpha2, gamma);
+        t30[1] = threshold30(P1);
+        t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma));
+        t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
+      }
       uint32_t e[5];
-      e[0] = bernoulli14(P[0], r16);
-      e[1] = bernoulli14(P[1], r16);
-      e[2] = bernoulli14(P[2], r16);
-      e[3] = flag ? bernoulli14(__dmul_rn(clamp01(P[0]), rho), r16) : 0u;
-      e[4] = flag ? bernoulli14(__dmul_rn(clamp01(P[1]), rho), r16) : 0u;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
+      if (!flag) e[3] = e[4] = 0u;
       // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
@@ -339,6 +360,50 @@ __device__ __forceinline__ void build_tables(const WarpShared& sh, const SlicePa
         row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
       }
     }
+  }
+}
+
+// Per-day totals (abm_wards.cpp:445-459 fused), out of line (once per warp and day): per-lane halves -> packed 16-bit
+// integers -> transposing butterfly over the warp (each step halves the registers and doubles the lanes summed) -> one RED
+// per lane = (slice, metric, simulation).  cnt[q] / cnt[kNS*4 + q]: colonised / detected counts of state word q.
+__device__ __forceinline__ void flush_day_counts(const FastArgs& a, int64_t d, int64_t sim0, const uint32_t (&cnt)[kNS * 8]) {
+  const int lane = threadIdx.x & 31;
+  constexpr int kRegs = kNS * 8;   // 8 or 16 registers of two packed counts
+  static_assert(kRegs == 8 || kRegs == 16, "butterfly sizes");
+  uint32_t r[kRegs];
+#pragma unroll
+  for (int q = 0; q < kNS * 4; ++q) {     // per-lane counts are at most kFlushEvery: exact as halves, no carry between halves
+    r[(q >> 2) * 8 + (q & 3)] = h2_to_u16x2(cnt[q]);
+    r[(q >> 2) * 8 + 4 + (q & 3)] = h2_to_u16x2(cnt[kNS * 4 + q]);
+  }
+#pragma unroll
+  for (int w = kRegs / 2, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int q = 0; q < w; ++q) {
+      const uint32_t send = up ? r[q] : r[q + w], keep = up ? r[q + w] : r[q];
+      r[q] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, bit);
+    }
+  }
+#pragma unroll
+  for (int bit = 16 / kRegs; bit >= 1; bit >>= 1) r[0] += __shfl_xor_sync(0xFFFFFFFFu, r[0], bit);
+  // the register a lane ends up with: t = slice(0/1 bit) | metric(1) | word(2); its low / high half = simulations 2*word, 2*word+1
+  const int t = lane >> (kRegs == 16 ? 1 : 2);
+  const int sl = t >> 3, metric = (t >> 2) & 1, k = (t & 3) * 2 + (lane & 1);
+  const uint32_t v = (lane & 1) ? (r[0] >> 16) : (r[0] & 0xFFFFu);
+  int32_t* dst = metric ? a.counts_det : a.counts_col;
+  const bool emit = kRegs == 16 || !(lane & 2);
+  if (emit && v != 0 && dst && d < a.counts_ld) atomicAdd(&dst[d + a.counts_ld * (sim0 + sl * 8 + k)], (int)v);
+}
+
+// What the warp's records add to the ward-day most of them feed (warp-accumulated halves -> one RED per word), out of line.
+__device__ __forceinline__ void push_pressure(uint32_t* dst, const uint32_t (&acc)[kNS * 4]) {
+  uint32_t v[kNS * 4];
+#pragma unroll
+  for (int q = 0; q < kNS * 4; ++q) v[q] = __reduce_add_sync(0xFFFFFFFFu, h2_to_u16x2(acc[q]));
+  if ((threadIdx.x & 31) == 0 && dst) {
+#pragma unroll
+    for (int q = 0; q < kNS * 4; ++q) red_add(dst + q, v[q]);
   }
 }
 
@@ -377,36 +442,11 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
 #pragma unroll
   for (int q = 0; q < kNW; ++q) ccol[q] = cdet[q] = 0;
 
-  // per-day totals (abm_wards.cpp:445-459 fused): per-lane halves -> packed 16-bit integers -> transposing butterfly over
-  // the warp (each step halves the registers and doubles the lanes summed) -> one RED per lane = (slice, metric, simulation)
   auto flush_counts = [&]() {
-    constexpr int kRegs = kNS * 8;   // 8 or 16 registers of two packed counts
-    static_assert(kRegs == 8 || kRegs == 16, "butterfly sizes");
-    uint32_t r[kRegs];
+    uint32_t cnt[kNS * 8];
 #pragma unroll
-    for (int q = 0; q < kNW; ++q) {     // per-lane counts are at most kFlushEvery: exact as halves, no carry between halves
-      r[(q >> 2) * 8 + (q & 3)] = h2_to_u16x2(ccol[q]);
-      r[(q >> 2) * 8 + 4 + (q & 3)] = h2_to_u16x2(cdet[q]);
-      ccol[q] = cdet[q] = 0;
-    }
-#pragma unroll
-    for (int w = kRegs / 2, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-      const bool up = (lane & bit) != 0;
-#pragma unroll
-      for (int q = 0; q < w; ++q) {
-        const uint32_t send = up ? r[q] : r[q + w], keep = up ? r[q + w] : r[q];
-        r[q] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, bit);
-      }
-    }
-#pragma unroll
-    for (int bit = 16 / kRegs; bit >= 1; bit >>= 1) r[0] += __shfl_xor_sync(0xFFFFFFFFu, r[0], bit);
-    // the register a lane ends up with: t = slice(0/1 bit) | metric(1) | word(2); its low / high half = simulations 2*word, 2*word+1
-    const int t = lane >> (kRegs == 16 ? 1 : 2);
-    const int sl = t >> 3, metric = (t >> 2) & 1, k = (t & 3) * 2 + (lane & 1);
-    const uint32_t v = (lane & 1) ? (r[0] >> 16) : (r[0] & 0xFFFFu);
-    int32_t* dst = metric ? a.counts_det : a.counts_col;
-    const bool emit = kRegs == 16 || !(lane & 2);
-    if (emit && v != 0 && dst && d < a.counts_ld) atomicAdd(&dst[d + a.counts_ld * (c.sim0 + sl * 8 + k)], (int)v);
+    for (int q = 0; q < kNW; ++q) { cnt[q] = ccol[q]; cnt[kNW + q] = cdet[q]; ccol[q] = cdet[q] = 0; }
+    flush_day_counts(a, d, c.sim0, cnt);
   };
 
   if (pl.w0 < pl.w1) {
@@ -417,25 +457,20 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     const uint4* pm = a.meta + da + pl.w0 + lane;
     uint4* pt = c.traj ? c.traj + (da + pl.w0 + lane) * kNS : nullptr;
     const uint32_t x2 = kCodeA2 ^ ((kCodeZero - (uint32_t)a.ttd) * kHalves);   // A <-> "D = ttd" (:135 / :147)
-    int since_flush = 0;
 
     uint32_t pacc[kNW], wmain = kNone, wsegl = 0xFFFFFFFFu;  // wmain / wsegl are warp-uniform
 #pragma unroll
     for (int q = 0; q < kNW; ++q) pacc[q] = 0;
     auto flush_warp = [&]() {
-      uint32_t v[kNW];
+      uint32_t acc[kNW];   // a copy: the accumulators themselves must stay in registers
 #pragma unroll
-      for (int q = 0; q < kNW; ++q) { v[q] = __reduce_add_sync(0xFFFFFFFFu, h2_to_u16x2(pacc[q])); pacc[q] = 0; }
-      if (lane == 0 && wmain != kNone) {
-        uint32_t* dst = c.press + (int64_t)wmain * kNW;
-#pragma unroll
-        for (int q = 0; q < kNW; ++q) red_add(dst + q, v[q]);
-      }
+      for (int q = 0; q < kNW; ++q) { acc[q] = pacc[q]; pacc[q] = 0; }
+      push_pressure(wmain != kNone ? c.press + (int64_t)wmain * kNW : nullptr, acc);
     };
 
     // the ring of table rows holds ward-days [.., built_hi); start with what the run needs first
     uint32_t built_hi = min(pl.sl_last + 1u, pl.sl_first + (uint32_t)kWarpTableSegs);
-    build_tables<REPLAY>(sh, par, a, c, seg0, pl.sl_first, built_hi, test_h, test_a);
+    build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, pl.sl_first, built_hi, test_h, test_a);
     __syncwarp();
     PHASE_ADD(0);  // table
 
@@ -449,7 +484,15 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
 #pragma unroll
       for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pc + s * 32);
     }
-    for (uint32_t i = lane; i < n_run + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
+    // blocks of at most kFlushEvery trips: the per-lane half counters stay exact; the flush between blocks is outside the
+    // trip loop proper
+    for (uint32_t blk = 0; blk < n_run; blk += 32u * kFlushEvery) {
+    if (blk) flush_counts();
+    const uint32_t blk_end = min(n_run, blk + 32u * kFlushEvery);
+#ifdef AMRO_TRIP_UNROLL
+#pragma unroll AMRO_TRIP_UNROLL
+#endif
+    for (uint32_t i = blk + lane; i < blk_end + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
       const bool active = i < n_run;
       const uint4 meta = n_meta;
       uint4 prev[kNS];
@@ -471,9 +514,9 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
       bool pending = active;
       for (;;) {   // one pass unless the 32 records span more ward-days than the table ring holds
         const uint32_t seg_end = min(seg_hi + 1u, seg_lo + (uint32_t)kWarpTableSegs);
-        if (built_hi < seg_end) {
+        if (__builtin_expect(built_hi < seg_end, 0)) {
           __syncwarp();
-          build_tables<REPLAY>(sh, par, a, c, seg0, max(built_hi, seg_lo), seg_end, test_h, test_a);
+          build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, max(built_hi, seg_lo), seg_end, test_h, test_a);
           built_hi = seg_end;
           __syncwarp();
         }
@@ -491,7 +534,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
             post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
           } else {
             const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
-            if (any_init) post = step_record<true>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+            if (__builtin_expect(any_init, 0)) post = step_record_first(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
             else post = step_record<false>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
           }
           if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
@@ -510,7 +553,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
         // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
         // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
         // records that go elsewhere (transfers) add on their own.
-        if (seg_lo != wsegl) {   // seg_lo: the ward of the pass's first record (warp-uniform)
+        if (__builtin_expect(seg_lo != wsegl, 0)) {   // seg_lo: the ward of the pass's first record (warp-uniform)
           wsegl = seg_lo;
           const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
           if (m != wmain) { flush_warp(); wmain = m; }
@@ -525,11 +568,11 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> 10) & kHalves);   // 1.0 = 0x3C00 -> 1
         }
         pending = pending && !on;
-        if (!__any_sync(0xFFFFFFFFu, pending)) break;
+        if (__builtin_expect(!__any_sync(0xFFFFFFFFu, pending), 1)) break;
         seg_lo = __reduce_min_sync(0xFFFFFFFFu, pending ? segl : 0xFFFFFFFFu);
       }
       pt = pt ? pt + 32 * kNS : nullptr;
-      if (++since_flush == kFlushEvery) { flush_counts(); since_flush = 0; }
+    }
     }
     PHASE_ADD(1);  // records (thread 0's view)
     flush_warp();
@@ -578,6 +621,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
     const int64_t n = a.n_seg * (kNS * 4), per = (n + G - 1) / G;
     const int64_t lo = rank * per, hi = min(n, lo + per);
     for (int64_t i = lo + tid; i < hi; i += THREADS) __stcg(&c.press[i], 0u);
+  }
+  __syncthreads();
+  if (tid < 16 * kNS) {   // thresholds of colonised patients under a finite force of infection (0 * F = 0)
+    const int s = tid >> 4, h = (tid >> 3) & 1, k = tid & 7;
+    SliceParams& p = par[s];
+    const double P1 = class_probability(1, h, 0.0, p.alpha[k], p.alpha2[k], p.gamma[k]);
+    const double P2 = class_probability(2, h, 0.0, p.alpha[k], p.alpha2[k], p.gamma[k]);
+    p.t30[0][h][k] = threshold30(P1);
+    p.t30[1][h][k] = threshold30(P2);
+    p.t30[2][h][k] = threshold30(__dmul_rn(clamp01(P1), h ? p.rho_i[k] : p.rho_h[k]));
   }
   __syncthreads();   // parameters visible to every warp of the CTA
   bar.arrive();

@@ -11,7 +11,7 @@ for line in out.stderr.splitlines():
         grab = 3
     if "registers" in line or "spill" in line:
         print(line.strip())
-sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4amro6k_fastILb0ELi128ELi6EEEvNS_8FastArgsE", "/tmp/kf.cubin"], capture_output=True, text=True).stdout
+sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4amro6k_fastILb0ELi128ELi4EEEvNS_8FastArgsE", "/tmp/kf.cubin"], capture_output=True, text=True).stdout
 ins = []
 for l in sass.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
