@@ -221,15 +221,23 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
   int shape = kShapeTeam;
   if (const char* e = std::getenv("AMRO_FAST_SHAPE")) shape = (e[0] == 'w') ? kShapeWide : kShapeTeam;
-  int G = 1;
+  // Team size: all resident CTA slots are dealt out to the teams, the first `extra` teams taking one more, so that every SM
+  // hosts the same number of CTAs (measured: a grid that leaves some SMs one CTA short is ~5-10 % slower, because the
+  // fuller SMs make their teams' barriers late).  AMRO_FAST_G fixes the team size, AMRO_FAST_CTAS_PER_SM caps the slots.
+  int G = 1, extra = 0;
   if (shape == kShapeTeam) {
-    const int cap = fast_max_coresident_ctas(T->device, replay, shape);
+    int cap = fast_max_coresident_ctas(T->device, replay, shape);
     if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
-    const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (2 * kTeamThreads));  // a CTA wants a few warps of records
-    G = (int)std::max<int64_t>(1, std::min<int64_t>(cap / std::max<int64_t>(n_teams, 1), useful));
-    if (n_teams > cap) G = 1;
+    if (const char* e = std::getenv("AMRO_FAST_CTAS_PER_SM")) cap = std::min(cap, std::max(1, std::atoi(e)) * sms);
+    // every warp pays a fixed price per day (barrier, tables, totals): it wants about a dozen 32-record trips to spread it
+    // over -- measured on config 2: 7 CTAs per team (11 trips per warp and day) beat both 6 and 8-10 (profiles/sweeps.txt)
+    const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / (11 * kTeamThreads));
+    if (n_teams <= cap) {
+      G = (int)(cap / n_teams); extra = (int)(cap % n_teams);
+      if (G >= useful) { G = (int)useful; extra = 0; }
+    }
   }
-  if (const char* e = std::getenv("AMRO_FAST_G")) G = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("AMRO_FAST_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
   const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
   if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
   if (ring_chunks * 32 * kSlicesPerTeam * (int64_t)sizeof(uint4) >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: day too large for 32-bit slot offsets");
@@ -275,11 +283,11 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
   ensure_size(T->ws_barrier, (size_t)n_teams);
   AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));
-  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G;
+  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.teams_plus_one = extra;
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
-  fast_launch(st, f, replay, shape, (int)(n_teams * G));
+  fast_launch(st, f, replay, shape, (int)(n_teams * G + extra));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
 

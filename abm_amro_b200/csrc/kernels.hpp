@@ -109,7 +109,8 @@ struct FastArgs {
   int32_t* counts_det;
   int64_t counts_ld;
   unsigned int* team_barrier;    // [n_teams] zeroed by the caller
-  int ctas_per_team;             // CTAs that share a slice (1 = no inter-CTA barrier)
+  int ctas_per_team;             // CTAs that share a team's slices (1 = no inter-CTA barrier) ...
+  int teams_plus_one;            // ... the first teams_plus_one teams have one more, so that the grid fills the SMs evenly
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]

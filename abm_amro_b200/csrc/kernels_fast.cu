@@ -590,9 +590,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   SliceParams* par = reinterpret_cast<SliceParams*>(smem_raw);   // [kNS]
   const WarpShared sh = carve_shared<REPLAY>(smem_raw + kNS * sizeof(SliceParams), warp);
-  const int G = a.ctas_per_team;
-  const int64_t team = blockIdx.x / G;                 // one team per kNS slices of 8 simulations
-  const int rank = blockIdx.x % G;
+  // one team per kNS slices of 8 simulations; the first teams_plus_one teams have ctas_per_team + 1 CTAs (the grid is sized
+  // to give every SM the same number of CTAs: an SM with one CTA more than its neighbours would make its teams wait)
+  const int big = a.teams_plus_one * (a.ctas_per_team + 1);
+  const bool in_big = (int)blockIdx.x < big;
+  const int G = a.ctas_per_team + (in_big ? 1 : 0);
+  const int64_t team = in_big ? blockIdx.x / G : a.teams_plus_one + ((int)blockIdx.x - big) / G;
+  const int rank = in_big ? blockIdx.x % G : ((int)blockIdx.x - big) % G;
   const uint32_t gw = (uint32_t)(rank * kWarps + warp), n_gw = (uint32_t)(G * kWarps);   // this warp within its team
   TeamBarrier bar{a.team_barrier + team, 0u, n_gw, G == 1};
   const int64_t ring = a.ring_chunks * (kNS * 32);
@@ -758,7 +762,7 @@ void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
-  if (a.ctas_per_team > 1)
+  if (a.ctas_per_team > 1 || a.teams_plus_one > 0)
     AMRO_CUDA(cudaLaunchCooperativeKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
   else
     AMRO_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
