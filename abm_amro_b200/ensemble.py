@@ -43,7 +43,7 @@ def collapse(moments, total_sims: int, group=None):
     detected (reference: abm_wards.cpp:617-620, ``stddev(., 1, 1)``).  Returns float64 [n_days x 4]."""
     import torch
     import torch.distributed as dist
-    m = moments.clone()
+    m = moments.clone(memory_format=torch.contiguous_format)   # a transposed view of the C ABI buffer is not contiguous
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group)
     n = float(total_sims)

@@ -52,6 +52,12 @@ def lib():
         _lib.amro_oracle_threshold.argtypes = [C.c_double]
         _lib.amro_oracle_philox_u32.restype = C.c_uint32
         _lib.amro_oracle_philox_u32.argtypes = [_u64, _u64, _u64, C.c_uint32]
+        _lib.amro_oracle_philox_chunk.restype = C.c_uint32
+        _lib.amro_oracle_philox_chunk.argtypes = [_u64, _u64, _u64, C.c_uint32]
+        _lib.amro_oracle_threshold30.restype = C.c_uint32
+        _lib.amro_oracle_threshold30.argtypes = [C.c_double]
+        _lib.amro_oracle_bernoulli14.restype = C.c_uint32
+        _lib.amro_oracle_bernoulli14.argtypes = [C.c_double, C.c_uint32]
         _lib.amro_oracle_total_positive.restype = C.c_int64
         _lib.amro_oracle_simulate_and_collapse.restype = C.c_int64
     return _lib
@@ -133,6 +139,20 @@ def threshold(p: float) -> int:
 
 def philox_u32(seed, row, sim, kind) -> int:
     return int(lib().amro_oracle_philox_u32(seed & 0xFFFFFFFFFFFFFFFF, row, sim, kind))
+
+
+def philox_chunk(seed, index, sim, stream) -> int:
+    """16-bit chunk of (index, global simulation, stream): the daily draw (stream 0, & 0x3FFF) and the ward-day dither (stream 6)."""
+    return int(lib().amro_oracle_philox_chunk(seed & 0xFFFFFFFFFFFFFFFF, index, sim, stream))
+
+
+def threshold30(p: float) -> int:
+    return int(lib().amro_oracle_threshold30(float(p)))
+
+
+def bernoulli14(p: float, r16: int) -> int:
+    """Dithered 14-bit threshold of the daily step: (T30(p) + r16) >> 16."""
+    return int(lib().amro_oracle_bernoulli14(float(p), int(r16)))
 
 
 def progress_patients_probability_ward_1_timestep(ward_matrix, total_patients, parameters, n_sims,

@@ -197,6 +197,9 @@ off, n = ensemble.shard_sims(S, world, rank)
 c, d = counts(off, n)
 mom = ensemble.day_moments(torch.from_numpy(np.ascontiguousarray(c.T)), torch.from_numpy(np.ascontiguousarray(d.T)))
 got = ensemble.collapse(mom, S).numpy()
+# the fused run hands over the transpose of a [4 x n_days] buffer (bench.py): a non-contiguous view must work too
+got_t = ensemble.collapse(mom.t().contiguous().t(), S).numpy()
+assert np.array_equal(got, got_t)
 cf, df = counts(0, S)
 want = np.stack([cf.mean(1), df.mean(1), cf.std(1), df.std(1)], 1)
 assert np.allclose(got, want, rtol=0, atol=1e-9), np.abs(got - want).max()

@@ -78,6 +78,46 @@ def test_threshold_map():
         assert (t - 1) * 2.0 ** -32 < p <= t * 2.0 ** -32  # number of r with r * 2^-32 < p
 
 
+def test_dithered_daily_threshold_is_exact_in_expectation():
+    # RNG spec of the daily step (abm_amro_b200/csrc/rng.cuh): fires iff v14 < B(p), B(p) = (T30(p) + r16) >> 16.
+    # Averaged over the 2^16 dithers the firing probability is T30(p) / 2^30 exactly; "never" and "always" have no dither.
+    assert oracle.threshold30(0.0) == 0 and oracle.threshold30(-3.0) == 0 and oracle.threshold30(float("nan")) == 0
+    assert oracle.threshold30(1.0) == 2 ** 30 and oracle.threshold30(1.5) == 2 ** 30 and oracle.threshold30(float("inf")) == 2 ** 30
+    assert oracle.threshold30(0.5) == 2 ** 29 and oracle.threshold30(2.0 ** -30) == 1 and oracle.threshold30(2.0 ** -31) == 1
+    for r in (0, 1, 12345, 65535):
+        assert oracle.bernoulli14(0.0, r) == 0 and oracle.bernoulli14(1.0, r) == 2 ** 14
+    rs = np.arange(65536, dtype=np.int64)
+    for p in list(np.random.default_rng(1).random(20)) + [1e-9, 0.25, 0.999999999, 1 - 2.0 ** -30]:
+        t = oracle.threshold30(p)
+        assert (t - 1) * 2.0 ** -30 < p <= t * 2.0 ** -30
+        b = (t + rs) >> 16                                   # what the oracle / the kernels compute per dither
+        assert b.min() >= 0 and b.max() <= 2 ** 14
+        assert int(b.sum()) == t                             # sum_r P(v14 < B) * 2^14 = T30: exact marginal
+        for r in (0, 777, 65535):
+            assert oracle.bernoulli14(p, r) == int((t + r) >> 16)
+
+
+def test_philox_chunks_are_the_halves_of_the_words():
+    seed, row, stream = 0x1234567890ABCDEF, 987654321, 6
+    for group in (0, 5):
+        words = oracle.philox4x32_10([row & 0xFFFFFFFF, row >> 32, group, stream], [seed & 0xFFFFFFFF, seed >> 32])
+        for k in range(8):
+            assert oracle.philox_chunk(seed, row, group * 8 + k, stream) == (words[k >> 1] >> (16 * (k & 1))) & 0xFFFF
+
+
+def test_philox_mode_dither_follows_the_ward_day():
+    # the dither index is the ward-day in the reference's visiting order (day ascending, ward ascending), so a run is
+    # reproduced by stepping its days one at a time only if the ward-day counter carries on
+    wm, tp, n_init = synth.make_hospital(3, 30, 4, seed=9)
+    par = synth.particle_parameters(8, seed=2)
+    icp = np.full((n_init, 8), 0.3); idp = np.full((n_init, 8), 0.4)
+    a = oracle.simulate_discrete_model(icp, idp, wm, tp, par, 1, 2, 1, 5, rng=oracle.Rng(oracle.RNG_PHILOX))
+    b = oracle.simulate_discrete_model(icp, idp, wm, tp, par, 1, 2, 1, 5, rng=oracle.Rng(oracle.RNG_PHILOX))
+    assert np.array_equal(a, b)
+    c = oracle.simulate_discrete_model(icp, idp, wm, tp, par, 1, 2, 1, 6, rng=oracle.Rng(oracle.RNG_PHILOX))
+    assert not np.array_equal(a[:, 6:], c[:, 6:])
+
+
 def test_philox_mode_is_a_function_of_row_and_global_simulation():
     wm, tp, n_init = synth.make_hospital(3, 40, 8, seed=3)
     par = synth.particle_parameters(12, seed=1)
