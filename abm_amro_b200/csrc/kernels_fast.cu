@@ -38,6 +38,8 @@
 #include "rng.cuh"
 #include "topology.hpp"
 
+#define AMRO_PRAGMA_STR(x) _Pragma(#x)
+#define AMRO_PRAGMA_UNROLL(n) AMRO_PRAGMA_STR(unroll n)
 namespace amro {
 #ifdef AMRO_PROFILE_PHASES
 __device__ unsigned long long g_phase_cycles[8];   // development only: summed cycles of thread 0 of every CTA per phase
@@ -218,11 +220,6 @@ __device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, cons
     o[j] = m1 & (q ^ t);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// first day only (U0 present): out of line, the record loop stays small
-__device__ __forceinline__ uint4 step_record_first(const uint4* __restrict__ tab, const uint4 pre, const uint4 rnd, uint32_t x2) {
-  return step_record<true>(tab, pre, rnd, x2);
 }
 
 // One record, eight simulations, replay mode: the caller's uniforms, compared in fp64 as the reference does.
@@ -433,7 +430,9 @@ __device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32
 }
 
 // ---- one day of the team's slices: the run of the day's records that belongs to this warp (abm_wards.cpp:384-407) ----
-template <bool REPLAY>
+// FIRST: the day of the initial state (its records may hold U0); a separate instance keeps that variant of the step out of
+// the loop every other day runs.
+template <bool REPLAY, bool FIRST>
 __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, const SliceParams* par, const FastArgs& a,
                                             const TeamCtx& c, int64_t d, const DayPlan& pl, TeamBarrier& bar) {
   const int lane = threadIdx.x & 31;
@@ -490,7 +489,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     if (blk) flush_counts();
     const uint32_t blk_end = min(n_run, blk + 32u * kFlushEvery);
 #ifdef AMRO_TRIP_UNROLL
-#pragma unroll AMRO_TRIP_UNROLL
+    AMRO_PRAGMA_UNROLL(AMRO_TRIP_UNROLL)
 #endif
     for (uint32_t i = blk + lane; i < blk_end + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
       const bool active = i < n_run;
@@ -508,7 +507,6 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
       const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
       const int h = (int)(info >> kInfoHShift);
       const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
-      const bool any_init = __any_sync(0xFFFFFFFFu, active && src == kSrcInit);   // U0 only comes straight from the initial draw
       const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, active ? segl : 0u);
       uint32_t seg_lo = __shfl_sync(0xFFFFFFFFu, segl, 0);                          // lane 0 is active in every trip
       bool pending = active;
@@ -534,8 +532,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
             post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
           } else {
             const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
-            if (__builtin_expect(any_init, 0)) post = step_record_first(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
-            else post = step_record<false>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+            post = step_record<FIRST>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
           }
           if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
           if (pt && on) __stcg(pt + s, post);
@@ -686,7 +683,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   for (int64_t d = 0; d < a.n_days; ++d) {
     bar.wait();
     PHASE_ADD(3);  // team barrier wait
-    process_day<REPLAY>(PHASE_ARG sh, par, a, c, d, plan, bar);
+    if (d == 0) process_day<REPLAY, true>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
+    else process_day<REPLAY, false>(PHASE_ARG sh, par, a, c, d, plan, bar);
     plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
   }
 }
