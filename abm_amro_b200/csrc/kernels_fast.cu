@@ -467,109 +467,107 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
       push_pressure(wmain != kNone ? c.press + (int64_t)wmain * kNW : nullptr, acc);
     };
 
-    // the ring of table rows holds ward-days [.., built_hi); start with what the run needs first
-    uint32_t built_hi = min(pl.sl_last + 1u, pl.sl_first + (uint32_t)kWarpTableSegs);
-    build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, pl.sl_first, built_hi, test_h, test_a);
-    __syncwarp();
-    PHASE_ADD(0);  // table
-
-    // software pipeline: the loads of the next trip are in flight while this one computes
+    // The run is stepped in batches of at most kWarpTableSegs ward-days: build their tables, then run the trips that hold
+    // their records.  A trip that straddles two batches is run once per batch, each time with the other batch's lanes
+    // switched off (they step an uncolonised state against the all-zero table row: nothing happens, nothing is stored).
     const uint32_t n_run = pl.w1 - pl.w0;
-    uint4 n_meta = make_uint4(0u, kNone, kNone, 0u), n_prev[kNS];
+    uint32_t since = 0;   // trips since the per-lane half counters were flushed (they stay exact up to kFlushEvery)
+    for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kWarpTableSegs) {
+      const uint32_t n_tab = min((uint32_t)kWarpTableSegs, pl.sl_last + 1u - sl);
+      __syncwarp();   // the previous batch's rows are no longer read
+      build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, sl, sl + n_tab, test_h, test_a);
+      __syncwarp();
+      PHASE_ADD(0);  // table
+      // trips (32-record chunks of the run) that hold records of these ward-days
+      const int64_t sb = seg0 + sl;
+      const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(&a.seg_row_start[sb]) - da)) - pl.w0;
+      const uint32_t re = min(pl.w1, (uint32_t)(__ldg(&a.seg_row_start[sb + n_tab]) - da)) - pl.w0;
+      uint32_t tb = rb >> 5;
+      const uint32_t t_end = (re + 31u) >> 5;
+      while (tb < t_end) {
+        const uint32_t te = min(t_end, tb + (kFlushEvery - since));
+        const uint4* pmt = pm + (int64_t)tb * 32;
+        const uint4* pct = pc + (int64_t)tb * (kNS * 32);
+        uint4* ptt = pt ? pt + (int64_t)tb * (kNS * 32) : nullptr;
+        // software pipeline: the loads of the next trip are in flight while this one computes
+        uint4 n_meta = make_uint4(0u, kNone, kNone, 0u), n_prev[kNS];
 #pragma unroll
-    for (int s = 0; s < kNS; ++s) n_prev[s] = make_uint4(0u, 0u, 0u, 0u);
-    if ((uint32_t)lane < n_run) {
-      n_meta = __ldg(pm);
+        for (int s = 0; s < kNS; ++s) n_prev[s] = make_uint4(0u, 0u, 0u, 0u);
+        if (tb * 32u + (uint32_t)lane < n_run) {
+          n_meta = __ldg(pmt);
 #pragma unroll
-      for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pc + s * 32);
-    }
-    // blocks of at most kFlushEvery trips: the per-lane half counters stay exact; the flush between blocks is outside the
-    // trip loop proper
-    for (uint32_t blk = 0; blk < n_run; blk += 32u * kFlushEvery) {
-    if (blk) flush_counts();
-    const uint32_t blk_end = min(n_run, blk + 32u * kFlushEvery);
+          for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pct + s * 32);
+        }
 #ifdef AMRO_TRIP_UNROLL
-    AMRO_PRAGMA_UNROLL(AMRO_TRIP_UNROLL)
+        AMRO_PRAGMA_UNROLL(AMRO_TRIP_UNROLL)
 #endif
-    for (uint32_t i = blk + lane; i < blk_end + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
-      const bool active = i < n_run;
-      const uint4 meta = n_meta;
-      uint4 prev[kNS];
+        for (uint32_t i = tb * 32u + lane; i < te * 32u + (uint32_t)lane; i += 32u) {   // i: run-relative; warp-uniform trip count
+          const uint4 meta = n_meta;
+          uint4 prev[kNS];
 #pragma unroll
-      for (int s = 0; s < kNS; ++s) prev[s] = n_prev[s];
-      pm += 32; pc += kNS * 32;
-      n_meta = make_uint4(0u, kNone, kNone, 0u);
-      if (i + 32u < n_run) {
-        n_meta = __ldg(pm);
+          for (int s = 0; s < kNS; ++s) prev[s] = n_prev[s];
+          pmt += 32; pct += kNS * 32;
+          n_meta = make_uint4(0u, kNone, kNone, 0u);
+          if (i + 32u < min(n_run, te * 32u)) {
+            n_meta = __ldg(pmt);
 #pragma unroll
-        for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pc + s * 32);
-      }
-      const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
-      const int h = (int)(info >> kInfoHShift);
-      const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
-      const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, active ? segl : 0u);
-      uint32_t seg_lo = __shfl_sync(0xFFFFFFFFu, segl, 0);                          // lane 0 is active in every trip
-      bool pending = active;
-      for (;;) {   // one pass unless the 32 records span more ward-days than the table ring holds
-        const uint32_t seg_end = min(seg_hi + 1u, seg_lo + (uint32_t)kWarpTableSegs);
-        if (__builtin_expect(built_hi < seg_end, 0)) {
-          __syncwarp();
-          build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, max(built_hi, seg_lo), seg_end, test_h, test_a);
-          built_hi = seg_end;
-          __syncwarp();
-        }
-        const bool on = pending && segl < seg_end;
-        // lanes that are off step an uncolonised state against the all-zero row: nothing happens, nothing is stored
-        const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * 2 + h) * kNS : kZeroRow * kNS;
-        const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
-        uint32_t colw[kNW], detw[kNW];
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-          uint4 pre = prev[s];
-          if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
-          uint4 post;
-          if constexpr (REPLAY) {
-            post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
-          } else {
-            const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
-            post = step_record<FIRST>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+            for (int s = 0; s < kNS; ++s) n_prev[s] = __ldcg(pct + s * 32);
           }
-          if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
-          if (pt && on) __stcg(pt + s, post);
-          const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
+          const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
+          const int h = (int)(info >> kInfoHShift);
+          const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
+          const bool on = i < n_run && segl - sl < n_tab;   // this batch's records (unsigned compare: segl >= sl too)
+          const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * 2 + h) * kNS : kZeroRow * kNS;
+          const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
+          uint32_t colw[kNW], detw[kNW];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                      // 1.0 per half-word: colonised (:477-485), D <= 0 (:500-509)
-            colw[s * 4 + j] = h2_ge_one(pw[j], kCodeA2);
-            detw[s * 4 + j] = h2_ge_one(pw[j], kCodeZero2);
+          for (int s = 0; s < kNS; ++s) {
+            uint4 pre = prev[s];
+            if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);  // (C=0, D=inf) x 8, :359-360
+            uint4 post;
+            if constexpr (REPLAY) {
+              post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
+            } else {
+              const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
+              post = step_record<FIRST>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
+            }
+            if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
+            if (ptt && on) __stcg(ptt + s, post);
+            const uint32_t pw[4] = {post.x, post.y, post.z, post.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                      // 1.0 per half-word: colonised (:477-485), D <= 0 (:500-509)
+              colw[s * 4 + j] = h2_ge_one(pw[j], kCodeA2);
+              detw[s * 4 + j] = h2_ge_one(pw[j], kCodeZero2);
+            }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < kNW; ++q) { ccol[q] = h2_add(ccol[q], colw[q]); cdet[q] = h2_add(cdet[q], detw[q]); }
+          for (int q = 0; q < kNW; ++q) { ccol[q] = h2_add(ccol[q], colw[q]); cdet[q] = h2_add(cdet[q], detw[q]); }
 
-        // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
-        // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
-        // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
-        // records that go elsewhere (transfers) add on their own.
-        if (__builtin_expect(seg_lo != wsegl, 0)) {   // seg_lo: the ward of the pass's first record (warp-uniform)
-          wsegl = seg_lo;
-          const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
-          if (m != wmain) { flush_warp(); wmain = m; }
-        }
-        const bool has = nseg != kNone, mine = nseg == wmain;
-        const uint32_t mine2 = mine ? kOne2 : 0u;
+          // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) --------------------------------
+          // Most records of a warp's run feed the same ward-day (same ward, next day): lanes keep a running packed sum
+          // for it, reduced across the warp (REDUX) and added with one RED per word only when that ward-day changes;
+          // records that go elsewhere (transfers) add on their own.
+          const uint32_t seg_lo = max(sl, __shfl_sync(0xFFFFFFFFu, segl, 0));   // the ward of the trip's first record of this batch (about)
+          if (__builtin_expect(seg_lo != wsegl, 0)) {
+            wsegl = seg_lo;
+            const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
+            if (m != wmain) { flush_warp(); wmain = m; }
+          }
+          const bool has = nseg != kNone, mine = nseg == wmain;
+          const uint32_t mine2 = mine ? kOne2 : 0u;
 #pragma unroll
-        for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
-        if (has && !mine) {
-          uint32_t* dst = c.press + (int64_t)nseg * kNW;
+          for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
+          if (has && !mine) {
+            uint32_t* dst = c.press + (int64_t)nseg * kNW;
 #pragma unroll
-          for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> 10) & kHalves);   // 1.0 = 0x3C00 -> 1
+            for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> 10) & kHalves);   // 1.0 = 0x3C00 -> 1
+          }
+          if (ptt) ptt += 32 * kNS;
         }
-        pending = pending && !on;
-        if (__builtin_expect(!__any_sync(0xFFFFFFFFu, pending), 1)) break;
-        seg_lo = __reduce_min_sync(0xFFFFFFFFu, pending ? segl : 0xFFFFFFFFu);
+        since += te - tb;
+        tb = te;
+        if (since == kFlushEvery) { flush_counts(); since = 0; }
       }
-      pt = pt ? pt + 32 * kNS : nullptr;
-    }
     }
     PHASE_ADD(1);  // records (thread 0's view)
     flush_warp();
