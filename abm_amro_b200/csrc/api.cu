@@ -205,6 +205,8 @@ struct DeviceInputs {  // device views of the run's inputs (uploaded copies or t
   const double* u_icol; const double* u_idet; int64_t ui_ld;
 };
 
+constexpr bool kClusterBarrierByDefault = true;
+
 uint64_t schedule_u64(int v) { return (uint64_t)(int64_t)v; }  // int -> unsigned 64-bit, as `uword % int` does (:391-392)
 
 void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
@@ -238,6 +240,17 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     }
   }
   if (const char* e = std::getenv("AMRO_FAST_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
+  // Teams of 2..8 equal CTAs run as thread-block clusters when all of them can be resident at once: the hardware cluster
+  // barrier replaces the counter in global memory.  AMRO_FAST_BARRIER=global / cluster forces one.
+  int use_cluster = 0;
+  if (shape == kShapeTeam && G > 1 && extra == 0) {
+    const char* e = std::getenv("AMRO_FAST_BARRIER");
+    const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
+    // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)
+    int Gc = std::min(G, 8);
+    if (!std::getenv("AMRO_FAST_G") && Gc > 2 && (Gc & 1)) Gc -= 1;
+    if (want && fast_max_coresident_clusters(T->device, replay, shape, Gc) >= n_teams) { use_cluster = 1; G = Gc; }
+  }
   const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
   if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
   if (ring_chunks * 32 * kSlicesPerTeam * (int64_t)sizeof(uint4) >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: day too large for 32-bit slot offsets");
@@ -283,7 +296,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
   ensure_size(T->ws_barrier, (size_t)n_teams);
   AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));
-  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.teams_plus_one = extra;
+  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.teams_plus_one = extra; f.cluster_barrier = use_cluster;
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));

@@ -111,6 +111,7 @@ struct FastArgs {
   unsigned int* team_barrier;    // [n_teams] zeroed by the caller
   int ctas_per_team;             // CTAs that share a team's slices (1 = no inter-CTA barrier) ...
   int teams_plus_one;            // ... the first teams_plus_one teams have one more, so that the grid fills the SMs evenly
+  int cluster_barrier;           // 1: every team is a thread-block cluster and meets at the hardware cluster barrier
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
@@ -119,6 +120,7 @@ size_t fast_shared_bytes(bool replay, int shape);
 int fast_threads(int shape);
 // CTAs of the given launch shape that can be co-resident (bound of a cooperative launch)
 int fast_max_coresident_ctas(int device, bool replay, int shape);
+int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster_size);
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid);
 
 // Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run

@@ -261,23 +261,33 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
+//   kBarCta      a team of one CTA: __syncthreads
+//   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
+//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, relaxed poll + acquire fence)
+constexpr int kBarCta = 0, kBarGlobal = 1, kBarCluster = 2;
 struct TeamBarrier {
   unsigned* ctr;
   unsigned target;
   unsigned n_warps;   // warps of the team
-  bool one_cta;
+  int mode;
   __device__ __forceinline__ void arrive() {
-    if (one_cta) return;
+    if (mode == kBarCta) return;
     __syncwarp();
+    if (mode == kBarCluster) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      return;
+    }
     target += n_warps;
-#ifdef AMRO_EXP_NOFENCE   // timing experiment only (breaks the ordering the barrier exists for)
-    if ((threadIdx.x & 31) == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-#else
     if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-#endif
   }
   __device__ __forceinline__ void wait() {
-    if (one_cta) { __syncthreads(); return; }
+    if (mode == kBarCta) { __syncthreads(); return; }
+    if (mode == kBarCluster) {
+      __syncwarp();
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      return;
+    }
     if ((threadIdx.x & 31) == 0) {
       while ((int)(ld_relaxed(ctr) - target) < 0) {}
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -593,7 +603,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   const int64_t team = in_big ? blockIdx.x / G : a.teams_plus_one + ((int)blockIdx.x - big) / G;
   const int rank = in_big ? blockIdx.x % G : ((int)blockIdx.x - big) % G;
   const uint32_t gw = (uint32_t)(rank * kWarps + warp), n_gw = (uint32_t)(G * kWarps);   // this warp within its team
-  TeamBarrier bar{a.team_barrier + team, 0u, n_gw, G == 1};
+  TeamBarrier bar{a.team_barrier + team, 0u, n_gw, G == 1 ? kBarCta : (a.cluster_barrier ? kBarCluster : kBarGlobal)};
   const int64_t ring = a.ring_chunks * (kNS * 32);
 
   TeamCtx c;
@@ -645,6 +655,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
 #pragma unroll 1
       for (int s = 0; s < kNS; ++s) {
         uint32_t w[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
+        uint4 rc_hi = make_uint4(0, 0, 0, 0), rc_lo = rc_hi, rd_hi = rc_hi, rd_lo = rc_hi;
+        if constexpr (!REPLAY) {   // one call per stream serves the slice's eight simulations (rng.cuh: philox_u32)
+          const uint32_t r0 = (uint32_t)r, r1 = (uint32_t)((uint64_t)r >> 32), g = c.gslice0 + (uint32_t)s;
+          const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+          rc_hi = philox4x32_10(r0, r1, g, kStreamInitCol, k0, k1); rc_lo = philox4x32_10(r0, r1, g, kStreamInitCol + 1u, k0, k1);
+          rd_hi = philox4x32_10(r0, r1, g, kStreamInitDet, k0, k1); rd_lo = philox4x32_10(r0, r1, g, kStreamInitDet + 1u, k0, k1);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int64_t sim = c.sim0 + s * 8 + k;
@@ -655,8 +672,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
               c0 = a.u_icol[r + a.ui_ld * sim] < pc;
               d0 = a.u_idet[r + a.ui_ld * sim] < pd;
             } else {
-              c0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitCol) < threshold33(pc);
-              d0 = (uint64_t)philox_u32(a.seed, (uint64_t)r, a.sim_offset + sim, kStreamInitDet) < threshold33(pd);
+              c0 = (uint64_t)((chunk16(rc_hi, k) << 16) | chunk16(rc_lo, k)) < threshold33(pc);
+              d0 = (uint64_t)((chunk16(rd_hi, k) << 16) | chunk16(rd_lo, k)) < threshold33(pd);
             }
           }
           // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0:
@@ -685,6 +702,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
     else process_day<REPLAY, false>(PHASE_ARG sh, par, a, c, d, plan, bar);
     plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
   }
+  if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
 }
 
 // ---- packed trajectory -> the reference's float64 columns ------------------------------------------------------
@@ -753,15 +771,46 @@ int fast_max_coresident_ctas(int device, bool replay, int shape) {
   return per_sm * sms;
 }
 
+// CTAs of the cluster launch that can be co-resident, in clusters (0 if the shape cannot be launched as clusters)
+int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster_size) {
+  (void)device;
+  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+  const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cluster_size * 1024u);
+  cfg.blockDim = dim3((unsigned)fast_threads(shape));
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid) {
   const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
-  if (a.ctas_per_team > 1 || a.teams_plus_one > 0)
+  if (a.cluster_barrier) {   // every team is one thread-block cluster (the hardware co-schedules its CTAs)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)fast_threads(shape));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)a.ctas_per_team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AMRO_CUDA(cudaLaunchKernelExC(&cfg, k, params));
+  } else if (a.ctas_per_team > 1 || a.teams_plus_one > 0) {
     AMRO_CUDA(cudaLaunchCooperativeKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
-  else
+  } else {
     AMRO_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)fast_threads(shape)), params, smem, st));
+  }
 }
 
 void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,

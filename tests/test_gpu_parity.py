@@ -75,7 +75,8 @@ def test_replay_fractional_weights_use_the_general_path(golden):
 
 CASES = [  # wards, census, days, S, ttd, tsh, tsa
     (1, 6, 3, 1, 0, 1, 1), (5, 300, 30, 20, 2, 7, 1), (30, 2000, 12, 64, 2, 7, 1), (4, 100, 15, 9, 0, 1, 3),
-    (12, 150, 9, 33, 5, 2, 2), (2, 700, 6, 8, 1, 3, 1)]
+    (12, 150, 9, 33, 5, 2, 2), (2, 700, 6, 8, 1, 3, 1),
+    (40, 100, 8, 17, 1, 2, 1)]   # tiny wards: a 32-record trip spans more ward-days than a warp's table ring holds
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
@@ -105,6 +106,21 @@ def test_replay_and_philox_match_oracle(case, shape):
             assert np.array_equal(summary_only.counts_detected, free.counts_detected)
             c, d = free.counts_colonized.astype(float), free.counts_detected.astype(float)   # exact integers in float64
             assert np.array_equal(summary_only.moments, np.stack([c.sum(1), (c * c).sum(1), d.sum(1), (d * d).sum(1)], 1))
+
+
+def test_long_runs_flush_the_per_lane_counters(monkeypatch):
+    # one CTA per team and 150,000 records a day: every warp steps more than 1024 trips a day, so the per-lane half-precision
+    # day counters (exact up to 1024) are flushed in the middle of a run
+    monkeypatch.setenv("AMRO_FAST_G", "1")
+    wm, tp, n_init = synth.make_hospital(3, 150_000, 2, seed=4)
+    S = 8
+    par = synth.tutorial_parameters(S)
+    ref = oracle.simulate_discrete_model(np.full((n_init, S), 0.3), np.full((n_init, S), 0.3), wm, tp, par, 2, 1, 1, 8,
+                                         rng=oracle.Rng(oracle.RNG_PHILOX))
+    with engine.Topology(wm, tp, n_init) as topo:
+        got = topo.simulate(par, 0.3, 0.3, 2, 1, 1, 8, path=capi.PATH_FAST)
+        assert np.array_equal(got.counts_colonized, oracle.total_positive_colonized(ref, S))
+        assert np.array_equal(got.counts_detected, oracle.total_positive_detected(ref, S))
 
 
 def test_unsorted_rows_and_sharded_ensembles_give_the_same_numbers():
