@@ -243,11 +243,11 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // Teams of 2..8 equal CTAs run as thread-block clusters when all of them can be resident at once: the hardware cluster
   // barrier replaces the counter in global memory.  AMRO_FAST_BARRIER=global / cluster forces one.
   int use_cluster = 0;
-  if (shape == kShapeTeam && G > 1 && extra == 0) {
+  if (shape == kShapeTeam && G > 1 && G <= 8 && extra == 0) {   // larger teams (few simulations, big days) keep their size
     const char* e = std::getenv("AMRO_FAST_BARRIER");
     const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
     // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)
-    int Gc = std::min(G, 8);
+    int Gc = G;
     if (!std::getenv("AMRO_FAST_G") && Gc > 2 && (Gc & 1)) Gc -= 1;
     if (want && fast_max_coresident_clusters(T->device, replay, shape, Gc) >= n_teams) { use_cluster = 1; G = Gc; }
   }
