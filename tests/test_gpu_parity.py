@@ -108,6 +108,28 @@ def test_replay_and_philox_match_oracle(case, shape):
             assert np.array_equal(summary_only.moments, np.stack([c.sum(1), (c * c).sum(1), d.sum(1), (d * d).sum(1)], 1))
 
 
+@pytest.mark.parametrize("g,barrier", [(3, "cluster"), (3, "global"), (8, "cluster"), (12, "global")])
+def test_teams_of_several_ctas_match_the_oracle(monkeypatch, g, barrier):
+    # small hospitals run one CTA per team; force teams of several CTAs (thread-block cluster barrier / counter in global
+    # memory) and check the free-running stream and the replayed uniforms bit for bit, state included
+    monkeypatch.setenv("AMRO_FAST_G", str(g))
+    monkeypatch.setenv("AMRO_FAST_BARRIER", barrier)
+    nw, cen, nd, S, ttd, tsh, tsa = 12, 3000, 10, 40, 2, 3, 1
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=21)
+    par = synth.particle_parameters(S, seed=4)
+    icp, idp = np.full((n_init, S), 0.25), np.full((n_init, S), 0.5)
+    t = random_tensors(wm.shape[0], S, n_init, seed=6)
+    ref = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 3, rng=oracle.Rng(oracle.RNG_PHILOX))
+    ref_replay = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 3, rng=oracle.Rng(oracle.RNG_TENSOR, **t))
+    with engine.Topology(wm, tp, n_init) as topo:
+        free = topo.simulate(par, icp, idp, ttd, tsh, tsa, 3, path=capi.PATH_FAST, want_state=True)
+        assert np.array_equal(free.state, ref[:, 6:])
+        assert np.array_equal(free.counts_colonized, oracle.total_positive_colonized(ref, S))
+        assert np.array_equal(free.counts_detected, oracle.total_positive_detected(ref, S))
+        rep = topo.simulate(par, icp, idp, ttd, tsh, tsa, 3, rng_mode=capi.RNG_REPLAY, path=capi.PATH_FAST, want_state=True, **t)
+        assert np.array_equal(rep.state, ref_replay[:, 6:])
+
+
 def test_long_runs_flush_the_per_lane_counters(monkeypatch):
     # one CTA per team and 150,000 records a day: every warp steps more than 1024 trips a day, so the per-lane half-precision
     # day counters (exact up to 1024) are flushed in the middle of a run
