@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.hpp"
@@ -530,11 +531,31 @@ void hash_bytes(Hash128& h, const void* data, size_t n_bytes) {
   h.a = rotl64(a0 ^ a2, 17) * 0x9E3779B97F4A7C15ull ^ (a1 + n);
   h.b = rotl64(a1 ^ a3, 23) * 0xC2B2AE3D27D4EB4Full ^ (a0 + n);
 }
+// A large dense matrix is hashed in slabs by a few threads (the hash of a 175 MB ward_matrix on one core costs more than
+// the run it saves compiling for); the slab hashes are then chained in order, so the key does not depend on the thread count.
+void hash_dense(Hash128& h, const double* m, size_t n) {
+  constexpr size_t kSlab = (size_t)1 << 20;   // doubles per slab (8 MB)
+  const size_t n_slabs = (n + kSlab - 1) / kSlab;
+  if (n_slabs <= 2) { hash_bytes(h, m, sizeof(double) * n); return; }
+  std::vector<Hash128> part(n_slabs);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 8), n_slabs);
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < n_thr; ++t)
+    pool.emplace_back([&, t] {
+      for (size_t sl = t; sl < n_slabs; sl += n_thr) {
+        const size_t lo = sl * kSlab, hi = std::min(n, lo + kSlab);
+        hash_bytes(part[sl], m + lo, sizeof(double) * (hi - lo));
+      }
+    });
+  for (auto& th : pool) th.join();
+  hash_bytes(h, part.data(), sizeof(Hash128) * n_slabs);
+}
 void hash_matrix(Hash128& h, const double* m, int64_t rows, int64_t cols, int64_t ld) {
   const int64_t dims[3] = {rows, cols, 0};
   hash_bytes(h, dims, sizeof dims);
-  if (ld == rows) hash_bytes(h, m, sizeof(double) * (size_t)(rows * cols));
-  else for (int64_t c = 0; c < cols; ++c) hash_bytes(h, m + c * ld, sizeof(double) * (size_t)rows);
+  if (ld == rows) hash_dense(h, m, (size_t)(rows * cols));
+  else for (int64_t c = 0; c < cols; ++c) hash_dense(h, m + c * ld, (size_t)rows);
 }
 
 struct CachedTopology {

@@ -322,15 +322,30 @@ __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* p
   const bool flag = h ? test_a : test_h;
   const double rho = h ? p.rho_i[k] : p.rho_h[k];
   const double beta = p.beta[k], alpha = p.alpha[k], alpha2 = p.alpha2[k], gamma = p.gamma[k];
+  // the loads of the next pass are in flight while this one computes
+  auto lane_seg = [&](uint32_t sl0) { return kNS == 2 ? sl0 : min(sl0 + (uint32_t)hi, b1 - 1u); };   // an odd tail is simply built twice
+  uint32_t pk_next = 0u;
+  double n_next = 1.0;
+  if (b0 < b1) {
+    const int64_t seg = seg0 + lane_seg(b0);
+    pk_next = __ldcg(&press[(seg * kNS + s) * 4 + (k >> 1)]);
+    n_next = __ldg(&a.seg_N[seg]);
+  }
 #pragma unroll 1
   for (uint32_t sl0 = b0; sl0 < b1; sl0 += kPerPass) {
-    const uint32_t sl = kNS == 2 ? sl0 : min(sl0 + (uint32_t)hi, b1 - 1u);   // an odd tail is simply built twice
+    const uint32_t sl = lane_seg(sl0);
     const int64_t seg = seg0 + sl;
     const int slot = (int)(sl & (kWarpTableSegs - 1));
-    const uint32_t pk = __ldcg(&press[(seg * kNS + s) * 4 + (k >> 1)]);
+    const uint32_t pk = pk_next;
+    const double n_seg = n_next;
+    if (sl0 + kPerPass < b1) {
+      const int64_t sn = seg0 + lane_seg(sl0 + kPerPass);
+      pk_next = __ldcg(&press[(sn * kNS + s) * 4 + (k >> 1)]);
+      n_next = __ldg(&a.seg_N[sn]);
+    }
     const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
     // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
-    const double F = __dmul_rn(__ddiv_rn(beta, __ldg(&a.seg_N[seg])), (double)cnt);
+    const double F = __dmul_rn(__ddiv_rn(beta, n_seg), (double)cnt);
     const bool finite = fabs(F) <= 1.7976931348623157e308;
     if constexpr (REPLAY) {
 #pragma unroll
