@@ -40,7 +40,8 @@ class SimArgs(C.Structure):
                 ("u_icol", C.c_void_p), ("u_idet", C.c_void_p), ("ui_ld", _i64),
                 ("counts_colonized", C.c_void_p), ("counts_detected", C.c_void_p),
                 ("state_out", C.c_void_p), ("so_ld", _i64),
-                ("p_out", C.c_void_p), ("day_moments", C.c_void_p), ("pressure_out", C.c_void_p), ("stream", C.c_void_p),
+                ("p_out", C.c_void_p), ("day_moments", C.c_void_p), ("pressure_out", C.c_void_p),
+                ("observed_colonized", C.c_void_p), ("observed_detected", C.c_void_p), ("distance", C.c_void_p), ("stream", C.c_void_p),
                 ("path_used", C.c_int32), ("launches", C.c_int32), ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
 
 

@@ -208,6 +208,27 @@ struct DeviceInputs {  // device views of the run's inputs (uploaded copies or t
 
 constexpr bool kClusterBarrierByDefault = true;
 
+// amro_sim_args::distance: per-simulation squared distance of the per-day counts to the observed series (device kernel;
+// with host pointers the two short series go up and S doubles come back)
+void emit_distance(amro_topology* T, amro_sim_args* A, const int32_t* col, const int32_t* det, int64_t S, bool on_device,
+                   cudaStream_t st, int& launches) {
+  if (!A->distance) return;
+  if (!A->observed_colonized && !A->observed_detected) fail(AMRO_EINVAL, "distance needs observed_colonized and/or observed_detected");
+  const int64_t Dd = T->H.n_days_out;
+  if (on_device) {
+    distance_to_data(st, col, det, Dd, S, Dd, A->observed_colonized, A->observed_detected, A->distance);
+  } else {
+    DevBuf<double> oc, od, out;
+    if (A->observed_colonized) oc.upload(A->observed_colonized, (size_t)Dd, st);
+    if (A->observed_detected) od.upload(A->observed_detected, (size_t)Dd, st);
+    out.alloc((size_t)S);
+    distance_to_data(st, col, det, Dd, S, Dd, oc.p, od.p, out.p);
+    AMRO_CUDA(cudaMemcpyAsync(A->distance, out.p, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st));
+    AMRO_CUDA(cudaStreamSynchronize(st));
+  }
+  launches++;
+}
+
 uint64_t schedule_u64(int v) { return (uint64_t)(int64_t)v; }  // int -> unsigned 64-bit, as `uword % int` does (:391-392)
 
 void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
@@ -321,6 +342,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     }
     A->launches++;
   }
+  emit_distance(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
   const int64_t* pos_of = H.identity_order ? nullptr : T->pos_of.p;
   if (A->state_out) {
     if (on_device) {
@@ -408,8 +430,8 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     const int64_t pa = H.day_push_start[d], pb = H.day_push_start[d + 1];
     if (pb > pa) { gen_propagate(st, C, Dp, ld, S, T->push_src.p + pa, T->push_dst.p + pa, pb - pa, tmp.p); launches += 2; }
   }
-  if (A->counts_colonized || A->day_moments) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
-  if (A->counts_detected || A->day_moments) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
+  if (A->counts_colonized || A->day_moments || A->distance) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
+  if (A->counts_detected || A->day_moments || A->distance) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
   DevBuf<double> dm;
   if (A->day_moments) {
     double* dst = A->day_moments;
@@ -417,6 +439,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     day_moments(st, counts.p, counts.p + H.n_days_out * S, H.n_days_out, S, H.n_days_out, dst, H.n_days_out);
     launches++;
   }
+  emit_distance(T, A, counts.p, counts.p + H.n_days_out * S, S, on_device, st, launches);
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   AMRO_CUDA(cudaGetLastError());
 

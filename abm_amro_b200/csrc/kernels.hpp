@@ -48,6 +48,9 @@ void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int6
                int mode, int32_t* counts, int64_t ld_out);
 void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n);
 // out[day + ld*{0,1,2,3}] = sum / sum of squares over simulations of col[day + ld_c*s], then of det[...]
+// out[s] = sum over days with data (non-NaN) of (col - obs_col)^2 + (det - obs_det)^2; either series may be nullptr
+void distance_to_data(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
+                      const double* obs_col, const double* obs_det, double* out);
 void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld);
 
 // ----------------------------------------------------------------------------------------------------

@@ -186,6 +186,22 @@ __global__ void k_day_moments(const int32_t* __restrict__ col, const int32_t* __
   if (lane == 0) { out[day] = a; out[day + ld] = b; out[day + 2 * ld] = c; out[day + 3 * ld] = d; }
 }
 
+// per-simulation squared distance between the per-day counts and observed series: one warp per simulation (its days are
+// contiguous: coalesced).  Sums of squares of integers minus data, accumulated in float64 in a fixed lane/shuffle order.
+__global__ void k_distance(const int32_t* __restrict__ col, const int32_t* __restrict__ det, int64_t n_days, int64_t S, int64_t ld_c,
+                           const double* __restrict__ obs_col, const double* __restrict__ obs_det, double* __restrict__ out) {
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= S) return;
+  double acc = 0.0;
+  for (int64_t d = lane; d < n_days; d += 32) {
+    if (obs_col) { const double o = obs_col[d]; if (o == o) { const double e = (double)col[d + ld_c * s] - o; acc += e * e; } }
+    if (obs_det) { const double o = obs_det[d]; if (o == o) { const double e = (double)det[d + ld_c * s] - o; acc += e * e; } }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  if (lane == 0) out[s] = acc;
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -223,6 +239,11 @@ void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int6
 void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld) {
   if (n_days <= 0) return;
   k_day_moments<<<blocks_for(n_days * 32), kThreads, 0, st>>>(col, det, n_days, S, ld_c, out, ld);
+}
+void distance_to_data(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
+                      const double* obs_col, const double* obs_det, double* out) {
+  if (S <= 0) return;
+  k_distance<<<blocks_for(S * 32), kThreads, 0, st>>>(col, det, n_days, S, ld_c, obs_col, obs_det, out);
 }
 void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64_t n) {
   if (n <= 0) return;

@@ -40,6 +40,7 @@ class SimResult:
     launches: int
     kernel_ms: float
     total_ms: float
+    distance: np.ndarray | None = None    # [S] squared distance of the per-day counts to observed series, if asked for
 
 
 class Topology:
@@ -98,7 +99,10 @@ class Topology:
                  n_sims: int | None = None, sim_offset: int = 0, rng_mode: int = capi.RNG_PHILOX,
                  path: int = capi.PATH_AUTO, keep_trajectory: bool = False, want_counts: bool = True,
                  want_state: bool = False, want_p: bool = False, want_pressure: bool = False,
-                 want_moments: bool = False, u_col=None, u_det=None, u_icol=None, u_idet=None) -> SimResult:
+                 want_moments: bool = False, u_col=None, u_det=None, u_icol=None, u_idet=None,
+                 observed_colonized=None, observed_detected=None) -> SimResult:
+        """``observed_*``: per-day series (NaN = no data); the result then carries ``distance`` [S], the per-simulation sum
+        of squared differences between the simulated per-day counts and the data, computed on the device."""
         i = self.info
         par = _f64(parameters)
         S = int(n_sims if n_sims is not None else par.shape[0])
@@ -136,8 +140,21 @@ class Topology:
             pr = np.zeros((i.n_segments, S), dtype=np.int32, order="F"); a.pressure_out = pr.ctypes.data
         if want_moments:
             mo = np.zeros((i.n_days_out, 4), order="F"); a.day_moments = mo.ctypes.data
+        dist = None
+        if observed_colonized is not None or observed_detected is not None:
+            dist = np.zeros(S)
+            a.distance = dist.ctypes.data
+            for name, val in (("observed_colonized", observed_colonized), ("observed_detected", observed_detected)):
+                if val is not None:
+                    arr = np.ascontiguousarray(val, dtype=np.float64)
+                    if arr.shape != (i.n_days_out,):
+                        raise RuntimeError(f"{name}: expected shape ({i.n_days_out},), got {arr.shape}")
+                    keep.append(arr)
+                    setattr(a, name, arr.ctypes.data)
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
-        return SimResult(cc, cd, st, p, pr, mo, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        r = SimResult(cc, cd, st, p, pr, mo, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        r.distance = dist
+        return r
 
     # ---- device-resident run (inputs already in HBM; nothing crosses PCIe) ---------------------------------
     def simulate_device(self, parameters_ptr: int, p_rows: int, p_ld: int, icp_ptr: int, idp_ptr: int,

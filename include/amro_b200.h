@@ -118,6 +118,12 @@ typedef struct amro_sim_args {
                                   all-reduce over the GPUs of an ensemble needs for simulate_and_collapse           */
   int32_t* pressure_out;       /* FAST path: [n_segments x S] ld = n_segments: colonised count per
                                   ward-day before its step (the reference's sum(W), :99)                  */
+  /* distance to data (what a parameter-inference loop needs back from a 64k-particle sweep is one number per
+     particle, not the [days x S] counts): distance[s] = sum over days of (colonised(day, s) - observed_colonized[day])^2
+     + (detected(day, s) - observed_detected[day])^2; either series may be NULL, NaN entries are days without data */
+  const double* observed_colonized;   /* [n_days_out] or NULL                                             */
+  const double* observed_detected;    /* [n_days_out] or NULL                                             */
+  double*  distance;           /* [S] or NULL                                                              */
   void*    stream;             /* cudaStream_t when pointers_on_device, else ignored                      */
 
   /* filled on return */

@@ -130,6 +130,24 @@ def test_teams_of_several_ctas_match_the_oracle(monkeypatch, g, barrier):
         assert np.array_equal(rep.state, ref_replay[:, 6:])
 
 
+@pytest.mark.parametrize("path", [capi.PATH_FAST, capi.PATH_GENERAL])
+def test_distance_to_data_is_computed_on_the_device(path):
+    # a sweep hands back one number per particle -- the squared distance of its per-day counts to the data
+    wm, tp, n_init = synth.make_hospital(4, 120, 20, seed=12)
+    S = 37
+    par = synth.particle_parameters(S, seed=8)
+    g = np.random.default_rng(5)
+    obs_c, obs_d = g.integers(0, 120, 20).astype(float), g.integers(0, 60, 20).astype(float)
+    obs_c[3] = np.nan; obs_d[[0, 7]] = np.nan                     # days without data
+    with engine.Topology(wm, tp, n_init) as topo:
+        r = topo.simulate(par, 0.2, 0.3, 2, 7, 1, 9, path=path, observed_colonized=obs_c, observed_detected=obs_d)
+        c, d = r.counts_colonized.astype(float), r.counts_detected.astype(float)
+        want = np.nansum((c - obs_c[:, None]) ** 2, 0) + np.nansum((d - obs_d[:, None]) ** 2, 0)
+        assert np.allclose(r.distance, want, rtol=1e-13, atol=0)  # sums of integers' squares: exact up to summation order
+        only_d = topo.simulate(par, 0.2, 0.3, 2, 7, 1, 9, path=path, want_counts=False, observed_detected=obs_d)
+        assert np.allclose(only_d.distance, np.nansum((d - obs_d[:, None]) ** 2, 0), rtol=1e-13, atol=0)
+
+
 def test_long_runs_flush_the_per_lane_counters(monkeypatch):
     # one CTA per team and 150,000 records a day: every warp steps more than 1024 trips a day, so the per-lane half-precision
     # day counters (exact up to 1024) are flushed in the middle of a run
