@@ -207,6 +207,7 @@ struct DeviceInputs {  // device views of the run's inputs (uploaded copies or t
 };
 
 constexpr bool kClusterBarrierByDefault = true;
+constexpr int kMaxClusterCtas = 16;   // sm_100 allows clusters of up to 16 CTAs (more than 8 is "non-portable": opted in per kernel)
 
 // amro_sim_args::distance: per-simulation squared distance of the per-day counts to the observed series (device kernel;
 // with host pointers the two short series go up and S doubles come back)
@@ -265,7 +266,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // Teams of 2..8 equal CTAs run as thread-block clusters when all of them can be resident at once: the hardware cluster
   // barrier replaces the counter in global memory.  AMRO_FAST_BARRIER=global / cluster forces one.
   int use_cluster = 0;
-  if (shape == kShapeTeam && G > 1 && G <= 8 && extra == 0) {   // larger teams (few simulations, big days) keep their size
+  if (shape == kShapeTeam && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
     const char* e = std::getenv("AMRO_FAST_BARRIER");
     const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
     // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)

@@ -792,6 +792,7 @@ int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster
   const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cluster_size > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cluster_size * 1024u);
   cfg.blockDim = dim3((unsigned)fast_threads(shape));
