@@ -265,8 +265,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (const char* e = std::getenv("AMRO_FAST_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
   // Teams of 2..8 equal CTAs run as thread-block clusters when all of them can be resident at once: the hardware cluster
   // barrier replaces the counter in global memory.  AMRO_FAST_BARRIER=global / cluster forces one.
+  // A grid that leaves a quarter of the CTA slots empty anyway runs the instance compiled for three CTAs per SM (168
+  // registers per thread instead of 128: the scheduler has room to overlap the eight pairs of a record): +3 % on config 2
+  if (shape == kShapeTeam && !std::getenv("AMRO_FAST_SHAPE") && (int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms)
+    shape = kShapeRoomy;
   int use_cluster = 0;
-  if (shape == kShapeTeam && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
+  if (shape != kShapeWide && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
     const char* e = std::getenv("AMRO_FAST_BARRIER");
     const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
     // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)

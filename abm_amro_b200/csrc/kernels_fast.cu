@@ -769,7 +769,9 @@ extern "C" void amro_debug_phase_cycles(unsigned long long* out, int reset) {
 namespace {
 template <bool REPLAY>
 const void* kernel_ptr(int shape) {
-  return shape == kShapeWide ? (const void*)k_fast<REPLAY, kWideThreads, 1> : (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks>;
+  return shape == kShapeWide    ? (const void*)k_fast<REPLAY, kWideThreads, 1>
+         : shape == kShapeRoomy ? (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks - 1>
+                                : (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks>;
 }
 }  // namespace
 
