@@ -35,19 +35,30 @@ def day_moments(counts_col, counts_det):
     return torch.stack([c.sum(0), (c * c).sum(0), d.sum(0), (d * d).sum(0)], dim=1)
 
 
+def reduce_moments(moments, group=None):
+    """The ONE collective of a run: sum the per-rank day moments over the ranks, in place (``moments`` must be a
+    contiguous tensor: the C ABI's ``day_moments`` buffer as it is, ``[4 x n_days]``, or its copy)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    return moments
+
+
+def moments_to_collapse(m, total_sims: int):
+    """Reduced day moments ``[n_days x 4]`` -> the columns of ``simulate_and_collapse``: mean colonised, mean detected,
+    population sd colonised, population sd detected (reference: abm_wards.cpp:617-620, ``stddev(., 1, 1)``)."""
+    import torch
+    n = float(total_sims)
+    mean = m[:, [0, 2]] / n
+    var = torch.clamp(m[:, [1, 3]] / n - mean * mean, min=0.0)
+    return torch.cat([mean, var.sqrt()], dim=1)
+
+
 def collapse(moments, total_sims: int, group=None):
     """``moments`` is float64 [n_days x 4] (``day_moments`` above, or the transpose of the C ABI's
     ``amro_sim_args.day_moments`` buffer, which the fused run fills on the device).
     All-reduce the per-rank day moments (the ONE collective of a run) and turn them into the columns of
-    ``simulate_and_collapse``: mean colonised, mean detected, population sd colonised, population sd
-    detected (reference: abm_wards.cpp:617-620, ``stddev(., 1, 1)``).  Returns float64 [n_days x 4]."""
+    ``simulate_and_collapse``.  Returns float64 [n_days x 4]."""
     import torch
-    import torch.distributed as dist
     m = moments.clone(memory_format=torch.contiguous_format)   # a transposed view of the C ABI buffer is not contiguous
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group)
-    n = float(total_sims)
-    mean_c, mean_d = m[:, 0] / n, m[:, 2] / n
-    var_c = torch.clamp(m[:, 1] / n - mean_c * mean_c, min=0.0)
-    var_d = torch.clamp(m[:, 3] / n - mean_d * mean_d, min=0.0)
-    return torch.stack([mean_c, mean_d, var_c.sqrt(), var_d.sqrt()], dim=1)
+    return moments_to_collapse(reduce_moments(m, group), total_sims)

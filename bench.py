@@ -252,8 +252,8 @@ def run_ours(args, rank, world, local_rank):
         r = topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), idp_d.data_ptr(), cc_d.data_ptr(),
                                  cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset,
                                  stream=stream.cuda_stream, day_moments_ptr=mom_d.data_ptr() if world > 1 else 0)
-        if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members
-            ensemble.collapse(mom_d.t(), S * world)
+        if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members, summed in place
+            ensemble.reduce_moments(mom_d)
         return r
 
     def barrier():
@@ -276,6 +276,9 @@ def run_ours(args, rank, world, local_rank):
         barrier()
     elapsed_ms = e0.elapsed_time(e1)
     path_used = r.path_used
+    if world > 1:  # what simulate_and_collapse reports, from the last step's reduced moments: [n_days x 4], finite
+        stats = ensemble.moments_to_collapse(mom_d.t(), S * world)
+        assert bool(torch.isfinite(stats).all())
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
