@@ -296,6 +296,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.meta = T->meta.p;
   f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p; f.seg_main_next = T->seg_main_next.p;
   f.identity_order = H.identity_order ? 1 : 0;
+  f.has_half = H.has_half ? 1 : 0;
   f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
   f.seg_N = T->seg_N.p;
   f.R = H.R; f.n_init = H.n_init; f.n_days = H.total_days + 1; f.n_seg = H.n_seg; f.ring_chunks = ring_chunks;

@@ -85,6 +85,7 @@ struct FastArgs {
   const uint32_t* init_seg;
   const uint32_t* init_slot;
   int identity_order;            // records are stepped in their original row order (row = position)
+  int has_half;                  // some records weigh 1/2: ward pressure is counted in halves, tables exist per weight
   const int64_t* day_start;
   const int64_t* day_seg_start;
   const int64_t* seg_row_start;

@@ -66,6 +66,7 @@ constexpr int kFlushEvery = 1024;              // row iterations between flushes
 constexpr uint32_t kHalves = 0x00010001u;      // one in each half-word
 constexpr uint32_t kCodeA2 = kCodeA * kHalves, kCodeZero2 = kCodeZero * kHalves, kCodeCnt2 = kCodeCnt * kHalves, kCodeU02 = kCodeU0 * kHalves;
 constexpr uint32_t kOne2 = 0x3C003C00u;        // half2 (1.0, 1.0)
+constexpr uint32_t kTwo2 = 0x40004000u;        // half2 (2.0, 2.0)
 
 __device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -113,8 +114,8 @@ struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
 
 // Transition probability for unit weight (W = C), force of infection F -- the reference's expression order, one
 // IEEE operation at a time (:95-112).  pc: 0 = uncolonised, 1 = colonised undetected, 2 = colonised detected.
-__device__ __forceinline__ double class_probability(int pc, int h, double F, double alpha, double alpha2, double gamma) {
-  const double W = pc ? 1.0 : 0.0;
+__device__ __forceinline__ double class_probability(int pc, int h, double F, double alpha, double alpha2, double gamma, double w = 1.0) {
+  const double W = pc ? w : 0.0;   // :95  W = C * w
   const double det = (pc == 2) ? 1.0 : 0.0;
   const double coef = __dadd_rn(__dmul_rn(__dsub_rn(1.0, det), __dsub_rn(1.0, alpha)),
                                 __dmul_rn(det, __dsub_rn(1.0, alpha2)));
@@ -136,16 +137,17 @@ __device__ __forceinline__ uint32_t code_delta(uint32_t cls, bool hit, int ttd) 
 }
 
 // Shared memory (dynamic): the slice parameters, then for EACH WARP the tables of up to kWarpTableSegs ward-days.
-//   free-running: tab  uint4[kWarpTableSegs*2*kNS*kTabRow] at [((ward-day*2 + is_new)*kNS + slice)*kTabRow + e]; word j of an entry belongs
+//   free-running: tab  uint4 at [((ward-day*4 + is_new*2 + half weight)*kNS + slice)*kTabRow + e]; word j of an entry belongs
 //                      to simulations 2j (low half) and 2j+1 (high half); 14-bit Bernoulli thresholds b (rng.cuh):
 //                        e=0  bU               uncolonised:        colonised today  <=>  v14 < bU
 //                        e=1  bU ^ bA          A / pending
 //                        e=2  bA ^ bB          detected
 //                        e=3  bUh              uncolonised, tested positive today (0 when nobody is tested)
 //                        e=4  bUh ^ bAh        A
-//   replay:       P    double[kWarpTableSegs*2][kNS][3][8] the transition probabilities themselves
+//   replay:       P    double at [(((ward-day*4 + is_new*2 + half weight)*kNS + slice)*3 + class)*8 + sim]: the transition probabilities themselves
 constexpr int kWarpTableSegs = 8;              // ring of ward-day tables per warp (power of two)
-constexpr int kZeroRow = kWarpTableSegs * 2;   // + one all-zero row: lanes without a record step against it
+constexpr int kRowsPerSeg = 4;                 // (is_new, weight class): weight 1 / weight 1/2
+constexpr int kZeroRow = kWarpTableSegs * kRowsPerSeg;   // + one all-zero row: lanes without a record step against it
 constexpr int kNS = kSlicesPerTeam;   // slices (of 8 simulations) a team steps together: a thread carries one record x 16 simulations
 // element (uint4) index of slot q of the team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
 __host__ __device__ inline int64_t ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kNS * 32) + (q & 31u); }
@@ -154,7 +156,7 @@ struct WarpShared {
   double* P;
 };
 __host__ __device__ inline size_t warp_table_bytes(bool replay) {
-  return (size_t)(kWarpTableSegs * 2 + 1) * kNS * (replay ? 24 * sizeof(double) : kTabRow * sizeof(uint4));
+  return (size_t)(kWarpTableSegs * kRowsPerSeg + 1) * kNS * (replay ? 24 * sizeof(double) : kTabRow * sizeof(uint4));
 }
 __host__ __device__ inline size_t fast_smem_bytes(bool replay, int threads) {
   return kNS * sizeof(SliceParams) + (size_t)(threads / 32) * warp_table_bytes(replay);
@@ -344,42 +346,49 @@ __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* p
       n_next = __ldg(&a.seg_N[sn]);
     }
     const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
-    // :98-99  F = (beta / N) * sum(W); with unit weights sum(W) is the exact integer count
-    const double F = __dmul_rn(__ddiv_rn(beta, n_seg), (double)cnt);
+    // :98-99  F = (beta / N) * sum(W).  sum(W) is exact: the count of colonised records, or, when some records weigh 1/2,
+    // the count in halves times 0.5 (sums of halves are exact in float64 in any order, Armadillo's two accumulators included)
+    const double sumW = a.has_half ? __dmul_rn((double)cnt, 0.5) : (double)cnt;
+    const double F = __dmul_rn(__ddiv_rn(beta, n_seg), sumW);
     const bool finite = fabs(F) <= 1.7976931348623157e308;
-    if constexpr (REPLAY) {
+    const uint32_t r16 = REPLAY ? 0u : chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gslice0 + (uint32_t)s, kStreamDither,
+                                                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
+#pragma unroll 1
+    for (int wc = 0; wc <= (a.has_half ? 1 : 0); ++wc) {   // weight class of the record: 1, then 1/2
+      const double w = wc ? 0.5 : 1.0;
+      const int trow = ((slot * kRowsPerSeg + h * 2 + wc) * kNS + s);
+      if constexpr (REPLAY) {
 #pragma unroll
-      for (int pc = 0; pc < 3; ++pc) sh.P[(((slot * 2 + h) * kNS + s) * 3 + pc) * 8 + k] = class_probability(pc, h, F, alpha, alpha2, gamma);
-    } else {
-      // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
-      // never re-tested (:131 / :134)
-      const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gslice0 + (uint32_t)s, kStreamDither,
-                                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
-      const double P0 = class_probability(0, h, F, alpha, alpha2, gamma);
-      uint32_t t30[5];
-      t30[0] = threshold30(P0);
-      t30[3] = threshold30(__dmul_rn(clamp01(P0), rho));
-      if (finite) {
-        t30[1] = p.t30[0][h][k]; t30[2] = p.t30[1][h][k]; t30[4] = p.t30[2][h][k];
+        for (int pc = 0; pc < 3; ++pc) sh.P[(trow * 3 + pc) * 8 + k] = class_probability(pc, h, F, alpha, alpha2, gamma, w);
       } else {
-        const double P1 = class_probability(1, h, F, alpha, alpha2, gamma);
-        t30[1] = threshold30(P1);
-        t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma));
-        t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
-      }
-      uint32_t e[5];
+        // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
+        // never re-tested (:131 / :134)
+        const double P0 = class_probability(0, h, F, alpha, alpha2, gamma, w);
+        uint32_t t30[5];
+        t30[0] = threshold30(P0);
+        t30[3] = threshold30(__dmul_rn(clamp01(P0), rho));
+        if (finite && wc == 0) {
+          t30[1] = p.t30[0][h][k]; t30[2] = p.t30[1][h][k]; t30[4] = p.t30[2][h][k];
+        } else {   // a colonised half-weight record feels the ward's pressure too: P = coef/2 + F/2 (:108-109)
+          const double P1 = class_probability(1, h, F, alpha, alpha2, gamma, w);
+          t30[1] = threshold30(P1);
+          t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma, w));
+          t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
+        }
+        uint32_t e[5];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
-      if (!flag) e[3] = e[4] = 0u;
-      // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
+        for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
+        if (!flag) e[3] = e[4] = 0u;
+        // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
-        e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
-      }
-      if (!(k & 1)) {
-        uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + ((slot * 2 + h) * kNS + s) * kTabRow) + (k >> 1);
-        row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
+        for (int q = 0; q < 5; ++q) {
+          const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
+          e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
+        }
+        if (!(k & 1)) {
+          uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + trow * kTabRow) + (k >> 1);
+          row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
+        }
       }
     }
   }
@@ -542,7 +551,8 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           const int h = (int)(info >> kInfoHShift);
           const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
           const bool on = i < n_run && segl - sl < n_tab;   // this batch's records (unsigned compare: segl >= sl too)
-          const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * 2 + h) * kNS : kZeroRow * kNS;
+          const uint32_t wc = (info >> kInfoHalfShift) & 1u;   // the record weighs 1/2
+          const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * kRowsPerSeg + h * 2 + (int)wc) * kNS : kZeroRow * kNS;
           const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
           uint32_t colw[kNW], detw[kNW];
 #pragma unroll
@@ -579,13 +589,18 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
             if (m != wmain) { flush_warp(); wmain = m; }
           }
           const bool has = nseg != kNone, mine = nseg == wmain;
-          const uint32_t mine2 = mine ? kOne2 : 0u;
+          // what the record adds to its successor's ward-day: 1, or -- when the hospital has half-weight records and the
+          // pressure is therefore counted in halves -- 2 if the successor is a whole record and 1 if it is a half one
+          const bool two = a.has_half && !((info >> kInfoNextHalfShift) & 1u);   // the weight is the SUCCESSOR's (W = C * w of the row it becomes)
+          const uint32_t mine2 = mine ? (two ? kTwo2 : kOne2) : 0u;
 #pragma unroll
           for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
           if (has && !mine) {
             uint32_t* dst = c.press + (int64_t)nseg * kNW;
+            const uint32_t sh1 = two ? 9u : 10u;   // 1.0 = 0x3C00 -> 1 (>> 10) or 2 (>> 9, masked to bit 1)
+            const uint32_t msk = two ? 2u * kHalves : kHalves;
 #pragma unroll
-            for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> 10) & kHalves);   // 1.0 = 0x3C00 -> 1
+            for (int q = 0; q < kNW; ++q) red_add(dst + q, (colw[q] >> sh1) & msk);
           }
           if (ptt) ptt += 32 * kNS;
         }
@@ -700,8 +715,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
         }
         __stcg(&c.pre[ring_slot(slot) + s * 32], make_uint4(w[0], w[1], w[2], w[3]));
         const uint32_t iseg = a.init_seg[r];
+        // initial rows sit on day 0 (fast-path condition): position = slot; a whole record counts 2 when pressure is in halves
+        const uint32_t unit = (a.has_half && !((__ldg(&a.meta[a.day_start[0] + slot].x) >> kInfoHalfShift) & 1u)) ? 2u : 1u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&c.press[((int64_t)iseg * kNS + s) * 4 + j], cw[j]);
+        for (int j = 0; j < 4; ++j) if (cw[j]) red_add(&c.press[((int64_t)iseg * kNS + s) * 4 + j], cw[j] * unit);
       }
     }
   }

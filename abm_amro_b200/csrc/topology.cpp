@@ -75,6 +75,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   T.n_days_out = (int64_t)cmax + 1;
   bool sorted = true;
   T.unit_weights = true;
+  T.dyadic_weights = true;
   T.binary_h = true;
   int64_t prev_day = -1;
   double prev_ward = 0.0;
@@ -93,6 +94,8 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
       prev_ward = wv;
       T.Rp++;
       if (T.w[r] != 1.0) T.unit_weights = false;
+      if (T.w[r] == 0.5) T.has_half = true;
+      else if (T.w[r] != 1.0) T.dyadic_weights = false;
       if (!(T.h[r] == 0.0 || T.h[r] == 1.0)) T.binary_h = false;
     } else {
       seen_unstepped = true;
@@ -209,12 +212,12 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
 
   // ---- FAST path encodings ------------------------------------------------------------------------------
   T.why_not_fast.clear();
-  if (!T.unit_weights) T.why_not_fast = "weights other than 1";
+  if (!T.dyadic_weights) T.why_not_fast = "weights other than 1 or 1/2";
   else if (!T.binary_h) T.why_not_fast = "is_new values other than 0/1";
   else if (T.Rp != R) T.why_not_fast = "rows whose day is never stepped";
   else if (!T.simple_final) T.why_not_fast = "next_day links that point to the same or an earlier day";
   else if (!ring) T.why_not_fast = "next_day links that skip a day";
-  else if (T.max_seg_rows > 65535) T.why_not_fast = "a ward-day with more than 65535 records";
+  else if (T.max_seg_rows > (T.has_half ? 32767 : 65535)) T.why_not_fast = "a ward-day with more than 65535 records (32767 with half weights)";
   else if (T.max_rows_per_day >= (int64_t)0xFFFFFFF0u) T.why_not_fast = "too many records in one day";
   else if (T.max_segs_per_day >= (int64_t)kInfoSegMask) T.why_not_fast = "too many wards in one day";
   if (T.why_not_fast.empty()) {
@@ -248,6 +251,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
           const int64_t pp = T.pos_of[pre_src[p]];  // in day d-1 (ring property)
           T.meta_next[pp] = (uint32_t)(p - T.day_start[d]);
           T.meta_nseg[pp] = seg_of_pos[p];
+          if (T.w[r] == 0.5) T.meta_info[pp] |= 1u << kInfoNextHalfShift;   // what pp's state adds to this ward-day's sum(W) is w of THIS row
         } else if (r < n_init) {
           kind = kSrcInit;
           if (d != 0) T.why_not_fast = "initial-state rows outside day 0";
@@ -255,7 +259,8 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
           T.init_slot[r] = (uint32_t)(p - T.day_start[d]);
           T.day_has_init[d] = 1;
         }
-        T.meta_info[p] = (T.h[r] == 1.0 ? (1u << kInfoHShift) : 0u) | (kind << kInfoSrcShift) | seg_local;
+        T.meta_info[p] = (T.h[r] == 1.0 ? (1u << kInfoHShift) : 0u) | (kind << kInfoSrcShift) |
+                         (T.w[r] == 0.5 ? (1u << kInfoHalfShift) : 0u) | seg_local;
       }
     }
   }

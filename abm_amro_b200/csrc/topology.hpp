@@ -12,10 +12,11 @@
 namespace amro {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no segment" / "no successor"
-// meta_info word of a record: bit 31 = is_new, bits 30:29 = where its pre-step state comes from, bits 28:0 = index of
-// its ward-day within the day
+// meta_info word of a record: bit 31 = is_new, bits 30:29 = where its pre-step state comes from, bit 28 = weight 1/2 (a
+// patient split over two wards), bit 27 = its successor weighs 1/2, bits 26:0 = index of its ward-day within the day
 constexpr uint32_t kSrcNone = 0u, kSrcPrev = 1u, kSrcInit = 2u;
-constexpr uint32_t kInfoHShift = 31, kInfoSrcShift = 29, kInfoSegMask = (1u << kInfoSrcShift) - 1u;
+constexpr uint32_t kInfoHShift = 31, kInfoSrcShift = 29, kInfoHalfShift = 28, kInfoNextHalfShift = 27,
+                   kInfoSegMask = (1u << kInfoNextHalfShift) - 1u;
 
 struct HostTopology {
   int64_t R = 0, n_init = 0;
@@ -24,6 +25,8 @@ struct HostTopology {
   int64_t Rp = 0;            // stepped rows: day integer in [0, total_days]
   int64_t n_seg = 0, max_rows_per_day = 0, max_segs_per_day = 0, max_seg_rows = 0;
   bool identity_order = false, unit_weights = false, binary_h = false, simple_final = false;
+  bool dyadic_weights = false;   // every stepped row weighs 1 or 1/2 (the FAST path counts ward pressure in halves then)
+  bool has_half = false;         // ... and some weigh 1/2
   bool fast_eligible = false, ring_eligible = false;
   std::string why_not_fast;
 

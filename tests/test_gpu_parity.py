@@ -60,29 +60,51 @@ def test_replay_matches_reference_golden(golden, name, path, shape):
         _check_against(z["out"], p, got, S)                   # ... and so does the GPU, from the same uniforms
 
 
-def test_replay_fractional_weights_use_the_general_path(golden):
+@pytest.mark.parametrize("path", [capi.PATH_FAST, capi.PATH_GENERAL])
+def test_replay_half_weights_match_reference_golden(golden, path):
+    # patients split over two wards weigh 1/2 in each: the fused kernel counts ward pressure in halves and keeps tables per
+    # weight (a colonised half-weight record feels the ward's pressure too); the float64 path takes any weight
     z = golden("replay_b")
     ttd, tsh, tsa = (int(x) for x in z["args"])
     out, p, t, _ = stream_to_tensors(z["icp"], z["idp"], z["wm"], z["tp"], z["par"], ttd, tsh, tsa, z["stream"])
+    assert set(np.unique(z["wm"][:, 4])) == {0.5, 1.0}
     with engine.Topology(z["wm"], z["tp"], z["icp"].shape[0]) as topo:
-        assert not topo.info.fast_eligible
-        got = topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, rng_mode=capi.RNG_REPLAY, want_state=True, want_p=True, **t)
-        assert got.path_used == capi.PATH_GENERAL
+        assert topo.info.fast_eligible
+        got = topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, rng_mode=capi.RNG_REPLAY, path=path, want_state=True, want_p=True, **t)
+        assert got.path_used == path
         _check_against(z["out"], p, got, z["icp"].shape[1])
+
+
+def test_other_fractional_weights_use_the_general_path():
+    wm, tp, n_init = synth.make_hospital(3, 40, 8, seed=2, p_split=0.3)
+    wm = wm.copy(order="F")
+    wm[wm[:, 4] == 0.5, 4] = 0.25                                    # not 1 or 1/2: only the float64 path takes it
+    S = 5
+    par = synth.particle_parameters(S, seed=1)
+    icp = np.full((n_init, S), 0.3); idp = np.full((n_init, S), 0.4)
+    t = random_tensors(wm.shape[0], S, n_init, seed=3)
+    ref, refp = oracle.simulate_discrete_model(icp, idp, wm, tp, par, 1, 2, 1, 5, return_p=True, rng=oracle.Rng(oracle.RNG_TENSOR, **t))
+    with engine.Topology(wm, tp, n_init) as topo:
+        assert not topo.info.fast_eligible and b"weights" in topo.info.why_not_fast
+        got = topo.simulate(par, icp, idp, 1, 2, 1, 5, rng_mode=capi.RNG_REPLAY, want_state=True, want_p=True, **t)
+        assert got.path_used == capi.PATH_GENERAL
+        _check_against(ref, refp, got, S)
         with pytest.raises(ValueError, match="weights"):
-            topo.simulate(z["par"], z["icp"], z["idp"], ttd, tsh, tsa, 1, path=capi.PATH_FAST)
+            topo.simulate(par, icp, idp, 1, 2, 1, 5, path=capi.PATH_FAST)
 
 
 CASES = [  # wards, census, days, S, ttd, tsh, tsa
     (1, 6, 3, 1, 0, 1, 1), (5, 300, 30, 20, 2, 7, 1), (30, 2000, 12, 64, 2, 7, 1), (4, 100, 15, 9, 0, 1, 3),
     (12, 150, 9, 33, 5, 2, 2), (2, 700, 6, 8, 1, 3, 1),
-    (40, 100, 8, 17, 1, 2, 1)]   # tiny wards: a 32-record trip spans more ward-days than a warp's table ring holds
+    (40, 100, 8, 17, 1, 2, 1),   # tiny wards: a 32-record trip spans more ward-days than a warp's table ring holds
+    (6, 400, 12, 19, 2, 3, 1, 0.2), (3, 90, 10, 16, 0, 1, 1, 0.5)]   # last entry: share of patients split over two wards (weight 1/2)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
 def test_replay_and_philox_match_oracle(case, shape):
-    nw, cen, nd, S, ttd, tsh, tsa = case
-    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=nw + cen)
+    nw, cen, nd, S, ttd, tsh, tsa = case[:7]
+    p_split = case[7] if len(case) > 7 else 0.0
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=nw + cen, p_split=p_split)
     par = synth.particle_parameters(S, seed=3)
     g = np.random.default_rng(1)
     icp, idp = g.random((n_init, S)) * 0.6, g.random((n_init, S))
@@ -93,9 +115,9 @@ def test_replay_and_philox_match_oracle(case, shape):
     with engine.Topology(wm, tp, n_init) as topo:
         for path in (capi.PATH_FAST, capi.PATH_GENERAL):
             got = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, rng_mode=capi.RNG_REPLAY, path=path, want_state=True,
-                                want_p=True, want_pressure=(path == capi.PATH_FAST), **t)
+                                want_p=True, want_pressure=(path == capi.PATH_FAST and p_split == 0.0), **t)
             _check_against(ref, refp, got, S)
-            if path == capi.PATH_FAST:   # per-ward colonisation-pressure counts (the reference's sum(W), :99)
+            if path == capi.PATH_FAST and p_split == 0.0:   # per-ward colonisation-pressure counts (the reference's sum(W), :99)
                 c0 = (t["u_icol"] < icp).astype(float)
                 assert np.array_equal(got.pressure, expected_pressure(wm, n_init, got.state, c0, topo.debug_arrays()))
             free = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path, want_state=True)

@@ -110,6 +110,9 @@ def test_topology_compiler_sorts_like_the_reference_visits():
 def test_fast_path_eligibility_reasons():
     wm, tp, n_init = synth.make_hospital(3, 30, 6, seed=5, p_split=0.3)
     with engine.Topology(wm, tp, n_init, device=-1) as t:
+        assert t.info.fast_eligible                                             # weights 1 and 1/2: pressure counted in halves
+    w2 = wm.copy(); w2[w2[:, 4] == 0.5, 4] = 0.3
+    with engine.Topology(w2, tp, n_init, device=-1) as t:
         assert not t.info.fast_eligible and b"weights" in t.info.why_not_fast
     wm, tp, n_init = synth.make_hospital(3, 30, 6, seed=5)
     w2 = wm.copy(); w2[0, 3] = 0.5
