@@ -170,6 +170,35 @@ def test_distance_to_data_is_computed_on_the_device(path):
         assert np.allclose(only_d.distance, np.nansum((d - obs_d[:, None]) ** 2, 0), rtol=1e-13, atol=0)
 
 
+def test_degenerate_wards_and_extreme_parameters_match_the_oracle():
+    # N = 0 gives an infinite or NaN force of infection and comparisons that are simply false; probabilities
+    # above 1 and below 0 are not clamped; a schedule longer than the run never tests; ttd = 0 detects on the day of the test
+    wm, tp, n_init = synth.make_hospital(6, 90, 9, seed=31, p_split=0.2)
+    tp = tp.copy(order="F")
+    tp[(tp[:, 1] == 2), 2] = 0.0                                      # ward 2: N = 0 every day -> F = inf (or NaN when nobody is colonised)
+    S = 24
+    par = synth.particle_parameters(S, seed=2)
+    par[0] = [0.0, 5.0, 0.9, 1.0, 0.0, 1.0]                          # never clears, beta so large that P > 1
+    par[1] = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]                          # always clears, nothing transmits, nothing is detected
+    par[2] = [1.5, -0.3, -0.1, 2.0, -0.5, 0.5]                       # outside [0, 1] everywhere
+    g = np.random.default_rng(3)
+    icp, idp = g.random((n_init, S)), g.random((n_init, S))
+    t = random_tensors(wm.shape[0], S, n_init, seed=9)
+    for ttd, tsh, tsa in ((0, 1, 1), (3, 1000, 2), (7, 2, 1000)):
+        with np.errstate(all="ignore"):
+            ref, refp = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 4, return_p=True,
+                                                       rng=oracle.Rng(oracle.RNG_TENSOR, **t))
+            ref_free = oracle.simulate_discrete_model(icp, idp, wm, tp, par, ttd, tsh, tsa, 4, rng=oracle.Rng(oracle.RNG_PHILOX))
+        with engine.Topology(wm, tp, n_init) as topo:
+            assert topo.info.fast_eligible
+            for path in (capi.PATH_FAST, capi.PATH_GENERAL):
+                got = topo.simulate(par, icp, idp, ttd, tsh, tsa, 4, rng_mode=capi.RNG_REPLAY, path=path, want_state=True, want_p=True, **t)
+                assert np.array_equal(got.state, ref[:, 6:])
+                assert np.array_equal(got.p, refp, equal_nan=True)      # inf and NaN probabilities included, bit for bit
+                free = topo.simulate(par, icp, idp, ttd, tsh, tsa, 4, path=path, want_state=True)
+                assert np.array_equal(free.state, ref_free[:, 6:])
+
+
 def test_long_runs_flush_the_per_lane_counters(monkeypatch):
     # one CTA per team and 150,000 records a day: every warp steps more than 1024 trips a day, so the per-lane half-precision
     # day counters (exact up to 1024) are flushed in the middle of a run
