@@ -239,6 +239,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const int64_t S = A->n_sims, S_pad = (S + kTeamSims - 1) / kTeamSims * kTeamSims, n_slices = S_pad / kSimsPerSlice;
   const int64_t n_teams = n_slices / kSlicesPerTeam;   // padded simulations have zero parameters and are never read back
   const bool want_traj = A->keep_trajectory || A->state_out;
+  const bool lean = !replay && !want_traj && !H.has_half && H.identity_order;   // the kernel instance without those cases
   // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, six per SM, G of them per slice) measured equal or better
   // than WIDE (one 768-thread CTA per slice) on every configuration tried (profiles/sweeps.txt), so it is the default;
   // AMRO_FAST_SHAPE=w forces WIDE (kept for the tests and for comparison).
@@ -251,7 +252,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // fuller SMs make their teams' barriers late).  AMRO_FAST_G fixes the team size, AMRO_FAST_CTAS_PER_SM caps the slots.
   int G = 1, extra = 0;
   if (shape == kShapeTeam) {
-    int cap = fast_max_coresident_ctas(T->device, replay, shape);
+    int cap = fast_max_coresident_ctas(T->device, replay, lean, shape);
     if (cap <= 0) fail(AMRO_ECUDA, "fast kernel cannot be made resident on this device");
     if (const char* e = std::getenv("AMRO_FAST_CTAS_PER_SM")) cap = std::min(cap, std::max(1, std::atoi(e)) * sms);
     // every warp pays a fixed price per day (barrier, tables, totals): it wants about a dozen 32-record trips to spread it
@@ -276,7 +277,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)
     int Gc = G;
     if (!std::getenv("AMRO_FAST_G") && Gc > 2 && (Gc & 1)) Gc -= 1;
-    if (want && fast_max_coresident_clusters(T->device, replay, shape, Gc) >= n_teams) { use_cluster = 1; G = Gc; }
+    if (want && fast_max_coresident_clusters(T->device, replay, lean, shape, Gc) >= n_teams) { use_cluster = 1; G = Gc; }
   }
   const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
   if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
@@ -328,7 +329,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
-  fast_launch(st, f, replay, shape, (int)(n_teams * G + extra));
+  fast_launch(st, f, replay, lean, shape, (int)(n_teams * G + extra));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
 

@@ -123,9 +123,10 @@ inline int64_t fast_ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kSlicesP
 size_t fast_shared_bytes(bool replay, int shape);
 int fast_threads(int shape);
 // CTAs of the given launch shape that can be co-resident (bound of a cooperative launch)
-int fast_max_coresident_ctas(int device, bool replay, int shape);
-int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster_size);
-void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid);
+int fast_max_coresident_ctas(int device, bool replay, bool lean, int shape);
+int fast_max_coresident_clusters(int device, bool replay, bool lean, int shape, int cluster_size);
+// lean: no trajectory, unit weights, rows already in (day, ward) order: the instance compiled without the other cases
+void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, bool lean, int shape, int grid);
 
 // Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run
 void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,

@@ -313,7 +313,7 @@ struct TeamCtx {
 // The probabilities of colonised patients (:103-112 with W = 1) do not depend on the ward's pressure unless the force of
 // infection is not finite (N = 0): their 30-bit thresholds are evaluated once per run (SliceParams::t30) and only the
 // ward-day's dither is added here; a non-finite force takes the general expression.
-template <bool REPLAY>
+template <bool REPLAY, bool LEAN>
 __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* par, const FastArgs& a, const uint32_t* press, uint32_t gslice0,
                                           int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
   const int lane = threadIdx.x & 31;
@@ -348,13 +348,13 @@ __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* p
     const uint32_t cnt = (k & 1) ? (pk >> 16) : (pk & 0xFFFFu);
     // :98-99  F = (beta / N) * sum(W).  sum(W) is exact: the count of colonised records, or, when some records weigh 1/2,
     // the count in halves times 0.5 (sums of halves are exact in float64 in any order, Armadillo's two accumulators included)
-    const double sumW = a.has_half ? __dmul_rn((double)cnt, 0.5) : (double)cnt;
+    const double sumW = (!LEAN && a.has_half) ? __dmul_rn((double)cnt, 0.5) : (double)cnt;
     const double F = __dmul_rn(__ddiv_rn(beta, n_seg), sumW);
     const bool finite = fabs(F) <= 1.7976931348623157e308;
     const uint32_t r16 = REPLAY ? 0u : chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gslice0 + (uint32_t)s, kStreamDither,
                                                             (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
 #pragma unroll 1
-    for (int wc = 0; wc <= (a.has_half ? 1 : 0); ++wc) {   // weight class of the record: 1, then 1/2
+    for (int wc = 0; wc <= ((!LEAN && a.has_half) ? 1 : 0); ++wc) {   // weight class of the record: 1, then 1/2
       const double w = wc ? 0.5 : 1.0;
       const int trow = ((slot * kRowsPerSeg + h * 2 + wc) * kNS + s);
       if constexpr (REPLAY) {
@@ -466,7 +466,9 @@ __device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32
 // ---- one day of the team's slices: the run of the day's records that belongs to this warp (abm_wards.cpp:384-407) ----
 // FIRST: the day of the initial state (its records may hold U0); a separate instance keeps that variant of the step out of
 // the loop every other day runs.
-template <bool REPLAY, bool FIRST>
+// LEAN: a summary run (no trajectory) of a hospital with unit weights whose rows are already in (day, ward) order -- the
+// common case, compiled without the code (and the registers) of the other cases.
+template <bool REPLAY, bool FIRST, bool LEAN>
 __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, const SliceParams* par, const FastArgs& a,
                                             const TeamCtx& c, int64_t d, const DayPlan& pl, TeamBarrier& bar) {
   const int lane = threadIdx.x & 31;
@@ -488,7 +490,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kNS * 32) + lane;   // this lane's slot of the run's first chunk
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
     const uint4* pm = a.meta + da + pl.w0 + lane;
-    uint4* pt = c.traj ? c.traj + (da + pl.w0 + lane) * kNS : nullptr;
+    uint4* pt = (!LEAN && c.traj) ? c.traj + (da + pl.w0 + lane) * kNS : nullptr;
     const uint32_t x2 = kCodeA2 ^ ((kCodeZero - (uint32_t)a.ttd) * kHalves);   // A <-> "D = ttd" (:135 / :147)
 
     uint32_t pacc[kNW], wmain = kNone, wsegl = 0xFFFFFFFFu;  // wmain / wsegl are warp-uniform
@@ -509,7 +511,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kWarpTableSegs) {
       const uint32_t n_tab = min((uint32_t)kWarpTableSegs, pl.sl_last + 1u - sl);
       __syncwarp();   // the previous batch's rows are no longer read
-      build_tables<REPLAY>(sh, par, a, c.press, c.gslice0, seg0, sl, sl + n_tab, test_h, test_a);
+      build_tables<REPLAY, LEAN>(sh, par, a, c.press, c.gslice0, seg0, sl, sl + n_tab, test_h, test_a);
       __syncwarp();
       PHASE_ADD(0);  // table
       // trips (32-record chunks of the run) that hold records of these ward-days
@@ -549,7 +551,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           }
           const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
           const int h = (int)(info >> kInfoHShift);
-          const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
+          const int64_t orig = (LEAN || a.identity_order) ? da + pl.w0 + i : (int64_t)meta.w;
           const bool on = i < n_run && segl - sl < n_tab;   // this batch's records (unsigned compare: segl >= sl too)
           const uint32_t wc = (info >> kInfoHalfShift) & 1u;   // the record weighs 1/2
           const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * kRowsPerSeg + h * 2 + (int)wc) * kNS : kZeroRow * kNS;
@@ -591,7 +593,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           const bool has = nseg != kNone, mine = nseg == wmain;
           // what the record adds to its successor's ward-day: 1, or -- when the hospital has half-weight records and the
           // pressure is therefore counted in halves -- 2 if the successor is a whole record and 1 if it is a half one
-          const bool two = a.has_half && !((info >> kInfoNextHalfShift) & 1u);   // the weight is the SUCCESSOR's (W = C * w of the row it becomes)
+          const bool two = (!LEAN && a.has_half) && !((info >> kInfoNextHalfShift) & 1u);   // the weight is the SUCCESSOR's (W = C * w of the row it becomes)
           const uint32_t mine2 = mine ? (two ? kTwo2 : kOne2) : 0u;
 #pragma unroll
           for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
@@ -618,7 +620,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
   PHASE_ADD(2);  // totals
 }
 
-template <bool REPLAY, int THREADS, int MINB>
+template <bool REPLAY, bool LEAN, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kWarps = THREADS / 32;
@@ -730,8 +732,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   for (int64_t d = 0; d < a.n_days; ++d) {
     bar.wait();
     PHASE_ADD(3);  // team barrier wait
-    if (d == 0) process_day<REPLAY, true>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
-    else process_day<REPLAY, false>(PHASE_ARG sh, par, a, c, d, plan, bar);
+    if (d == 0) process_day<REPLAY, true, LEAN>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
+    else process_day<REPLAY, false, LEAN>(PHASE_ARG sh, par, a, c, d, plan, bar);
     plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
@@ -784,20 +786,24 @@ extern "C" void amro_debug_phase_cycles(unsigned long long* out, int reset) {
 //   TEAM  small CTAs, several per SM, cooperate on a slice with one team barrier per day (cooperative launch).  For
 //         few simulations and many records per day.
 namespace {
-template <bool REPLAY>
-const void* kernel_ptr(int shape) {
-  return shape == kShapeWide    ? (const void*)k_fast<REPLAY, kWideThreads, 1>
-         : shape == kShapeRoomy ? (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks - 1>
-                                : (const void*)k_fast<REPLAY, kTeamThreads, kTeamMinBlocks>;
+template <bool REPLAY, bool LEAN>
+const void* kernel_ptr_of(int shape) {
+  return shape == kShapeWide    ? (const void*)k_fast<REPLAY, LEAN, kWideThreads, 1>
+         : shape == kShapeRoomy ? (const void*)k_fast<REPLAY, LEAN, kTeamThreads, kTeamMinBlocks - 1>
+                                : (const void*)k_fast<REPLAY, LEAN, kTeamThreads, kTeamMinBlocks>;
+}
+// the lean instance exists for free-running runs only (replay is a correctness mode)
+const void* kernel_ptr(bool replay, bool lean, int shape) {
+  return replay ? kernel_ptr_of<true, false>(shape) : lean ? kernel_ptr_of<false, true>(shape) : kernel_ptr_of<false, false>(shape);
 }
 }  // namespace
 
 int fast_threads(int shape) { return shape == kShapeWide ? kWideThreads : kTeamThreads; }
 size_t fast_shared_bytes(bool replay, int shape) { return fast_smem_bytes(replay, fast_threads(shape)); }
 
-int fast_max_coresident_ctas(int device, bool replay, int shape) {
+int fast_max_coresident_ctas(int device, bool replay, bool lean, int shape) {
   int per_sm = 0, sms = 0;
-  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+  const void* k = kernel_ptr(replay, lean, shape);
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -806,9 +812,9 @@ int fast_max_coresident_ctas(int device, bool replay, int shape) {
 }
 
 // CTAs of the cluster launch that can be co-resident, in clusters (0 if the shape cannot be launched as clusters)
-int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster_size) {
+int fast_max_coresident_clusters(int device, bool replay, bool lean, int shape, int cluster_size) {
   (void)device;
-  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+  const void* k = kernel_ptr(replay, lean, shape);
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   if (cluster_size > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -825,8 +831,8 @@ int fast_max_coresident_clusters(int device, bool replay, int shape, int cluster
   return n;
 }
 
-void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, int shape, int grid) {
-  const void* k = replay ? kernel_ptr<true>(shape) : kernel_ptr<false>(shape);
+void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, bool lean, int shape, int grid) {
+  const void* k = kernel_ptr(replay, lean, shape);
   const size_t smem = fast_smem_bytes(replay, fast_threads(shape));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
