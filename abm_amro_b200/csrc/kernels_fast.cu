@@ -604,12 +604,13 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           for (int q = 0; q < kNW; ++q) pacc[q] = h2_fma(colw[q], mine2, pacc[q]);
           if (has && !mine) {
             uint32_t* dst = c.press + (int64_t)nseg * kNW;
-            const uint32_t sh1 = two ? 9u : 10u;   // 1.0 = 0x3C00 -> 1 (>> 10) or 2 (>> 9, masked to bit 1)
-            const uint32_t msk = two ? 2u * kHalves : kHalves;
+            // half flags (0x3C00 per half-word) -> integer 1 (or 2) per half-word with one multiply-high on the FMA pipe:
+            // floor(0x3C00 * 279621 / 2^32) = 1, floor(0x3C000000 * 279621 / 2^32) = 65536, and their sum for both
+            const uint32_t mul = two ? 559242u : 279621u;
 #pragma unroll
             for (int q = 0; q < kNW; q += 2) {   // (the 128-register lean instance measured faster with 32-bit REDs)
-              if constexpr (LEAN) { red_add(dst + q, (colw[q] >> sh1) & msk); red_add(dst + q + 1, (colw[q + 1] >> sh1) & msk); }
-              else red_add2(dst + q, (colw[q] >> sh1) & msk, (colw[q + 1] >> sh1) & msk);
+              if constexpr (LEAN) { red_add(dst + q, __umulhi(colw[q], mul)); red_add(dst + q + 1, __umulhi(colw[q + 1], mul)); }
+              else red_add2(dst + q, __umulhi(colw[q], mul), __umulhi(colw[q + 1], mul));
             }
           }
           if (ptt) ptt += 32 * kNS;
