@@ -274,9 +274,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (shape != kShapeWide && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
     const char* e = std::getenv("AMRO_FAST_BARRIER");
     const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
-    // clusters of an even size pack the GPCs better: measured on config 2, 6 and 8 CTAs beat 5 and 7 (profiles/sweeps.txt)
-    int Gc = G;
-    if (!std::getenv("AMRO_FAST_G") && Gc > 2 && (Gc & 1)) Gc -= 1;
+    const int Gc = G;
     if (want && fast_max_coresident_clusters(T->device, replay, lean, shape, Gc) >= n_teams) { use_cluster = 1; G = Gc; }
   }
   const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
