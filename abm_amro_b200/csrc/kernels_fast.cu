@@ -2,7 +2,7 @@
 //
 // Replaces the nest  simulate_discrete_model_internal_one -> progress_patients_1_timestep ->
 // progress_patients_probability_ward_1_timestep  (src/amro/abm_wards.cpp:322-414 / :219-257 / :70-159) fused
-// with total_positive_colonized/_detected (:435-509), for hospitals with unit weights, is_new in {0,1},
+// with total_positive_colonized/_detected (:435-509), for hospitals with weights in {1, 1/2}, is_new in {0,1},
 // time_to_detect >= 0 and next_day links that connect consecutive days.
 //
 // State of one (record, simulation): a 16-bit code.
@@ -19,20 +19,24 @@
 //   steps like D = 0 with the probability of an uncolonised patient.
 //
 // Data layout (HBM):
-//   pre       [set][2][max records per day]  one 16-byte word = 8 simulations per record; buffer d&1 holds the
-//             state the records of day d start from.  A record's step WRITES its result into its successor's
-//             slot of buffer (d+1)&1 (next_day is a scatter, :402-407), so reading the pre-step state needs no
-//             dependent load.  Records without a predecessor ignore the slot and start uncolonised (:359-360).
-//   pressure  [set][ward-day][4] packed 16-bit counts: colonised patients a ward-day STARTS with = the
-//             reference's sum(W) (:99), accumulated by the previous day's pass (every record adds its new C to
-//             the ward-day of its successor): one pass over a day's records instead of two.
-//   meta      three 32-bit words per record shared by all simulations: (is_new, source, ward-day), successor
-//             slot, successor ward-day.
-// Work decomposition: a TEAM of ctas_per_team CTAs owns one slice (8 simulations) for every day; lanes map to
-// consecutive records, so state loads/stores are 128-bit and coalesced.  Teams never talk to each other; inside
-// a team the CTAs split each day's records and meet at one barrier per day.  Per ward-day, per simulation, the
-// transition probabilities a record can have (class x is_new) are evaluated in fp64 exactly as the reference
-// evaluates them and turned into integer thresholds kept in shared memory.
+//   ring      [team][2][chunk of 32 records][slice][32] one 16-byte word = 8 simulations of one record
+//             (fast_ring_slot); buffer d&1 holds the state the records of day d start from.  A record's step
+//             WRITES its result into its successor's slot of buffer (d+1)&1 (next_day is a scatter, :402-407),
+//             so reading the pre-step state needs no dependent load.  Records without a predecessor ignore the
+//             slot and start uncolonised (:359-360).
+//   pressure  [team][ward-day][slice][4] packed 16-bit counts (in halves when the hospital has weight-1/2 records):
+//             colonised weight a ward-day STARTS with = the reference's sum(W) (:99), accumulated by the previous
+//             day's pass (every record adds its new C to the ward-day of its successor): one pass over a day's
+//             records instead of two.
+//   meta      one uint4 per record shared by all simulations: (is_new | source kind | weight bits | ward-day index
+//             inside its day), successor's byte offset in the ring, successor's ward-day, original row.
+// Work decomposition: a TEAM of ctas_per_team CTAs owns kSlicesPerTeam slices (8 simulations each) for every day; a
+// lane holds one record x 16 simulations, lanes map to consecutive records, so state loads/stores are 128-bit and
+// coalesced.  Teams never talk to each other; inside a team the warps split each day's records into contiguous runs
+// and meet at one barrier per day (__syncthreads, the cluster barrier, or a release/acquire counter in global memory).
+// Per ward-day, per simulation, the transition probabilities a record can have (class x is_new x weight) are evaluated
+// in fp64 exactly as the reference evaluates them and turned into dithered 14-bit thresholds (rng.cuh) that every warp
+// builds into its own shared-memory table ring.
 #include "common.hpp"
 #include "kernels.hpp"
 #include "rng.cuh"
