@@ -1,5 +1,6 @@
 // C ABI of libamro_b200.so (include/amro_b200.h): host orchestration around the CUDA kernels.
 // There is no CPU fallback: every compute entry point needs a CUDA device and fails with AMRO_ECUDA otherwise.
+#include <cstdio>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -247,6 +248,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
   int shape = kShapeTeam;
   if (const char* e = std::getenv("AMRO_FAST_SHAPE")) shape = (e[0] == 'w') ? kShapeWide : kShapeTeam;
+  if (shape == kShapeWide && fast_shared_bytes(replay, shape) > (size_t)227 * 1024) shape = kShapeTeam;   // replay tables of 16 warps do not fit
   // Team size: all resident CTA slots are dealt out to the teams, the first `extra` teams taking one more, so that every SM
   // hosts the same number of CTAs (measured: a grid that leaves some SMs one CTA short is ~5-10 % slower, because the
   // fuller SMs make their teams' barriers late).  AMRO_FAST_G fixes the team size, AMRO_FAST_CTAS_PER_SM caps the slots.
@@ -325,6 +327,9 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));
   f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.teams_plus_one = extra; f.cluster_barrier = use_cluster;
 
+  if (std::getenv("AMRO_FAST_VERBOSE"))   // development: the launch shape chosen
+    std::fprintf(stderr, "[amro] fast launch: shape %d lean %d teams %lld G %d extra %d cluster %d grid %lld threads %d smem %zu\n", shape, (int)lean,
+                 (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), fast_threads(shape), fast_shared_bytes(replay, shape));
   EventPair ev;
   AMRO_CUDA(cudaEventRecord(ev.a, st));
   fast_launch(st, f, replay, lean, shape, (int)(n_teams * G + extra));

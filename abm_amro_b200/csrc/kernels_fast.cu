@@ -264,18 +264,18 @@ __device__ __forceinline__ uint4 step_record_replay(const WarpShared& sh, const 
 // The warps that share a team's slices (all warps of the team's CTAs) meet once per day: a warp may start day d+1 when
 // every warp of the team has finished day d (its successors' states and tomorrow's pressure are then complete).  Arrival
 // is a release increment of the team's counter by lane 0 after __syncwarp (which orders the other lanes' writes before
-// it); waiting is a relaxed poll by lane 0, one acquire fence, __syncwarp.  Nothing in the day loop synchronises a whole
+// it); waiting is an acquire-load poll by lane 0, then __syncwarp.  Nothing in the day loop synchronises a whole
 // CTA, so the latency of one warp's barrier or table build is covered by the other warps of the SM.  A team of one CTA
 // uses the hardware barrier instead.  The cooperative launch guarantees co-residency.
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 // Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
 //   kBarCta      a team of one CTA: __syncthreads
 //   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
-//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, relaxed poll + acquire fence)
+//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, acquire-load poll)
 constexpr int kBarCta = 0, kBarGlobal = 1, kBarCluster = 2;
 struct TeamBarrier {
   unsigned* ctr;
@@ -300,8 +300,7 @@ struct TeamBarrier {
       return;
     }
     if ((threadIdx.x & 31) == 0) {
-      while ((int)(ld_relaxed(ctr) - target) < 0) {}
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      while ((int)(ld_acquire(ctr) - target) < 0) {}   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
     }
     __syncwarp();
   }

@@ -14,4 +14,4 @@ with engine.Topology(wm, tp, n_init) as topo:
         r = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)
         ms.append(r.kernel_ms)
     upd = wm.shape[0] * S
-    print(f"{os.environ.get('AMRO_FAST_SHAPE','auto')} G={os.environ.get('AMRO_FAST_G','auto')}: {nw}w x {cen} x {nd}d x {S}: kernel {min(ms):.3f} ms, {upd / min(ms) / 1e6:.1f} G updates/s, frac {upd * (4 + 20 / S) / (min(ms) * 1e-3) / 6454.6e9:.3f}, total {r.total_ms:.2f} ms")
+    print(f"{os.environ.get('AMRO_FAST_SHAPE','auto')} G={os.environ.get('AMRO_FAST_G','auto')}: {nw}w x {cen} x {nd}d x {S}: kernel {min(ms):.3f} ms, {upd / min(ms) / 1e6:.1f} G updates/s, frac {upd * (4 + 20 / S) / (min(ms) * 1e-3) / 6454.6e9:.3f}, total {r.total_ms:.2f} ms, checksum {int(r.counts_colonized.astype(np.int64).sum())}/{int(r.counts_detected.astype(np.int64).sum())}")
