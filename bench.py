@@ -36,6 +36,9 @@ WORKLOADS = {
     "cfg1_5w_300p_100d_20s": (5, 300, 100, 20),
     "cfg2_30w_10kp_365d_1000s": (30, 10_000, 365, 1000),
     "cfg3_20w_5kp_180d_65536s": (20, 5_000, 180, 65_536),
+    # regional network at its full size: 3.65e8 patient-day rows (17.5 GB of float64 tables on the host, generated
+    # in ~1.5 min, compiled in ~0.5 min); not a default bench line, run with --workload and a few steps
+    "cfg4_500w_1Mp_365d_256s": (500, 1_000_000, 365, 256),
 }
 DEFAULT_WORKLOAD = "cfg2_30w_10kp_365d_1000s"
 TTD, TSH, TSA, SEED, ICP, IDP = 2, 7, 1, 42, 0.2, 0.2
@@ -129,6 +132,7 @@ def cpu_sample(workload: str, sample_days: int = 60, sims_per_proc: int = 32, re
     from abm_amro_b200 import synth
     from oracle import ref_runner
     wards, census, days, _ = WORKLOADS[workload]
+    sample_days = max(1, min(sample_days, 600_000 // census))   # about 6e5 patient-day rows per process
     wm, tp, n_init = synth.make_hospital(wards, census, min(days, sample_days), seed=1)
     R = wm.shape[0]
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
