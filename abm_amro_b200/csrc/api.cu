@@ -241,10 +241,11 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const int64_t n_teams = n_slices / kSlicesPerTeam;   // padded simulations have zero parameters and are never read back
   const bool want_traj = A->keep_trajectory || A->state_out;
   bool lean = !replay && !want_traj && !H.has_half && H.identity_order;   // the kernel instance without those cases
+  if (std::getenv("AMRO_FAST_NOLEAN")) lean = false;
   // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, six per SM, G of them per slice) measured equal or better
   // than WIDE (one 768-thread CTA per slice) on every configuration tried (profiles/sweeps.txt), so it is the default;
-  // AMRO_FAST_SHAPE=w forces WIDE (kept for the tests and for comparison); AMRO_FAST_LEAN keeps the lean instance at the
-  // roomy register budget and AMRO_FAST_VERBOSE prints the launch shape chosen (development).
+  // AMRO_FAST_SHAPE=w forces WIDE (kept for the tests and for comparison); AMRO_FAST_NOLEAN=1 runs the full instance where the
+  // lean one would do and AMRO_FAST_VERBOSE prints the launch shape chosen (development).
   int sms = 0;
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
   int shape = kShapeTeam;
@@ -272,7 +273,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // A grid that leaves a quarter of the CTA slots empty anyway runs the instance compiled for three CTAs per SM (168
   // registers per thread instead of 128: the scheduler has room to overlap the eight pairs of a record): +3 % on config 2
   if (shape == kShapeTeam && !std::getenv("AMRO_FAST_SHAPE") && (int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms)
-    { shape = kShapeRoomy; if (!std::getenv("AMRO_FAST_LEAN")) lean = false; }   // with 168 registers the lean instance measured 3 % slower on config 2: not used there
+    shape = kShapeRoomy;   // the lean instance stays lean (with 64-bit REDs there: kernels_fast.cu)
   int use_cluster = 0;
   if (shape != kShapeWide && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
     const char* e = std::getenv("AMRO_FAST_BARRIER");

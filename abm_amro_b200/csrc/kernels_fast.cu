@@ -272,6 +272,9 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+#ifndef AMRO_POLL_NS
+#define AMRO_POLL_NS 0
+#endif
 // Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
 //   kBarCta      a team of one CTA: __syncthreads
 //   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
@@ -299,8 +302,13 @@ struct TeamBarrier {
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       return;
     }
+#ifdef AMRO_EXP_NOBAR
+    return;   // timing only (wrong results)
+#endif
     if ((threadIdx.x & 31) == 0) {
-      while ((int)(ld_acquire(ctr) - target) < 0) {}   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
+      // acquire load = load + L1 invalidate, without the MEMBAR of a fence; the pause keeps the polling warp out of the issue
+      // slots of the SM's working warps (unpaced, a warp polled ~150 times per day)
+      while ((int)(ld_acquire(ctr) - target) < 0) { if (AMRO_POLL_NS > 0) __nanosleep(AMRO_POLL_NS); }
     }
     __syncwarp();
   }
@@ -476,7 +484,9 @@ __device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32
 // the loop every other day runs.
 // LEAN: a summary run (no trajectory) of a hospital with unit weights whose rows are already in (day, ward) order -- the
 // common case, compiled without the code (and the registers) of the other cases.
-template <bool REPLAY, bool FIRST, bool LEAN>
+// RED64: the transfers' pressure words are added two at a time (64-bit REDs).  Faster where the register budget is roomy
+// (config 2: 5.99 -> 5.68 ms with the lean instance), slower in the 128-register lean instance (particle sweep: 36.5 -> 38.7 ms).
+template <bool REPLAY, bool FIRST, bool LEAN, bool RED64>
 __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, const SliceParams* par, const FastArgs& a,
                                             const TeamCtx& c, int64_t d, const DayPlan& pl, TeamBarrier& bar) {
   const int lane = threadIdx.x & 31;
@@ -519,6 +529,9 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kWarpTableSegs) {
       const uint32_t n_tab = min((uint32_t)kWarpTableSegs, pl.sl_last + 1u - sl);
       __syncwarp();   // the previous batch's rows are no longer read
+#ifdef AMRO_EXP_NOTAB
+      if (d < 2)   // timing only (wrong results)
+#endif
       build_tables<REPLAY, LEAN>(sh, par, a, c.press, c.gslice0, seg0, sl, sl + n_tab, test_h, test_a);
       __syncwarp();
       PHASE_ADD(0);  // table
@@ -611,8 +624,8 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
             // floor(0x3C00 * 279621 / 2^32) = 1, floor(0x3C000000 * 279621 / 2^32) = 65536, and their sum for both
             const uint32_t mul = two ? 559242u : 279621u;
 #pragma unroll
-            for (int q = 0; q < kNW; q += 2) {   // (the 128-register lean instance measured faster with 32-bit REDs)
-              if constexpr (LEAN) { red_add(dst + q, __umulhi(colw[q], mul)); red_add(dst + q + 1, __umulhi(colw[q + 1], mul)); }
+            for (int q = 0; q < kNW; q += 2) {
+              if constexpr (!RED64) { red_add(dst + q, __umulhi(colw[q], mul)); red_add(dst + q + 1, __umulhi(colw[q + 1], mul)); }
               else red_add2(dst + q, __umulhi(colw[q], mul), __umulhi(colw[q + 1], mul));
             }
           }
@@ -636,6 +649,7 @@ template <bool REPLAY, bool LEAN, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kWarps = THREADS / 32;
+  constexpr bool kRed64 = !LEAN || (THREADS == kTeamThreads && MINB < kTeamMinBlocks);   // the roomy instance
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   SliceParams* par = reinterpret_cast<SliceParams*>(smem_raw);   // [kNS]
   const WarpShared sh = carve_shared<REPLAY>(smem_raw + kNS * sizeof(SliceParams), warp);
@@ -744,8 +758,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   for (int64_t d = 0; d < a.n_days; ++d) {
     bar.wait();
     PHASE_ADD(3);  // team barrier wait
-    if (d == 0) process_day<REPLAY, true, LEAN>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
-    else process_day<REPLAY, false, LEAN>(PHASE_ARG sh, par, a, c, d, plan, bar);
+    if (d == 0) process_day<REPLAY, true, LEAN, kRed64>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
+    else process_day<REPLAY, false, LEAN, kRed64>(PHASE_ARG sh, par, a, c, d, plan, bar);
     plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
