@@ -272,9 +272,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-#ifndef AMRO_POLL_NS
-#define AMRO_POLL_NS 0
-#endif
 // Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
 //   kBarCta      a team of one CTA: __syncthreads
 //   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
@@ -302,13 +299,8 @@ struct TeamBarrier {
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       return;
     }
-#ifdef AMRO_EXP_NOBAR
-    return;   // timing only (wrong results)
-#endif
     if ((threadIdx.x & 31) == 0) {
-      // acquire load = load + L1 invalidate, without the MEMBAR of a fence; the pause keeps the polling warp out of the issue
-      // slots of the SM's working warps (unpaced, a warp polled ~150 times per day)
-      while ((int)(ld_acquire(ctr) - target) < 0) { if (AMRO_POLL_NS > 0) __nanosleep(AMRO_POLL_NS); }
+      while ((int)(ld_acquire(ctr) - target) < 0) {}   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
     }
     __syncwarp();
   }
@@ -529,9 +521,6 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
     for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kWarpTableSegs) {
       const uint32_t n_tab = min((uint32_t)kWarpTableSegs, pl.sl_last + 1u - sl);
       __syncwarp();   // the previous batch's rows are no longer read
-#ifdef AMRO_EXP_NOTAB
-      if (d < 2)   // timing only (wrong results)
-#endif
       build_tables<REPLAY, LEAN>(sh, par, a, c.press, c.gslice0, seg0, sl, sl + n_tab, test_h, test_a);
       __syncwarp();
       PHASE_ADD(0);  // table
