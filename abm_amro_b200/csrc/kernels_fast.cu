@@ -316,7 +316,7 @@ struct TeamCtx {
 };
 
 // ---- tables of the ward-days [b0, b1) (indices within day d), built by ONE warp into its ring of table rows ----------
-// lane -> (slice, is_new, simulation): one ward-day per pass, both slices at once.
+// lane -> (slice, ward-day, simulation): two ward-days per pass, both slices and both is_new classes at once.
 
 // The probabilities of colonised patients (:103-112 with W = 1) do not depend on the ward's pressure unless the force of
 // infection is not finite (N = 0): their 30-bit thresholds are evaluated once per run (SliceParams::t30) and only the
@@ -325,15 +325,14 @@ template <bool REPLAY, bool LEAN>
 __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* par, const FastArgs& a, const uint32_t* press, uint32_t gslice0,
                                           int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
   const int lane = threadIdx.x & 31;
-  // kNS == 2: the upper half-warp takes the second slice; kNS == 1: it takes the next ward-day
-  const int hi = lane >> 4, s = kNS == 2 ? hi : 0, h = (lane >> 3) & 1, k = lane & 7;
-  constexpr uint32_t kPerPass = kNS == 2 ? 1u : 2u;
+  // lane -> (slice, ward-day of the pass, simulation); each lane builds the rows of both is_new classes of its ward-day.
+  // kNS == 2: two ward-days per pass; kNS == 1: four
+  const int s = kNS == 2 ? (lane >> 4) : 0, sub = kNS == 2 ? ((lane >> 3) & 1) : (lane >> 3), k = lane & 7;
+  constexpr uint32_t kPerPass = kNS == 2 ? 2u : 4u;
   const SliceParams& p = par[s];
-  const bool flag = h ? test_a : test_h;
-  const double rho = h ? p.rho_i[k] : p.rho_h[k];
   const double beta = p.beta[k], alpha = p.alpha[k], alpha2 = p.alpha2[k], gamma = p.gamma[k];
   // the loads of the next pass are in flight while this one computes
-  auto lane_seg = [&](uint32_t sl0) { return kNS == 2 ? sl0 : min(sl0 + (uint32_t)hi, b1 - 1u); };   // an odd tail is simply built twice
+  auto lane_seg = [&](uint32_t sl0) { return min(sl0 + (uint32_t)sub, b1 - 1u); };   // a short tail is simply built more than once
   uint32_t pk_next = 0u;
   double n_next = 1.0;
   if (b0 < b1) {
@@ -364,38 +363,43 @@ __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* p
 #pragma unroll 1
     for (int wc = 0; wc <= ((!LEAN && a.has_half) ? 1 : 0); ++wc) {   // weight class of the record: 1, then 1/2
       const double w = wc ? 0.5 : 1.0;
-      const int trow = ((slot * kRowsPerSeg + h * 2 + wc) * kNS + s);
-      if constexpr (REPLAY) {
 #pragma unroll
-        for (int pc = 0; pc < 3; ++pc) sh.P[(trow * 3 + pc) * 8 + k] = class_probability(pc, h, F, alpha, alpha2, gamma, w);
-      } else {
-        // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
-        // never re-tested (:131 / :134)
-        const double P0 = class_probability(0, h, F, alpha, alpha2, gamma, w);
-        uint32_t t30[5];
-        t30[0] = threshold30(P0);
-        t30[3] = threshold30(__dmul_rn(clamp01(P0), rho));
-        if (finite && wc == 0) {
-          t30[1] = p.t30[0][h][k]; t30[2] = p.t30[1][h][k]; t30[4] = p.t30[2][h][k];
-        } else {   // a colonised half-weight record feels the ward's pressure too: P = coef/2 + F/2 (:108-109)
-          const double P1 = class_probability(1, h, F, alpha, alpha2, gamma, w);
-          t30[1] = threshold30(P1);
-          t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma, w));
-          t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
-        }
-        uint32_t e[5];
+      for (int h = 0; h < 2; ++h) {   // hospitalised, then arrivals: two independent chains
+        const bool flag = h ? test_a : test_h;
+        const double rho = h ? p.rho_i[k] : p.rho_h[k];
+        const int trow = ((slot * kRowsPerSeg + h * 2 + wc) * kNS + s);
+        if constexpr (REPLAY) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
-        if (!flag) e[3] = e[4] = 0u;
-        // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
+          for (int pc = 0; pc < 3; ++pc) sh.P[(trow * 3 + pc) * 8 + k] = class_probability(pc, h, F, alpha, alpha2, gamma, w);
+        } else {
+          // dithered 14-bit thresholds (rng.cuh); U and A are tested today if it is a testing day, a running countdown is
+          // never re-tested (:131 / :134)
+          const double P0 = class_probability(0, h, F, alpha, alpha2, gamma, w);
+          uint32_t t30[5];
+          t30[0] = threshold30(P0);
+          t30[3] = threshold30(__dmul_rn(clamp01(P0), rho));
+          if (finite && wc == 0) {
+            t30[1] = p.t30[0][h][k]; t30[2] = p.t30[1][h][k]; t30[4] = p.t30[2][h][k];
+          } else {   // a colonised half-weight record feels the ward's pressure too: P = coef/2 + F/2 (:108-109)
+            const double P1 = class_probability(1, h, F, alpha, alpha2, gamma, w);
+            t30[1] = threshold30(P1);
+            t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma, w));
+            t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
+          }
+          uint32_t e[5];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
-          e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
-        }
-        if (!(k & 1)) {
-          uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + trow * kTabRow) + (k >> 1);
-          row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
+          for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
+          if (!flag) e[3] = e[4] = 0u;
+          // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, e[q], 1);
+            e[q] = (k & 1) ? (other | (e[q] << 16)) : (e[q] | (other << 16));
+          }
+          if (!(k & 1)) {
+            uint32_t* row = reinterpret_cast<uint32_t*>(sh.tab + trow * kTabRow) + (k >> 1);
+            row[0] = e[0]; row[4] = e[0] ^ e[1]; row[8] = e[1] ^ e[2]; row[12] = e[3]; row[16] = e[3] ^ e[4];
+          }
         }
       }
     }
