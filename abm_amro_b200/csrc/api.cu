@@ -272,7 +272,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // barrier replaces the counter in global memory.  AMRO_FAST_BARRIER=global / cluster forces one.
   // A grid that leaves a quarter of the CTA slots empty anyway runs the instance compiled for three CTAs per SM (168
   // registers per thread instead of 128: the scheduler has room to overlap the eight pairs of a record): +3 % on config 2
-  if (shape == kShapeTeam && !std::getenv("AMRO_FAST_SHAPE") && (int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms)
+  if (shape == kShapeTeam && !std::getenv("AMRO_FAST_SHAPE") && ((int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms || std::getenv("AMRO_FAST_ROOMY")))
     shape = kShapeRoomy;   // the lean instance stays lean (with 64-bit REDs there: kernels_fast.cu)
   int use_cluster = 0;
   if (shape != kShapeWide && G > 1 && G <= kMaxClusterCtas && extra == 0) {   // larger teams (few simulations, big days) keep their size
