@@ -150,6 +150,9 @@ def test_teams_of_several_ctas_match_the_oracle(monkeypatch, g, barrier):
         assert np.array_equal(free.counts_detected, oracle.total_positive_detected(ref, S))
         rep = topo.simulate(par, icp, idp, ttd, tsh, tsa, 3, rng_mode=capi.RNG_REPLAY, path=capi.PATH_FAST, want_state=True, **t)
         assert np.array_equal(rep.state, ref_replay[:, 6:])
+        lean = topo.simulate(par, icp, idp, ttd, tsh, tsa, 3, path=capi.PATH_FAST)   # summary run: the lean instance of the same team
+        assert np.array_equal(lean.counts_colonized, free.counts_colonized)
+        assert np.array_equal(lean.counts_detected, free.counts_detected)
 
 
 @pytest.mark.parametrize("path", [capi.PATH_FAST, capi.PATH_GENERAL])
