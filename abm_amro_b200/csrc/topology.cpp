@@ -171,8 +171,11 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   // C/D columns of row trunc(next_day); a later source wins.  A stepped row therefore starts its own day
   // from the last write made on an EARLIER day (or its initial state), and a write made on its own or a
   // later day only changes what the returned matrix shows for it.
-  std::vector<int64_t> last_writer(R, -1), seen_stamp(R, -1);
+  struct Written { int64_t writer, day; };   // last source row and the day it wrote on: one cache line per target
+  std::vector<Written> written(R, Written{-1, -1});
   std::vector<int64_t> pre_src(T.Rp, -1);  // original row of the effective predecessor
+  T.push_src.reserve((size_t)T.Rp);
+  T.push_dst.reserve((size_t)T.Rp);
   T.day_push_start.assign(D + 1, 0);
   T.simple_final = (T.Rp == R);
   bool ring = true;
@@ -180,7 +183,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   for (int64_t d = 0; d < D; ++d) {
     const int64_t a = T.day_start[d], b = T.day_start[d + 1];
     for (int64_t p = a; p < b; ++p) {
-      const int64_t src = last_writer[T.order[p]];
+      const int64_t src = written[T.order[p]].writer;
       pre_src[p] = src;
       if (src >= 0 && row_day[src] != d - 1) ring = false;
     }
@@ -198,11 +201,10 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
       if (!(nd < 18446744073709551616.0) || (uint64_t)nd >= (uint64_t)R)
         fail(AMRO_EINDEX, "Mat::elem(): index out of bounds (row %lld: next_day %g)", (long long)r, nd);
       const int64_t t = (int64_t)(uint64_t)nd;
-      if (seen_stamp[t] == d) continue;
-      seen_stamp[t] = d;
+      if (written[t].day == d) continue;
+      written[t] = Written{r, d};
       T.push_src.push_back(r);
       T.push_dst.push_back(t);
-      last_writer[t] = r;
       if (row_day[t] < 0 || row_day[t] <= d) T.simple_final = false;
     }
     std::reverse(T.push_src.begin() + base, T.push_src.end());
