@@ -569,12 +569,12 @@ void hash_bytes(Hash128& h, const void* data, size_t n_bytes) {
 // A large dense matrix is hashed in slabs by a few threads (the hash of a 175 MB ward_matrix on one core costs more than
 // the run it saves compiling for); the slab hashes are then chained in order, so the key does not depend on the thread count.
 void hash_dense(Hash128& h, const double* m, size_t n) {
-  constexpr size_t kSlab = (size_t)1 << 20;   // doubles per slab (8 MB)
+  constexpr size_t kSlab = (size_t)1 << 18;   // doubles per slab (2 MB): one core reads ~6 GB/s, so the slabs go to up to 16 threads
   const size_t n_slabs = (n + kSlab - 1) / kSlab;
   if (n_slabs <= 2) { hash_bytes(h, m, sizeof(double) * n); return; }
   std::vector<Hash128> part(n_slabs);
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 8), n_slabs);
+  const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 16), n_slabs);
   std::vector<std::thread> pool;
   for (size_t t = 0; t < n_thr; ++t)
     pool.emplace_back([&, t] {
@@ -635,11 +635,14 @@ namespace {
 
 // mean(X,1) / stddev(X,1,1) over simulations with Armadillo's operation order
 // (armadillo_bits/op_mean_meat.hpp:105-133, op_var_meat.hpp:85-106,175-219, arrayops_meat.hpp:917-936)
-void row_mean_sd(const double* x, int64_t n_days, int64_t S, int64_t ld, double* mean, double* sd) {
+// X: the counts as they come back from the device (int32) or a float64 matrix; every value is converted to double first
+template <class X>
+void row_mean_sd(const X* xs, int64_t n_days, int64_t S, int64_t ld, double* mean, double* sd) {
+  auto x = [xs](int64_t i) { return (double)xs[i]; };
   for (int64_t d = 0; d < n_days; ++d) {
     if (mean) {
       double acc = 0.0;
-      for (int64_t s = 0; s < S; ++s) acc += x[d + ld * s];
+      for (int64_t s = 0; s < S; ++s) acc += x(d + ld * s);
       mean[d] = acc / (double)S;
     }
     if (sd) {
@@ -647,16 +650,16 @@ void row_mean_sd(const double* x, int64_t n_days, int64_t S, int64_t ld, double*
       if (S >= 2) {
         double a1 = 0.0, a2 = 0.0;
         int64_t i;
-        for (i = 0; i + 1 < S; i += 2) { a1 += x[d + ld * i]; a2 += x[d + ld * (i + 1)]; }
-        if (i < S) a1 += x[d + ld * i];
+        for (i = 0; i + 1 < S; i += 2) { a1 += x(d + ld * i); a2 += x(d + ld * (i + 1)); }
+        if (i < S) a1 += x(d + ld * i);
         const double m = (a1 + a2) / (double)S;
         double q = 0.0, l = 0.0;
         for (i = 0; i + 1 < S; i += 2) {
-          const double ti = m - x[d + ld * i], tj = m - x[d + ld * (i + 1)];
+          const double ti = m - x(d + ld * i), tj = m - x(d + ld * (i + 1));
           q += (ti * ti) + (tj * tj);
           l += ti + tj;
         }
-        if (i < S) { const double ti = m - x[d + ld * i]; q += ti * ti; l += ti; }
+        if (i < S) { const double ti = m - x(d + ld * i); q += ti * ti; l += ti; }
         var = (q - (l * l) / (double)S) / (double)S;
       }
       sd[d] = std::sqrt(var);
@@ -735,10 +738,9 @@ extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_r
     a.counts_colonized = cc.data(); a.counts_detected = cd.data();
     rc = amro_simulate(topo, &a);
     if (rc) throw Error(rc, amro_last_error());
-    std::vector<double> xc((size_t)(Dd * S)), xd((size_t)(Dd * S)), mc(Dd), md(Dd), sc(Dd), sd(Dd);
-    for (size_t i = 0; i < xc.size(); ++i) { xc[i] = (double)cc[i]; xd[i] = (double)cd[i]; }
-    row_mean_sd(xc.data(), Dd, S, Dd, mc.data(), sc.data());                                 // :617-620
-    row_mean_sd(xd.data(), Dd, S, Dd, md.data(), sd.data());
+    std::vector<double> mc(Dd), md(Dd), sc(Dd), sd(Dd);
+    row_mean_sd(cc.data(), Dd, S, Dd, mc.data(), sc.data());                                 // :617-620
+    row_mean_sd(cd.data(), Dd, S, Dd, md.data(), sd.data());
     for (int64_t d = 0; d < Dd; ++d) {
       out[d] = (double)d;
       if (bug_compatible) {  // :625-628 write sd over the mean columns and leave 3-4 zero
