@@ -107,6 +107,27 @@ def test_topology_compiler_sorts_like_the_reference_visits():
     assert np.all(order[1:][same] > order[:-1][same])          # stable: original row order inside a ward-day
 
 
+def test_push_lists_keep_the_last_writer_of_every_target():
+    # abm_wards.cpp:402-407: after day d, its rows with next_day > 0 write into row trunc(next_day) in ascending row order,
+    # so the LAST source of a target wins; the compiled per-day push lists hold exactly those winners, ascending by source
+    wm, tp, n_init = synth.make_hospital(4, 120, 10, seed=3)
+    g = np.random.default_rng(0)
+    w2 = wm.copy(); R = w2.shape[0]
+    idx = g.choice(R, 300, replace=False)
+    w2[idx, 5] = g.integers(1, R, 300) + g.random(300) * 0.9      # duplicate, backward and fractional (truncated) targets
+    with engine.Topology(np.asfortranarray(w2), tp, n_init, device=-1) as t:
+        a = t.debug_arrays()
+        assert not t.info.fast_eligible
+    exp_src, exp_dst = [], []
+    for d in range(int(tp[:, 0].max()) + 1):
+        winner = {}
+        for r in np.nonzero((w2[:, 0] == d) & (w2[:, 5] > 0))[0]:
+            winner[int(w2[r, 5])] = int(r)
+        pairs = sorted((r, tgt) for tgt, r in winner.items())
+        exp_src += [r for r, _ in pairs]; exp_dst += [tgt for _, tgt in pairs]
+    assert np.array_equal(a["push_src"], exp_src) and np.array_equal(a["push_dst"], exp_dst)
+
+
 def test_fast_path_eligibility_reasons():
     wm, tp, n_init = synth.make_hospital(3, 30, 6, seed=5, p_split=0.3)
     with engine.Topology(wm, tp, n_init, device=-1) as t:
