@@ -492,7 +492,7 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
 
     int path = A->path;
     const bool fast_ok = H.fast_eligible && A->time_to_detect >= 0 && A->time_to_detect <= kMaxCountdown &&
-                         H.total_days <= kMaxCountdown && (A->sim_offset % 8 == 0);
+                         H.total_days <= kMaxCountdown && (A->sim_offset % 32 == 0);   // a team steps an aligned half of a group of 32 simulations (rng.cuh)
     if (path == AMRO_PATH_AUTO) path = fast_ok ? AMRO_PATH_FAST : AMRO_PATH_GENERAL;
     if (path == AMRO_PATH_FAST && !fast_ok)
       fail(AMRO_EINVAL, "fast path not available: %s", H.fast_eligible ? "time_to_detect / number of days / sim_offset out of range" : H.why_not_fast.c_str());

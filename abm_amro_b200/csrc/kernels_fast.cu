@@ -119,6 +119,7 @@ struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
   // kind 0: stays colonised, undetected (1 - alpha + gamma h); 1: stays colonised, detected (1 - alpha2 + gamma h);
   // 2: kind 0 and tested positive (clamp(P) * rho)
   uint32_t t30[3][2][8];
+  uint32_t r16_run[8];   // the run's dither of those thresholds (rng.cuh: kRunDitherIndex)
 };
 
 // Transition probability for unit weight (W = C), force of infection F -- the reference's expression order, one
@@ -180,7 +181,7 @@ __device__ __forceinline__ WarpShared carve_shared(unsigned char* raw, int warp)
 }
 
 // Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
-__device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t kx) {
+__device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
@@ -192,8 +193,40 @@ __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint3
     c0 = n0;
     c2 = n2;
   }
-  (void)kx;
   return make_uint4(c0, c1, c2, c3);
+}
+
+// The 14-bit daily draws of one record's 16 simulations (a team = one half of a group of 32 simulations): the group's
+// plane words (rng.cuh: 4 calls, 14 planes), this half of each as the rows of a 16 x 16 bit matrix held two rows per
+// register, transposed in registers (three block-swap stages between registers, one inside each).  v[i] = the draws of
+// simulations 2i (low half-word) and 2i + 1 (high) of the team.
+__device__ __forceinline__ void draws_u14x16(const FastArgs& a, int64_t orig, uint32_t g32, uint32_t half, uint32_t (&v)[8]) {
+  uint4 q[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) q[c] = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), g32, kStreamPlanes + (uint32_t)c);
+  const uint32_t sel = half ? 0x7632u : 0x5410u;
+  v[0] = __byte_perm(q[0].x, q[0].y, sel); v[1] = __byte_perm(q[0].z, q[0].w, sel);
+  v[2] = __byte_perm(q[1].x, q[1].y, sel); v[3] = __byte_perm(q[1].z, q[1].w, sel);
+  v[4] = __byte_perm(q[2].x, q[2].y, sel); v[5] = __byte_perm(q[2].z, q[2].w, sel);
+  v[6] = __byte_perm(q[3].x, q[3].y, sel); v[7] = 0u;   // planes 14 and 15 do not exist (kDrawBits = 14)
+  static_assert(kDrawBits == 14, "the transpose below drops planes 14 and 15");
+#pragma unroll
+  for (int st = 0; st < 3; ++st) {
+    const int k = 8 >> st, kk = k >> 1;
+    const uint32_t m = (st == 0 ? 0x00FFu : st == 1 ? 0x0F0Fu : 0x3333u) * kHalves;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i & kk) continue;
+      const uint32_t t = ((v[i] >> k) ^ v[i + kk]) & m;
+      v[i + kk] ^= t;
+      v[i] ^= t << k;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t t = ((v[i] >> 1) ^ (v[i] >> 16)) & 0x5555u;
+    v[i] ^= (t << 16) ^ (t << 1);
+  }
 }
 
 // One record, eight simulations, free-running mode; two simulations per 32-bit word, stepped together.
@@ -214,7 +247,7 @@ __device__ __forceinline__ uint4 step_record(const uint4* __restrict__ tab, cons
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t w = prew[j];
-    const uint32_t v = rw[j] & 0x3FFF3FFFu;
+    const uint32_t v = rw[j];   // two 14-bit draws
     const uint32_t mdet = h2_ge_mask(w, kCodeZero2);
     uint32_t mcnt = h2_ge_mask(w, kCodeCnt2);
     const uint32_t mcol = h2_ge_mask(w, kCodeA2);
@@ -311,7 +344,8 @@ struct TeamCtx {
   uint4* pre;          // [2][ring_chunks][kNS][32]
   uint4* traj;         // [R][kNS] or nullptr
   uint32_t* press;     // [n_seg][kNS][4]
-  uint32_t gslice0;    // global index of the team's first slice (Philox counter word 2)
+  uint32_t gslice0;    // global index of the team's first slice (counter word 2 of the dither / initial-state calls)
+  uint32_t g32, half;  // the team's 16 simulations: half `half` of the group of 32 simulations g32 (daily draws, rng.cuh)
   int64_t sim0;        // first simulation of the team (run-relative)
 };
 
@@ -386,9 +420,11 @@ __device__ __forceinline__ void build_tables(WarpShared sh, const SliceParams* p
             t30[2] = threshold30(class_probability(2, h, F, alpha, alpha2, gamma, w));
             t30[4] = threshold30(__dmul_rn(clamp01(P1), rho));
           }
+          // ward-free thresholds take the run's dither, the others the ward-day's (rng.cuh)
+          const uint32_t r16c = (finite && wc == 0) ? p.r16_run[k] : r16;
           uint32_t e[5];
 #pragma unroll
-          for (int q = 0; q < 5; ++q) e[q] = (t30[q] + r16) >> 16;
+          for (int q = 0; q < 5; ++q) e[q] = (t30[q] + ((q == 0 || q == 3) ? r16 : r16c)) >> 16;
           if (!flag) e[3] = e[4] = 0u;
           // pair up with the neighbouring simulation (lane ^ 1): word j = sims (2j, 2j+1)
 #pragma unroll
@@ -571,6 +607,8 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
           const int row = on ? ((int)(segl & (kWarpTableSegs - 1)) * kRowsPerSeg + h * 2 + (int)wc) * kNS : kZeroRow * kNS;
           const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
           uint32_t colw[kNW], detw[kNW];
+          uint32_t u14[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if constexpr (!REPLAY) draws_u14x16(a, orig, c.g32, c.half, u14);
 #pragma unroll
           for (int s = 0; s < kNS; ++s) {
             uint4 pre = prev[s];
@@ -579,7 +617,7 @@ __device__ __forceinline__ void process_day(PHASE_DECL const WarpShared& sh, con
             if constexpr (REPLAY) {
               post = step_record_replay(sh, par[s], a, pre, row + s, h, orig, c.sim0 + s * 8, h ? test_a : test_h, on);
             } else {
-              const uint4 rnd = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), c.gslice0 + (uint32_t)s, kStreamStep, 0);
+              const uint4 rnd = make_uint4(u14[(s & 1) * 4], u14[(s & 1) * 4 + 1], u14[(s & 1) * 4 + 2], u14[(s & 1) * 4 + 3]);
               post = step_record<FIRST>(sh.tab + (row + s) * kTabRow, pre, rnd, x2);
             }
             if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next) + s * 32, post);     // :402-407 the successor starts from this state
@@ -662,6 +700,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
   c.traj = a.traj ? a.traj + team * a.R * kNS : nullptr;
   c.press = a.pressure + team * a.n_seg * (kNS * 4);
   c.gslice0 = (uint32_t)((a.sim_offset >> 3) + (uint64_t)team * kNS);
+  static_assert(REPLAY || kNS == 2, "the free-running draws of a team are one half of a 32-simulation group");
+  c.g32 = c.gslice0 >> 2; c.half = (c.gslice0 >> 1) & 1u;   // sim_offset is a multiple of 16 (api.cu)
   c.sim0 = team * (kNS * 8);
 
   // ---- team setup: parameters and the all-zero table row to shared memory, pressure zeroed -----------------------
@@ -691,6 +731,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
     p.t30[0][h][k] = threshold30(P1);
     p.t30[1][h][k] = threshold30(P2);
     p.t30[2][h][k] = threshold30(__dmul_rn(clamp01(P1), h ? p.rho_i[k] : p.rho_h[k]));
+    if (!REPLAY && h == 0)
+      p.r16_run[k] = chunk16(philox4x32_10((uint32_t)kRunDitherIndex, (uint32_t)(kRunDitherIndex >> 32), c.gslice0 + (uint32_t)s, kStreamDither,
+                                           (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), k);
   }
   __syncthreads();   // parameters visible to every warp of the CTA
   bar.arrive();

@@ -94,9 +94,10 @@ __global__ void k_gen_update(GenArgs a, int64_t row_begin, int64_t row_end, int6
   uint32_t v14 = 0, r16 = 0;
   if (a.replay) {
     col = a.u_col[r + a.u_ld * s] < P;                                                 // :116
-  } else {  // rng.cuh: 14-bit draw against the threshold dithered per (ward-day, simulation)
-    v14 = philox_chunk(a.seed, (uint64_t)r, a.sim_offset + s, kStreamStep) & 0x3FFFu;
-    r16 = philox_chunk(a.seed, (uint64_t)a.seg_of_pos[p], a.sim_offset + s, kStreamDither);
+  } else {  // rng.cuh: 14-bit draw against the dithered threshold (dither of the ward-day, or of the run when P is ward-free)
+    const bool ward_free = (W == 1.0) && (fabs(force) <= 1.7976931348623157e308);
+    v14 = philox_u14(a.seed, (uint64_t)r, a.sim_offset + s);
+    r16 = philox_chunk(a.seed, ward_free ? kRunDitherIndex : (uint64_t)a.seg_of_pos[p], a.sim_offset + s, kStreamDither);
     col = v14 < bernoulli14(P, r16);
   }
   const bool h0 = (h == 0.0), h1 = (h == 1.0);

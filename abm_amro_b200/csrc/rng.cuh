@@ -1,26 +1,31 @@
 // Counter-based RNG of the free-running mode (DESIGN.md "RNG spec") and the probability -> threshold map.
 //
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11), hand-written; key = 64-bit seed, counter =
-// (index_lo, index_hi, sim_group, stream).  One call yields 128 bits = eight 16-bit chunks, one per
-// simulation of a group of 8 consecutive simulations.
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11), hand-written; key = 64-bit seed.
 //
-// Daily step (stream 0, index = patient-day record): the draw of (record, simulation) is v14 = chunk & 0x3FFF and
-//     Bernoulli(p) fires  <=>  v14 < B(p),      B(p) = (T30(p) + r16) >> 16  in [0, 2^14],
-// with T30(p) = ceil(p * 2^30) (0 for p <= 0 or NaN, 2^30 for p >= 1) and r16 the DITHER of the record's ward-day:
-// the 16-bit chunk of (stream 6, index = ward-day, simulation).  Rounding the 30-bit threshold to 14 bits with a
-// uniform dither keeps the probability of every draw exact to 2^-30 (E[B(p)] = T30(p) / 2^16; "never" and "always"
-// stay exact) while the kernel compares 14 bits per update -- as packed fp16 compares: every 14-bit pattern is a finite
-// non-negative half whose order is the integer order.  Draws of the records of one ward-day and simulation are coupled
-// only through the shared dither, by less than 2^-30 in any joint probability.
-// Initial state (streams 2..5, index = initial row): 32-bit uniform (chunk << 16 | chunk of stream+1) < T(p), T(p) =
-// #{r : r * 2^-32 < p}.
+// Daily step: the uniforms of a patient-day record are BIT-SLICED over groups of 32 consecutive simulations.  Plane word
+// j (0..13) of (record, group g = global sim >> 5) is word (j & 3) of the call with counter (row_lo, row_hi, g, 8 + (j >> 2));
+// bit (sim & 31) of plane j is bit j of the 14-bit draw u14(record, sim).  The bit-sliced kernel (kernels_bits.cu)
+// compares the planes with threshold planes directly -- one LOP3 per plane and 32 simulations; the other kernels gather
+// their simulations' bits.
+//     Bernoulli(p) fires  <=>  u14 < B(p),      B(p) = (T30(p) + r16) >> 16  in [0, 2^14],
+// with T30(p) = ceil(p * 2^30) (0 for p <= 0 or NaN, 2^30 for p >= 1) and r16 a DITHER: the 16-bit chunk of
+// (stream 6, index, sim) of a call with counter (index_lo, index_hi, sim >> 3, 6), where index = the record's ward-day, or
+// the all-ones index (one dither per simulation and run) when the probability does not depend on the ward (a record with
+// W = C*w = 1 under a finite force of infection).  Rounding the 30-bit threshold to 14 bits with a uniform dither keeps
+// the probability of every draw exact to 2^-30 (E[B(p)] = T30(p) / 2^16; "never" and "always" stay exact).  Draws that
+// share a dither are coupled only through it: the count of new colonisations of a ward-day of n records is over-dispersed
+// by at most n * 2^-14 relative to independent draws, and only where p < 2^-14.
+// Initial state (streams 2..5, index = initial row): one call with counter (row_lo, row_hi, sim >> 3, stream) serves 8
+// simulations; 32-bit uniform (chunk << 16 | chunk of stream+1) < T(p), T(p) = #{r : r * 2^-32 < p}.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace amro {
 
-constexpr uint32_t kStreamStep = 0, kStreamInitCol = 2, kStreamInitDet = 4, kStreamDither = 6;  // init: +1 = low half
+constexpr uint32_t kStreamInitCol = 2, kStreamInitDet = 4, kStreamDither = 6, kStreamPlanes = 8;  // init: +1 = low half; planes: 8..11
+constexpr int kDrawBits = 14;                              // planes of the daily draw
+constexpr uint64_t kRunDitherIndex = ~0ull;                // dither index of ward-independent probabilities
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
@@ -72,11 +77,25 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t row, uint
   return (chunk16(a, k) << 16) | chunk16(b, k);
 }
 
-// 16-bit chunk of (index, global sim, stream): the daily draw (stream 0, & 0x3FFF) and the ward-day dither (stream 6)
+// 16-bit chunk of (index, global sim, stream): the dither (stream 6)
 __device__ __forceinline__ uint32_t philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
   const uint4 a = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream, (uint32_t)seed,
                                 (uint32_t)(seed >> 32));
   return chunk16(a, (int)(sim & 7u));
+}
+
+// 14-bit daily draw of (row, global sim): its bit of each plane word (the gather the non-bit-sliced kernels do)
+__device__ __forceinline__ uint32_t philox_u14(uint64_t seed, uint64_t row, uint64_t sim) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), b = (uint32_t)(sim & 31u);
+  uint32_t u = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 a = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 5), kStreamPlanes + (uint32_t)c, k0, k1);
+    u |= ((a.x >> b) & 1u) << (4 * c);
+    u |= ((a.y >> b) & 1u) << (4 * c + 1);
+    if (c < 3) { u |= ((a.z >> b) & 1u) << (4 * c + 2); u |= ((a.w >> b) & 1u) << (4 * c + 3); }
+  }
+  return u;
 }
 
 }  // namespace amro

@@ -82,11 +82,14 @@ uint64_t amro_oracle_threshold(double p) {
   return (uint64_t)ceil(p * 4294967296.0);
 }
 
-/* RNG spec, daily step (abm_amro_b200/csrc/rng.cuh): one Philox call, counter (index_lo, index_hi, sim >> 3, stream),
- * serves the 8 simulations of a sim-group; simulation k = sim & 7 owns the 16-bit chunk (word[k>>1] >> 16*(k&1)).
- * The draw of (row, sim) is v14 = chunk(stream 0, row) & 0x3FFF and Bernoulli(p) fires iff v14 < B(p) with
- * B(p) = (T30(p) + r16) >> 16, T30(p) = ceil(p * 2^30) clamped to [0, 2^30], r16 = chunk(stream 6, ward-day): the
- * 30-bit threshold is rounded to 14 bits with a dither shared by the ward-day, so E[B(p)] = T30(p) / 2^16 exactly. */
+/* RNG spec, daily step (abm_amro_b200/csrc/rng.cuh).  The uniforms of a record are BIT-SLICED over groups of 32
+ * consecutive simulations: plane word j (0..13) of (row, group g = sim >> 5) is word (j & 3) of the Philox call with
+ * counter (row_lo, row_hi, g, 8 + (j >> 2)); bit (sim & 31) of plane j is bit j of the 14-bit draw u14(row, sim).
+ * Bernoulli(p) fires iff u14 < B(p) with B(p) = (T30(p) + r16) >> 16, T30(p) = ceil(p * 2^30) clamped to [0, 2^30], and
+ * r16 a 16-bit DITHER: the 30-bit threshold is rounded to 14 bits so that E[B(p)] = T30(p) / 2^16 exactly.  The dither is
+ * the 16-bit chunk of (stream 6, index, sim) with index = the record's ward-day -- or the all-ones index (one dither per
+ * simulation and run) when the probability does not depend on the ward: a record with W = C*w = 1 under a finite force of
+ * infection, whose P = coef + 0*F + gamma*h (:108-112). */
 uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(sim >> 3), stream};
@@ -94,6 +97,24 @@ uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, u
   amro_oracle_philox4x32_10(ctr, key, a);
   unsigned k = (unsigned)(sim & 7u);
   return (a[k >> 1] >> (16u * (k & 1u))) & 0xFFFFu;
+}
+uint32_t amro_oracle_philox_plane(uint64_t seed, uint64_t row, uint64_t group32, unsigned j) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)group32, 8u + (j >> 2)};
+  uint32_t a[4];
+  amro_oracle_philox4x32_10(ctr, key, a);
+  return a[j & 3u];
+}
+uint32_t amro_oracle_philox_u14(uint64_t seed, uint64_t row, uint64_t sim) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t u = 0;
+  for (unsigned c = 0; c < 4; ++c) {
+    uint32_t ctr[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 5), 8u + c};
+    uint32_t a[4];
+    amro_oracle_philox4x32_10(ctr, key, a);
+    for (unsigned q = 0; q < 4 && 4 * c + q < 14; ++q) u |= ((a[q] >> (sim & 31u)) & 1u) << (4 * c + q);
+  }
+  return u;
 }
 uint32_t amro_oracle_threshold30(double p) {
   if (!(p > 0.0)) return 0;
@@ -137,13 +158,24 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
   const uint64_t H = 3, Wc = 4, C0 = 6; /* :87-90 */
   double* prob = (double*)malloc(sizeof(double) * (n_rows ? n_rows : 1));
   if (!prob) return fail(AMRO_ORACLE_ERUNTIME, "out of memory");
+  /* PHILOX: the plane words of every (row, group of 32 simulations) of this call, drawn once (speed only) */
+  uint32_t* planes = NULL;
+  const uint64_t g_lo = rng->sim_offset >> 5, n_grp = n_sims ? ((rng->sim_offset + n_sims - 1) >> 5) - g_lo + 1 : 0;
+  if (rng->kind == AMRO_ORACLE_RNG_PHILOX && n_rows && n_sims) {
+    planes = (uint32_t*)malloc(sizeof(uint32_t) * n_rows * n_grp * 14);
+    if (!planes) { free(prob); return fail(AMRO_ORACLE_ERUNTIME, "out of memory"); }
+    for (uint64_t i = 0; i < n_rows; ++i)
+      for (uint64_t g = 0; g < n_grp; ++g)
+        for (unsigned j = 0; j < 14; ++j)
+          planes[(i * n_grp + g) * 14 + j] = amro_oracle_philox_plane(rng->seed, row_ids ? row_ids[i] : i, g_lo + g, j);
+  }
   for (uint64_t s = 0; s < n_sims; ++s) { /* :92 */
     const uint64_t cc = C0 + s, dc = C0 + s + n_sims;
     /* Armadillo bounds checks: .col(cc) first (:95), then parameters(s, beta) (:98), .col(dc) (:102) */
-    if (cc >= n_cols || Wc >= n_cols) { free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::col(): index out of bounds"); }
-    if (s >= p_rows || 1 >= p_cols) { free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::operator(): index out of bounds"); }
-    if (dc >= n_cols) { free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::col(): index out of bounds"); }
-    if (5 >= p_cols) { free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::operator(): index out of bounds"); }
+    if (cc >= n_cols || Wc >= n_cols) { free(planes); free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::col(): index out of bounds"); }
+    if (s >= p_rows || 1 >= p_cols) { free(planes); free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::operator(): index out of bounds"); }
+    if (dc >= n_cols) { free(planes); free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::col(): index out of bounds"); }
+    if (5 >= p_cols) { free(planes); free(prob); return fail(AMRO_ORACLE_EINDEX, "Mat::operator(): index out of bounds"); }
     const double alpha = AT(params, p_ld, s, 0), beta = AT(params, p_ld, s, 1), gamma = AT(params, p_ld, s, 2);
     const double rho_h = AT(params, p_ld, s, 3), alpha2 = AT(params, p_ld, s, 4), rho_i = AT(params, p_ld, s, 5);
 
@@ -175,14 +207,20 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
       if (p_out) p_out[gid + p_out_ld * s] = p;
       /* :116-120 colonisation draw, always taken */
       if (tie_kind == AMRO_ORACLE_RNG_PHILOX) {
-        v14 = amro_oracle_philox_chunk(rng->seed, gid, rng->sim_offset + s, 0) & 0x3FFFu;
-        r16 = amro_oracle_philox_chunk(rng->seed, rng->ward_day, rng->sim_offset + s, 6);
+        /* W (the column still holds C*w of this row) = 1 under a finite force: P does not depend on the ward */
+        const int ward_free = (AT(wm, ld, i, cc) == 1.0) && isfinite(force);
+        {
+          const uint64_t sim = rng->sim_offset + s;
+          const uint32_t* pl = planes + (i * n_grp + ((sim >> 5) - g_lo)) * 14;
+          for (unsigned j = 0; j < 14; ++j) v14 |= ((pl[j] >> (sim & 31u)) & 1u) << j;   /* = amro_oracle_philox_u14 */
+        }
+        r16 = amro_oracle_philox_chunk(rng->seed, ward_free ? UINT64_MAX : rng->ward_day, rng->sim_offset + s, 6);
         col = v14 < amro_oracle_bernoulli14(p, r16);
         rng->n_draws++;
       } else {
         double u;
         if (tie_kind == AMRO_ORACLE_RNG_GLIBC) u = glibc_randu();
-        else if (tie_kind == AMRO_ORACLE_RNG_STREAM) { if (stream_pop(rng, &u)) { free(prob); return AMRO_ORACLE_ERUNTIME; } }
+        else if (tie_kind == AMRO_ORACLE_RNG_STREAM) { if (stream_pop(rng, &u)) { free(planes); free(prob); return AMRO_ORACLE_ERUNTIME; } }
         else u = rng->u_col[gid + rng->u_ld * s];
         if (rng->rec_col) rng->rec_col[gid + rng->rec_ld * s] = u;
         rng->n_draws++;
@@ -205,7 +243,7 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
             } else {
               double u2;
               if (tie_kind == AMRO_ORACLE_RNG_GLIBC) u2 = glibc_randu();
-              else if (tie_kind == AMRO_ORACLE_RNG_STREAM) { if (stream_pop(rng, &u2)) { free(prob); return AMRO_ORACLE_ERUNTIME; } }
+              else if (tie_kind == AMRO_ORACLE_RNG_STREAM) { if (stream_pop(rng, &u2)) { free(planes); free(prob); return AMRO_ORACLE_ERUNTIME; } }
               else u2 = rng->u_det[gid + rng->u_ld * s];
               if (rng->rec_det) rng->rec_det[gid + rng->rec_ld * s] = u2;
               rng->n_draws++;
@@ -219,6 +257,7 @@ int amro_oracle_ward_step(double* wm, uint64_t n_rows, uint64_t n_cols, uint64_t
       }
     }
   }
+  free(planes);
   free(prob);
   return 0;
 }

@@ -70,6 +70,9 @@ uint64_t amro_oracle_threshold(double p);
 uint32_t amro_oracle_philox_u32(uint64_t seed, uint64_t row, uint64_t sim, uint32_t kind);
 /* daily step: 16-bit chunk of (index, sim, stream), 30-bit threshold and its dithered 14-bit rounding */
 uint32_t amro_oracle_philox_chunk(uint64_t seed, uint64_t index, uint64_t sim, uint32_t stream);
+/* bit-sliced daily uniforms: plane word j (0..13) of (row, group of 32 simulations), and the 14-bit draw of (row, sim) */
+uint32_t amro_oracle_philox_plane(uint64_t seed, uint64_t row, uint64_t group32, unsigned j);
+uint32_t amro_oracle_philox_u14(uint64_t seed, uint64_t row, uint64_t sim);
 uint32_t amro_oracle_threshold30(double p);
 uint32_t amro_oracle_bernoulli14(double p, uint32_t r16);
 

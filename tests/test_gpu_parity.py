@@ -356,9 +356,10 @@ def test_full_size_config2_properties():
         assert np.array_equal(a.counts_colonized, b.counts_colonized) and np.array_equal(a.counts_detected, b.counts_detected)
         assert np.all(a.counts_detected <= a.counts_colonized) and np.all(a.counts_colonized <= 10_000) and a.counts_colonized.min() > 0
         # a slice of the ensemble run on its own (another "GPU") reproduces its columns exactly
-        part = topo.simulate(par[496:560], 0.2, 0.2, 2, 7, 1, 42, sim_offset=496)
-        assert np.array_equal(part.counts_colonized, a.counts_colonized[:, 496:560])
-        assert np.array_equal(part.counts_detected, a.counts_detected[:, 496:560])
+        part = topo.simulate(par[512:576], 0.2, 0.2, 2, 7, 1, 42, sim_offset=512)
+        assert part.path_used == capi.PATH_FAST
+        assert np.array_equal(part.counts_colonized, a.counts_colonized[:, 512:576])
+        assert np.array_equal(part.counts_detected, a.counts_detected[:, 512:576])
         # another seed gives another ensemble with the same law: day-364 prevalence within 6 standard errors
         c = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 43)
         assert not np.array_equal(a.counts_colonized, c.counts_colonized)
