@@ -394,6 +394,133 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   A->path_used = AMRO_PATH_FAST;
 }
 
+// BITS path (kernels_bits.cu): summary runs of unit-weight hospitals in free-running mode with time_to_detect <= 2 -- the
+// state bit-sliced over simulations, a team = 64 simulations.  Same topology arrays, ring slots and outputs as run_fast.
+bool bits_eligible(const amro_topology* T, const amro_sim_args* A) {
+  const HostTopology& H = T->H;
+  if (std::getenv("AMRO_FAST_NOBITS")) return false;
+  return A->rng_mode != AMRO_RNG_REPLAY && !A->keep_trajectory && !A->state_out && !A->p_out && !H.has_half &&
+         A->time_to_detect >= 0 && A->time_to_detect <= kBitsMaxTtd;
+}
+
+void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
+  const HostTopology& H = T->H;
+  const int64_t kTeamSims = bits_sims_per_team();
+  const int64_t S = A->n_sims, S_pad = (S + kTeamSims - 1) / kTeamSims * kTeamSims, n_teams = S_pad / kTeamSims;
+  const int ttd = A->time_to_detect;
+  int sms = 0;
+  AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device));
+  // Team size: as in run_fast -- all resident CTA slots dealt out to the teams, capped where a warp would get fewer than
+  // about `trips` 32-record trips a day (every warp pays a fixed price per day: barrier, tables, count flushes).
+  // AMRO_BITS_G fixes the team size, AMRO_BITS_CTAS_PER_SM caps the slots, AMRO_BITS_TRIPS sets the target.
+  int shape = kShapeTeam;
+  if (const char* e = std::getenv("AMRO_BITS_SHAPE")) shape = e[0] == 'd' ? kShapeDense : e[0] == 'r' ? kShapeRoomy : kShapeTeam;
+  const bool shape_forced = std::getenv("AMRO_BITS_SHAPE") != nullptr;
+  int cap = bits_max_coresident_ctas(T->device, ttd, shape);
+  if (cap <= 0) fail(AMRO_ECUDA, "bit-sliced kernel cannot be made resident on this device");
+  if (const char* e = std::getenv("AMRO_BITS_CTAS_PER_SM")) cap = std::min(cap, std::max(1, std::atoi(e)) * sms);
+  int trips = 8;
+  if (const char* e = std::getenv("AMRO_BITS_TRIPS")) trips = std::max(1, std::atoi(e));
+  int G = 1, extra = 0;
+  const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / ((int64_t)trips * kTeamThreads));
+  if (n_teams <= cap) {
+    G = (int)(cap / n_teams); extra = (int)(cap % n_teams);
+    if (G >= useful) { G = (int)useful; extra = 0; }
+  }
+  if (const char* e = std::getenv("AMRO_BITS_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
+  if (!shape_forced && (int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms) shape = kShapeRoomy;
+  int use_cluster = 0;
+  if (G > 1 && G <= kMaxClusterCtas && extra == 0) {
+    const char* e = std::getenv("AMRO_FAST_BARRIER");
+    const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
+    if (want && bits_max_coresident_clusters(ttd, shape, G) >= n_teams) use_cluster = 1;
+  }
+  if ((G > 1 || extra > 0) && !use_cluster && (int64_t)n_teams * G + extra > bits_max_coresident_ctas(T->device, ttd, shape))
+    fail(AMRO_ECUDA, "bit-sliced kernel: the teams cannot be co-resident");
+  const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
+  if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
+  if (ring_chunks * 32 * kSlicesPerTeam * (int64_t)sizeof(uint4) >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: day too large for 32-bit slot offsets");
+  const int64_t n_days = H.total_days + 1;
+  const int64_t max_segs = std::max<int64_t>(H.max_segs_per_day, 1);
+  const int64_t press_days = A->pressure_out ? n_days + 1 : 3;
+
+  ensure_size(T->ws_pre, (size_t)(n_teams * 2 * ring_chunks * 32 * kSlicesPerTeam));
+  ensure_size(T->ws_pressure, (size_t)(n_teams * press_days * max_segs * kTeamSims));
+  ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
+  ensure_size(T->ws_params, (size_t)(S_pad * 6));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S_pad, st));
+  AMRO_CUDA(cudaMemsetAsync(T->ws_params.p, 0, sizeof(double) * S_pad * 6, st));
+  AMRO_CUDA(cudaMemcpy2DAsync(T->ws_params.p, S_pad * sizeof(double), in.params, in.p_ld * sizeof(double),
+                              S * sizeof(double), 6, cudaMemcpyDeviceToDevice, st));
+
+  FastArgs f{};
+  f.meta = T->meta.p;
+  f.init_seg = T->init_seg.p; f.init_slot = T->init_slot.p; f.seg_main_next = T->seg_main_next.p;
+  f.identity_order = H.identity_order ? 1 : 0;
+  f.has_half = 0;
+  f.day_start = T->day_start.p; f.day_seg_start = T->day_seg_start.p; f.seg_row_start = T->seg_row_start.p;
+  f.seg_N = T->seg_N.p;
+  f.R = H.R; f.n_init = H.n_init; f.n_days = n_days; f.n_seg = H.n_seg; f.ring_chunks = ring_chunks;
+  f.params = T->ws_params.p; f.p_ld = S_pad;
+  f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
+  f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
+  f.S = S; f.n_slices = S_pad / kSimsPerSlice;
+  f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
+  f.ttd = ttd;
+  for (int r = 0; r < 10; ++r) {
+    f.rk[2 * r] = (uint32_t)f.seed + (uint32_t)r * 0x9E3779B9u;
+    f.rk[2 * r + 1] = (uint32_t)(f.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
+  f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
+  f.pre = T->ws_pre.p; f.traj = nullptr;
+  f.pressure = T->ws_pressure.p;
+  f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
+  ensure_size(T->ws_barrier, (size_t)n_teams);
+  AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));
+  f.team_barrier = T->ws_barrier.p; f.ctas_per_team = G; f.teams_plus_one = extra; f.cluster_barrier = use_cluster;
+  f.max_segs_per_day = max_segs; f.press_days = (int)press_days;
+
+  if (std::getenv("AMRO_FAST_VERBOSE"))
+    std::fprintf(stderr, "[amro] bits launch: shape %d ttd %d teams %lld G %d extra %d cluster %d grid %lld threads %d smem %zu\n", shape, ttd,
+                 (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), kTeamThreads, bits_shared_bytes());
+  EventPair ev;
+  AMRO_CUDA(cudaEventRecord(ev.a, st));
+  bits_launch(st, f, shape, (int)(n_teams * G + extra));
+  AMRO_CUDA(cudaEventRecord(ev.b, st));
+  A->launches = 1;
+
+  const size_t cbytes = sizeof(int32_t) * (size_t)(H.n_days_out * S);
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
+  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  if (A->day_moments) {
+    if (on_device) day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, A->day_moments, H.n_days_out);
+    else {
+      DevBuf<double> dm;
+      dm.alloc((size_t)(4 * H.n_days_out));
+      day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, dm.p, H.n_days_out);
+      AMRO_CUDA(cudaMemcpyAsync(A->day_moments, dm.p, sizeof(double) * 4 * H.n_days_out, cudaMemcpyDeviceToHost, st));
+      AMRO_CUDA(cudaStreamSynchronize(st));
+    }
+    A->launches++;
+  }
+  emit_distance(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
+  if (A->pressure_out) {
+    if (on_device) bits_export_pressure(st, f.pressure, f.day_seg_start, n_days, max_segs, press_days, S, A->pressure_out, H.n_seg);
+    else {
+      DevBuf<int32_t> pb;
+      pb.alloc((size_t)(H.n_seg * S));
+      bits_export_pressure(st, f.pressure, f.day_seg_start, n_days, max_segs, press_days, S, pb.p, H.n_seg);
+      AMRO_CUDA(cudaMemcpyAsync(A->pressure_out, pb.p, sizeof(int32_t) * H.n_seg * S, cudaMemcpyDeviceToHost, st));
+      AMRO_CUDA(cudaStreamSynchronize(st));
+    }
+    A->launches++;
+  }
+  AMRO_CUDA(cudaStreamSynchronize(st));
+  A->kernel_ms = ev.ms();
+  A->path_used = AMRO_PATH_FAST;
+}
+
 void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
   const HostTopology& H = T->H;
   T->ensure_general();
@@ -531,7 +658,8 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
         in.u_col = d_uc.p; in.u_det = d_ud.p; in.u_ld = H.R; in.u_icol = d_uic.p; in.u_idet = d_uid.p; in.ui_ld = H.n_init;
       }
     }
-    if (path == AMRO_PATH_FAST) run_fast(T, A, in, st, on_device);
+    if (path == AMRO_PATH_FAST && bits_eligible(T, A)) run_bits(T, A, in, st, on_device);
+    else if (path == AMRO_PATH_FAST) run_fast(T, A, in, st, on_device);
     else run_general(T, A, in, st, on_device);
     AMRO_CUDA(cudaEventRecord(ev.b, st));
     AMRO_CUDA(cudaEventSynchronize(ev.b));

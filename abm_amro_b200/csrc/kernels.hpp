@@ -73,6 +73,7 @@ constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-
 #define AMRO_TEAM_MINBLOCKS 4
 #endif
 constexpr int kShapeWide = 0, kShapeTeam = 1, kShapeRoomy = 2;   // Roomy: Team with the register budget of 3 CTAs per SM
+constexpr int kShapeDense = 3;                                   // bit-sliced kernel only: the register budget of 6 CTAs per SM
 constexpr int kWideThreads = AMRO_WIDE_THREADS;     // one CTA per SM
 constexpr int kTeamThreads = AMRO_TEAM_THREADS;
 constexpr int kTeamMinBlocks = AMRO_TEAM_MINBLOCKS; // CTAs per SM the team shape's register budget is sized for
@@ -116,6 +117,9 @@ struct FastArgs {
   int ctas_per_team;             // CTAs that share a team's slices (1 = no inter-CTA barrier) ...
   int teams_plus_one;            // ... the first teams_plus_one teams have one more, so that the grid fills the SMs evenly
   int cluster_barrier;           // 1: every team is a thread-block cluster and meets at the hardware cluster barrier
+  // bit-sliced kernel (kernels_bits.cu): pressure is [n_teams][press_days][max_segs_per_day][words per team][32] 32-bit counts
+  int64_t max_segs_per_day;
+  int press_days;                // 3 (ring: today, tomorrow, the buffer being zeroed) or n_days + 1 (kept for export)
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
@@ -133,5 +137,21 @@ void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, cons
                  int64_t R, int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld);
 // out[seg + ld*sim] = colonised count the ward-day started with
 void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld);
+
+
+// ----------------------------------------------------------------------------------------------------
+// BITS path: the state bit-sliced over simulations (one bit per plane, 32 simulations per register): summary runs of
+// unit-weight hospitals with time_to_detect <= 2 in free-running mode.  See kernels_bits.cu.  Same ring / meta / launch
+// shapes (kShapeTeam, kShapeRoomy) as the FAST path; a team steps bits_sims_per_team() simulations.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kBitsMaxTtd = 2;
+int bits_sims_per_team();
+size_t bits_shared_bytes();
+int bits_max_coresident_ctas(int device, int ttd, int shape);
+int bits_max_coresident_clusters(int ttd, int shape, int cluster_size);
+void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid);
+// out[ward-day + ld*sim] = colonised count the ward-day started with (press_days = n_days + 1 runs only)
+void bits_export_pressure(cudaStream_t st, const uint32_t* pressure, const int64_t* day_seg_start, int64_t n_days, int64_t max_segs,
+                          int64_t press_days, int64_t S, int32_t* out, int64_t ld);
 
 }  // namespace amro

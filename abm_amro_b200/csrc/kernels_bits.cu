@@ -1,0 +1,564 @@
+// BITS path: the ward-level colonisation step with the state BIT-SLICED over simulations -- summary runs (per-day counts,
+// no trajectory) of unit-weight hospitals with time_to_detect <= 2, free-running mode, in ONE persistent kernel.
+//
+// Replaces the same nest as kernels_fast.cu (src/amro/abm_wards.cpp:322-414 / :219-257 / :70-159 fused with the totals
+// :435-509).  Where kernels_fast.cu keeps a 16-bit code per (record, simulation) and steps two simulations per 32-bit
+// register, this kernel keeps ONE BIT PER PLANE: a 32-bit register holds one plane of 32 simulations of one record,
+//   c    colonised                                  (reference: C = 1)
+//   det  countdown at or below zero                 (D <= 0: detected; with c = 0 it is the initial-state quirk of :372,
+//                                                     an uncolonised patient whose D reads 0)
+//   q1   result due tomorrow  (D = 1)               (time_to_detect >= 1)
+//   q2   result due in two days (D = 2)             (time_to_detect == 2)
+// so a record x 32 simulations is one 16-byte word and every logical step of the update is one LOP3 for 32 simulations:
+//   draws        the record's 14 plane words (rng.cuh) are compared with the THRESHOLD PLANES of its (ward-day, is_new):
+//                lt = (t & ~u) | (~(t ^ u) & lt), least significant plane first -- one LOP3 per plane and probability
+//                class, five classes (uncolonised / colonised / detected; tested positive: uncolonised / colonised)
+//   transition   col = c ? (det ? fB : fA) : fU;  tested = col & hit & ~(det | q1 | q2);  det' = col & (det | q1);
+//                q1' = col & q2;  q2' = tested      (:116-155: D -= 1 while a countdown runs, D = ttd on a positive test,
+//                D = inf otherwise; c' = 0 clears everything)
+//   counts       per-lane VERTICAL counters (bit-sliced ripple adders over the trips of a warp), turned into per-simulation
+//                integers by a 32 x 32 bit transpose across the warp (five shuffle stages) + POPC when a ward-day / the day ends
+// Data layout (HBM): the two-day state ring and the per-record meta words of kernels_fast.cu (same slots, same byte
+// offsets: a slot holds kBW 16-byte words = kBW x 32 simulations); ward pressure as 32-bit counts
+// [team][day mod press_days][ward-day of the day][word][32 simulations] (three days in flight; all days when exported).
+// Work decomposition, team barrier and day plan: team.cuh, as in kernels_fast.cu; a team = 32 * kBW simulations.
+#include "team.cuh"
+
+namespace amro {
+namespace {
+
+constexpr int kBW = kSlicesPerTeam;                 // 16-byte words of a ring slot = groups of 32 simulations of a team
+constexpr int kBitsSims = 32 * kBW;                 // simulations of a team
+#ifndef AMRO_BITS_SEGS
+#define AMRO_BITS_SEGS 4
+#endif
+constexpr int kBSegs = AMRO_BITS_SEGS;              // ring of ward-day tables per warp (power of two)
+constexpr int kTabWords = 80;                       // a table row: 5 tables x 16 words (14 planes, the "always" mask, a zero)
+constexpr int kTU = 0, kTA = 16, kTB = 32, kTUh = 48, kTAh = 64;   // word offsets of the tables in a row
+constexpr int kZeroRowB = kBSegs * 2;               // rows (ward-day, is_new) + one all-zero row: lanes without a record step against it
+constexpr int kXferCap = 96;                        // entries of a warp's transfer list (drained when fewer than 32 are free)
+constexpr int kCntPlanes = 5;                       // vertical counters count to 31
+constexpr int kFlushTrips = (1 << kCntPlanes) - 1;
+static_assert(kDrawBits == 14, "table rows hold 14 planes + the always mask");
+
+// 32 x 32 bit transpose across the warp: lane i holds row i; afterwards lane j holds column j (bit i = row i's bit j).
+// Per stage the lanes of a pair exchange the blocks they do not keep (rotated into place before the shuffle).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int k = 16 >> st;
+    const uint32_t m = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u : 0x55555555u;
+    const bool upper = (lane & k) != 0;
+    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, __funnelshift_l(x, x, upper ? k : 32 - k), k);
+    const uint32_t keep = upper ? ~m : m;
+    x = (x & keep) | (y & ~keep);
+  }
+  return x;
+}
+
+// Vertical counter: plane b holds bit b of a per-simulation count (32 simulations per register)
+struct VCount {
+  uint32_t v[kCntPlanes];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int b = 0; b < kCntPlanes; ++b) v[b] = 0u;
+  }
+  __device__ __forceinline__ void add(uint32_t x) {   // ripple-carry increment where x is set
+#pragma unroll
+    for (int b = 0; b < kCntPlanes; ++b) {
+      const uint32_t t = v[b] & x;
+      v[b] ^= x;
+      x = t;
+    }
+  }
+  // lane s <- the warp's total of simulation s after n_adds (warp-uniform) increments; the counter is cleared
+  __device__ __forceinline__ uint32_t flush(int lane, uint32_t n_adds) {
+    uint32_t c = 0u;
+#pragma unroll
+    for (int b = 0; b < kCntPlanes; ++b) {
+      if ((n_adds >> b) != 0u) c += (uint32_t)__popc(warp_transpose32(v[b], lane)) << b;
+      v[b] = 0u;
+    }
+    return c;
+  }
+};
+
+// Shared memory (dynamic): per CTA the team's parameters and the run-constant tables, per warp a ring of table rows and
+// the transfer list.
+//   par   double [6][kBitsSims]                      alpha, beta, gamma, rho_hospital, alpha2, rho_imported (:79-84)
+//   r16   uint32 [kBitsSims]                          the run's dither (rng.cuh: kRunDitherIndex)
+//   rc    uint32 [is_new][word][48]                   tables A, B, Ah under a finite force of infection (they do not depend on the ward)
+//   tab   uint32 [kZeroRowB + 1 rows][kTabWords]      per warp: rows (ward-day slot, is_new) of the warp's word
+//   xfer  uint2  [kXferCap]                           per warp: (ward-day of the successor within its day, colonised word)
+struct BitsShared {
+  double* par;
+  uint32_t* r16;
+  uint32_t* rc;
+  uint32_t* tab;
+  uint2* xfer;
+};
+constexpr size_t kCtaSharedBytes = sizeof(double) * 6 * kBitsSims + sizeof(uint32_t) * kBitsSims + sizeof(uint32_t) * 2 * kBW * 48;
+constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + sizeof(uint2) * kXferCap;
+static_assert(kCtaSharedBytes % 16 == 0 && kWarpSharedBytes % 16 == 0, "table rows are read as uint4");
+__host__ __device__ inline size_t bits_smem_bytes(int threads) { return kCtaSharedBytes + (size_t)(threads / 32) * kWarpSharedBytes; }
+__device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
+  BitsShared s;
+  s.par = reinterpret_cast<double*>(raw);
+  s.r16 = reinterpret_cast<uint32_t*>(raw + sizeof(double) * 6 * kBitsSims);
+  s.rc = s.r16 + kBitsSims;
+  unsigned char* mine = raw + kCtaSharedBytes + (size_t)warp * kWarpSharedBytes;
+  s.tab = reinterpret_cast<uint32_t*>(mine);
+  s.xfer = reinterpret_cast<uint2*>(s.tab + (kZeroRowB + 1) * kTabWords);
+  return s;
+}
+
+// What a warp needs about its team and its word: the warps of a team pair up -- a pair steps the same run of records,
+// one warp per group of 32 simulations (word w of the 16-byte-word ring slots).
+struct BitsCtx {
+  uint4* pre;          // [2][ring_chunks][kBW][32], offset to the warp's word
+  uint32_t* press;     // [press_days][max_segs][kBW][32], offset to the warp's word
+  uint32_t gsim0;      // global index of the first simulation of the warp's word (a multiple of 32)
+  int64_t sim0;        // first simulation of the warp's word (run-relative)
+  int w;               // the word
+};
+
+// element (uint4) index of slot q of a team's first word in a state-ring buffer laid out [chunk of 32 slots][word][32]
+__device__ __forceinline__ int64_t ring_slot_b(uint32_t q) { return (int64_t)(q >> 5) * (kBW * 32) + (q & 31u); }
+__device__ __forceinline__ uint32_t* press_of_day(const FastArgs& a, uint32_t* press, int64_t d) {
+  return press + (int64_t)(d % a.press_days) * a.max_segs_per_day * (kBW * 32);
+}
+
+// 14-bit thresholds of two tables -> their plane words in a table row: after the transpose lane j holds plane j of the
+// first table and lane 16 + j plane j of the second (bit 14 = "always": B = 2^14)
+__device__ __forceinline__ void store_planes(uint32_t* row, int first, int second, uint32_t b_first, uint32_t b_second, int lane) {
+  const uint32_t t = warp_transpose32(b_first | (b_second << 16), lane);
+  if (lane < 16) row[first + lane] = t;
+  else if (second >= 0) row[second + lane - 16] = t;
+}
+
+// ---- tables of the ward-days [b0, b1) (indices within day d) into the warp's ring; lane = simulation of the warp's word --
+// Uncolonised patients feel the ward: P0 = F + gamma h with F = (beta / N) * sum(W) (:98-112), dithered per ward-day.  The
+// colonised classes do not (W = 1: P = coef + 0 F + gamma h) unless F is not finite: their planes are copied from the
+// run-constant tables, or built here for the simulations whose F is inf / NaN (N = 0).
+__device__ __forceinline__ void build_tables_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, const uint32_t* press_day,
+                                                  int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
+  const int lane = threadIdx.x & 31;
+  const int sim = c.w * 32 + lane;
+  const double alpha = sh.par[sim], beta = sh.par[kBitsSims + sim], gamma = sh.par[2 * kBitsSims + sim];
+  const double alpha2 = sh.par[4 * kBitsSims + sim];
+  const uint32_t gs = c.gsim0 + (uint32_t)lane;
+#pragma unroll 1
+  for (uint32_t sl = b0; sl < b1; ++sl) {
+    const int64_t seg = seg0 + sl;
+    const int slot = (int)(sl & (kBSegs - 1));
+    const uint32_t cnt = __ldcg(press_day + (int64_t)sl * (kBW * 32) + lane);
+    const double n_seg = __ldg(&a.seg_N[seg]);
+    const double F = __dmul_rn(__ddiv_rn(beta, n_seg), (double)cnt);   // :98-99, sum(W) = the count of colonised records
+    const bool finite = fabs(F) <= 1.7976931348623157e308;
+    const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gs >> 3, kStreamDither, (uint32_t)a.seed,
+                                               (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
+    const bool all_finite = __all_sync(0xFFFFFFFFu, finite);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool flag = h ? test_a : test_h;
+      const double rho = sh.par[(h ? 5 : 3) * kBitsSims + sim];
+      uint32_t* row = sh.tab + (slot * 2 + h) * kTabWords;
+      const double P0 = class_probability(0, h, F, alpha, alpha2, gamma);
+      const uint32_t bU = (threshold30(P0) + r16) >> 16;
+      const uint32_t bUh = flag ? (threshold30(__dmul_rn(clamp01(P0), rho)) + r16) >> 16 : 0u;   // nobody is tested: never
+      store_planes(row, kTU, kTUh, bU, bUh, lane);
+      if (all_finite) {
+        const uint4* rc = reinterpret_cast<const uint4*>(sh.rc + (h * kBW + c.w) * 48);
+        if (lane < 8) reinterpret_cast<uint4*>(row + kTA)[lane] = rc[lane];
+        else if (lane < 12) reinterpret_cast<uint4*>(row + kTAh)[lane - 8] = flag ? rc[lane] : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        const uint32_t rd = finite ? sh.r16[sim] : r16;   // rng.cuh: ward-free probabilities take the run's dither
+        const double P1 = class_probability(1, h, F, alpha, alpha2, gamma), P2 = class_probability(2, h, F, alpha, alpha2, gamma);
+        const uint32_t bA = (threshold30(P1) + rd) >> 16, bB = (threshold30(P2) + rd) >> 16;
+        const uint32_t bAh = flag ? (threshold30(__dmul_rn(clamp01(P1), rho)) + rd) >> 16 : 0u;
+        store_planes(row, kTA, kTB, bA, bB, lane);
+        store_planes(row, kTAh, -1, bAh, 0u, lane);
+      }
+    }
+  }
+}
+
+// per-simulation day totals (:445-459 fused): lane s adds the count of simulation s of the warp's word
+__device__ __forceinline__ void emit_day_counts(const FastArgs& a, int64_t d, int64_t sim0, VCount& vcol, VCount& vdet, uint32_t n_adds) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t cc = vcol.flush(lane, n_adds), cd = vdet.flush(lane, n_adds);
+  if (d < a.counts_ld) {
+    const int64_t at = d + a.counts_ld * (sim0 + lane);
+    if (cc && a.counts_col) atomicAdd(&a.counts_col[at], (int)cc);
+    if (cd && a.counts_det) atomicAdd(&a.counts_det[at], (int)cd);
+  }
+}
+
+// ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
+template <int TTD>
+__device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int64_t d, const DayPlan& pl,
+                                                 int64_t seg0_next, TeamBarrier& bar, uint32_t gw, uint32_t n_gw) {
+  const int lane = threadIdx.x & 31;
+  VCount vcol, vdet;
+  vcol.clear(); vdet.clear();
+  uint32_t since = 0;   // trips since the day counters were flushed
+
+  // the pressure buffer of the day after tomorrow is nobody's input or output today: zero this warp's share of it
+  if (a.press_days == 3) {
+    uint32_t* z = press_of_day(a, c.press, d + 2);
+    const int64_t n = a.max_segs_per_day, lo = n * gw / n_gw, hi = n * (gw + 1) / n_gw;
+    for (int64_t i = lo; i < hi; ++i) __stcg(z + i * (kBW * 32) + lane, 0u);
+  }
+
+  if (pl.w0 < pl.w1) {
+    const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
+    const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
+    const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
+    char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
+    const uint4* pm = a.meta + da + pl.w0 + lane;
+    const uint32_t* press_day = press_of_day(a, c.press, d);
+    uint32_t* press_next = press_of_day(a, c.press, d + 1) + lane;
+    const uint32_t g32 = c.gsim0 >> 5;
+
+    VCount vmain;            // colonised records that feed the warp's current main ward-day of tomorrow
+    vmain.clear();
+    uint32_t wmain = kNone, wsegl = 0xFFFFFFFFu, since_main = 0;   // warp-uniform
+    uint32_t n_xfer = 0;                                            // entries in the transfer list (warp-uniform)
+    auto flush_main = [&]() {
+      const uint32_t v = vmain.flush(lane, since_main);
+      since_main = 0;
+      if (wmain != kNone && v) red_add(press_next + (int64_t)(wmain - (uint32_t)seg0_next) * (kBW * 32), v);
+    };
+    auto drain_xfer = [&]() {   // records that move to another ward: lane s adds simulation s to the successor's ward-day
+      __syncwarp();
+      for (uint32_t e = 0; e < n_xfer; ++e) {
+        const uint2 x = sh.xfer[e];
+        if ((x.y >> lane) & 1u) red_add(press_next + (int64_t)x.x * (kBW * 32), 1u);
+      }
+      __syncwarp();
+      n_xfer = 0;
+    };
+
+    const uint32_t n_run = pl.w1 - pl.w0;
+    for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kBSegs) {
+      const uint32_t n_tab = min((uint32_t)kBSegs, pl.sl_last + 1u - sl);
+      __syncwarp();   // the previous batch's rows are no longer read
+      build_tables_bits(sh, a, c, press_day, seg0, sl, sl + n_tab, test_h, test_a);
+      __syncwarp();
+      const int64_t sb = seg0 + sl;
+      const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(&a.seg_row_start[sb]) - da)) - pl.w0;
+      const uint32_t re = min(pl.w1, (uint32_t)(__ldg(&a.seg_row_start[sb + n_tab]) - da)) - pl.w0;
+      uint32_t tb = rb >> 5;
+      const uint32_t t_end = (re + 31u) >> 5;
+      while (tb < t_end) {
+        const uint32_t te = min(t_end, tb + ((uint32_t)kFlushTrips - since));
+        const uint4* pmt = pm + (int64_t)tb * 32;
+        const uint4* pct = pc + (int64_t)tb * (kBW * 32);
+        // software pipeline: the loads of the next trip are in flight while this one computes
+        uint4 n_meta = make_uint4(0u, kNone, kNone, 0u), n_prev = make_uint4(0u, 0u, 0u, 0u);
+        if (tb * 32u + (uint32_t)lane < n_run) { n_meta = __ldg(pmt); n_prev = __ldcg(pct); }
+        for (uint32_t i = tb * 32u + lane; i < te * 32u + (uint32_t)lane; i += 32u) {   // warp-uniform trip count
+          const uint4 meta = n_meta;
+          uint4 pre = n_prev;
+          pmt += 32; pct += kBW * 32;
+          n_meta = make_uint4(0u, kNone, kNone, 0u);
+          if (i + 32u < min(n_run, te * 32u)) { n_meta = __ldg(pmt); n_prev = __ldcg(pct); }
+          const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
+          const int h = (int)(info >> kInfoHShift);
+          const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
+          const bool on = i < n_run && segl - sl < n_tab;   // this batch's records
+          const uint4* tr = reinterpret_cast<const uint4*>(sh.tab + (on ? (int)(segl & (kBSegs - 1)) * 2 + h : kZeroRowB) * kTabWords);
+          const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
+          if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);   // (C = 0, D = inf) x 32, :359-360
+
+          // ---- draws: u < t per probability class, least significant plane first; four planes per Philox call (rng.cuh) ----
+          uint32_t lt[5] = {0u, 0u, 0u, 0u, 0u}, always[5];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint4 u = philox_rk(a, (uint32_t)orig, (uint32_t)((uint64_t)orig >> 32), g32, kStreamPlanes + (uint32_t)q4);
+            const uint32_t up[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+              const uint4 th = tr[t * 4 + q4];
+              const uint32_t tp[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (q4 * 4 + j < kDrawBits) lt[t] = (tp[j] & ~up[j]) | (~(tp[j] ^ up[j]) & lt[t]);
+                else if (q4 * 4 + j == kDrawBits) always[t] = tp[j];
+              }
+            }
+          }
+          const uint32_t fU = lt[0] | always[0], fA = lt[1] | always[1], fB = lt[2] | always[2];
+          const uint32_t fUh = lt[3] | always[3], fAh = lt[4] | always[4];
+          // ---- transition (:116-155) ----
+          const uint32_t cc = pre.x, det = pre.y, q1 = pre.z, q2 = pre.w;
+          const uint32_t col = (cc & ((det & fB) | (~det & fA))) | (~cc & fU);           // :116-120
+          const uint32_t hit = (cc & fAh) | (~cc & fUh);                                  // tested positive today (:134 / :146)
+          const uint32_t tested = col & hit & ~(det | q1 | q2);                           // no countdown running: D = ttd
+          uint4 post;
+          post.x = col;
+          post.y = col & (det | q1);                                                      // D -= 1 reaches or stays below 0 (:131-132)
+          post.z = 0u; post.w = 0u;
+          if (TTD == 0) post.y |= tested;
+          if (TTD == 1) post.z = tested;
+          if (TTD == 2) { post.z = col & q2; post.w = tested; }
+          if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next), post);         // :402-407 the successor starts from this state
+          vcol.add(col);
+          vdet.add(post.y);
+
+          // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) ----
+          // Most records of a run feed the same ward-day (same ward, tomorrow): a vertical counter for it, flushed when the
+          // ward changes.  A trip that straddles two wards is added in two parts; records that go elsewhere are listed.
+          const uint32_t seg_lo = max(sl, __shfl_sync(0xFFFFFFFFu, segl, 0));
+          if (__builtin_expect(seg_lo != wsegl, 0)) {
+            wsegl = seg_lo;
+            const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
+            if (m != wmain) { flush_main(); wmain = m; }
+          }
+          const bool has = nseg != kNone;
+          bool mine = has && nseg == wmain;
+          vmain.add(mine ? col : 0u);
+          ++since_main;
+          const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, on ? segl : 0u);
+          if (__builtin_expect(seg_hi > seg_lo, 0)) {   // the trip's last ward: its records start the next counter
+            const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_hi]);
+            wsegl = seg_hi;
+            if (m != wmain) {
+              flush_main();
+              wmain = m;
+              const bool mine2 = has && nseg == wmain;
+              vmain.add(mine2 ? col : 0u);
+              ++since_main;
+              mine = mine || mine2;
+            }
+          }
+          const bool is_x = has && !mine;
+          const uint32_t xm = __ballot_sync(0xFFFFFFFFu, is_x);
+          if (xm) {
+            if (is_x) sh.xfer[n_xfer + (uint32_t)__popc(xm & ((1u << lane) - 1u))] = make_uint2(nseg - (uint32_t)seg0_next, col);
+            n_xfer += (uint32_t)__popc(xm);
+            if (n_xfer > (uint32_t)(kXferCap - 32)) drain_xfer();
+          }
+        }
+        since += te - tb;
+        tb = te;
+        if (since == (uint32_t)kFlushTrips) {   // since_main <= since: the main counter cannot overflow either
+          flush_main();
+          emit_day_counts(a, d, c.sim0, vcol, vdet, since);
+          since = 0;
+        }
+      }
+    }
+    flush_main();
+    drain_xfer();
+  }
+  bar.arrive();   // tomorrow's pressure and states are out; the day totals below are nobody's input
+  emit_day_counts(a, d, c.sim0, vcol, vdet, since);
+}
+
+template <int TTD, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ FastArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kWarps = THREADS / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BitsShared sh = carve_bits(smem_raw, warp);
+  const int big = a.teams_plus_one * (a.ctas_per_team + 1);
+  const bool in_big = (int)blockIdx.x < big;
+  const int G = a.ctas_per_team + (in_big ? 1 : 0);
+  const int64_t team = in_big ? blockIdx.x / G : a.teams_plus_one + ((int)blockIdx.x - big) / G;
+  const int rank = in_big ? blockIdx.x % G : ((int)blockIdx.x - big) % G;
+  // the warps of a team pair up: pair `gw` of `n_gw` steps a run of the day's records, warp `w` of the pair its word
+  static_assert(kWarps % kBW == 0, "whole pairs per CTA");
+  const uint32_t gw_all = (uint32_t)(rank * kWarps + warp), gw = gw_all / kBW, n_gw = (uint32_t)(G * kWarps) / kBW;
+  TeamBarrier bar{a.team_barrier + team, 0u, (unsigned)(G * kWarps), G == 1 ? kBarCta : (a.cluster_barrier ? kBarCluster : kBarGlobal)};
+  const int64_t ring = a.ring_chunks * (kBW * 32);
+
+  uint4* team_pre = a.pre + team * 2 * ring;
+  uint32_t* team_press = a.pressure + team * a.press_days * a.max_segs_per_day * (kBW * 32);
+  const uint32_t team_gsim0 = (uint32_t)(a.sim_offset + (uint64_t)team * kBitsSims);
+  const int64_t team_sim0 = team * kBitsSims;
+  BitsCtx c;
+  c.w = (int)(gw_all % kBW);
+  c.pre = team_pre + c.w * 32;
+  c.press = team_press + c.w * 32;
+  c.gsim0 = team_gsim0 + (uint32_t)c.w * 32u;
+  c.sim0 = team_sim0 + c.w * 32;
+
+  // ---- team setup: parameters, run-constant tables and the all-zero rows to shared memory, pressure zeroed ------------
+  for (int q = tid; q < 6 * kBitsSims; q += THREADS) sh.par[q] = a.params[(team_sim0 + q % kBitsSims) + a.p_ld * (q / kBitsSims)];
+  for (int q = lane; q < kTabWords; q += 32) sh.tab[kZeroRowB * kTabWords + q] = 0u;
+  {
+    const int64_t n = (int64_t)a.press_days * a.max_segs_per_day * (kBW * 32), per = (n + G - 1) / G;
+    const int64_t lo = rank * per, hi = min(n, lo + per);
+    for (int64_t i = lo + tid; i < hi; i += THREADS) __stcg(&team_press[i], 0u);
+  }
+  __syncthreads();
+  for (int it = warp; it < 2 * kBW; it += kWarps) {   // (is_new, word): lane = simulation
+    const int h = it / kBW, w = it % kBW, sim = w * 32 + lane;
+    const double alpha = sh.par[sim], gamma = sh.par[2 * kBitsSims + sim], alpha2 = sh.par[4 * kBitsSims + sim];
+    const double rho = sh.par[(h ? 5 : 3) * kBitsSims + sim];
+    const uint32_t gs = team_gsim0 + (uint32_t)sim;
+    const uint32_t rd = chunk16(philox4x32_10((uint32_t)kRunDitherIndex, (uint32_t)(kRunDitherIndex >> 32), gs >> 3, kStreamDither,
+                                              (uint32_t)a.seed, (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
+    if (h == 0) sh.r16[sim] = rd;
+    const double P1 = class_probability(1, h, 0.0, alpha, alpha2, gamma), P2 = class_probability(2, h, 0.0, alpha, alpha2, gamma);
+    uint32_t* rc = sh.rc + (h * kBW + w) * 48;
+    store_planes(rc, 0, 16, (threshold30(P1) + rd) >> 16, (threshold30(P2) + rd) >> 16, lane);
+    store_planes(rc, 32, -1, (threshold30(__dmul_rn(clamp01(P1), rho)) + rd) >> 16, 0u, lane);
+  }
+  __syncthreads();
+  bar.arrive();
+  bar.wait();
+
+  // ---- initial state (:363-372) into the day-0 buffer: a lane draws 8 simulations of a row, four lanes make a word -----
+  {
+    const int64_t n = a.n_init, per = ((n + G - 1) / G + 7) / 8 * 8;
+    const int64_t lo = rank * per, hi = min(n, lo + per);
+    uint32_t* press0 = press_of_day(a, team_press, 0);
+    const int64_t seg00 = a.n_days > 0 ? __ldg(&a.day_seg_start[0]) : 0;
+    for (int64_t r0 = lo + warp * 8; r0 < hi; r0 += kWarps * 8) {
+      const int64_t r = r0 + (lane >> 2);
+      const int g = lane & 3;
+      const bool live = r < hi;
+      const uint32_t slot = live ? __ldg(&a.init_slot[r]) : kNone;   // kNone: overwritten by a predecessor before it is ever read
+      const uint32_t iseg = live ? __ldg(&a.init_seg[r]) : kNone;
+#pragma unroll 1
+      for (int w = 0; w < kBW; ++w) {
+        uint32_t c0 = 0u, d0 = 0u, valid = 0u;
+        if (slot != kNone) {
+          const uint32_t r_lo = (uint32_t)r, r_hi = (uint32_t)((uint64_t)r >> 32), gsl = ((team_gsim0 + (uint32_t)w * 32u) >> 3) + (uint32_t)g;
+          const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+          const uint4 rc_hi = philox4x32_10(r_lo, r_hi, gsl, kStreamInitCol, k0, k1), rc_lo = philox4x32_10(r_lo, r_hi, gsl, kStreamInitCol + 1u, k0, k1);
+          const uint4 rd_hi = philox4x32_10(r_lo, r_hi, gsl, kStreamInitDet, k0, k1), rd_lo = philox4x32_10(r_lo, r_hi, gsl, kStreamInitDet + 1u, k0, k1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int64_t sim = team_sim0 + w * 32 + g * 8 + k;
+            if (sim < a.S) {
+              const double pcol = a.icp[r * a.icp_rs + sim * a.icp_cs], pdet = a.idp[r * a.idp_rs + sim * a.idp_cs];
+              const bool cb = (uint64_t)((chunk16(rc_hi, k) << 16) | chunk16(rc_lo, k)) < threshold33(pcol);
+              const bool db = (uint64_t)((chunk16(rd_hi, k) << 16) | chunk16(rd_lo, k)) < threshold33(pdet);
+              c0 |= (cb ? 1u : 0u) << (g * 8 + k);
+              d0 |= (db ? 1u : 0u) << (g * 8 + k);
+              valid |= 1u << (g * 8 + k);
+            }
+          }
+        }
+        const uint32_t mine_c0 = c0;
+        c0 |= __shfl_xor_sync(0xFFFFFFFFu, c0, 1); c0 |= __shfl_xor_sync(0xFFFFFFFFu, c0, 2);
+        d0 |= __shfl_xor_sync(0xFFFFFFFFu, d0, 1); d0 |= __shfl_xor_sync(0xFFFFFFFFu, d0, 2);
+        valid |= __shfl_xor_sync(0xFFFFFFFFu, valid, 1); valid |= __shfl_xor_sync(0xFFFFFFFFu, valid, 2);
+        if (slot != kNone) {
+          // :372  D0 = d0*c0 is a 0/1 FLAG that the dynamics read as a countdown on day 0: uncolonised -> D = 0 (det without
+          // c); colonised, flag 0 -> D = 0: detected; flag 1 -> D = 1: due tomorrow if ttd >= 1, else neither pending nor
+          // detected (it is re-tested like D = inf)
+          const uint32_t flag1 = c0 & d0;
+          if (g == 0) __stcg(&team_pre[ring_slot_b(slot) + w * 32], make_uint4(c0, valid & ~flag1, TTD >= 1 ? flag1 : 0u, 0u));
+          if (iseg != kNone) {
+            uint32_t* dst = press0 + ((int64_t)(iseg - (uint32_t)seg00) * kBW + w) * 32 + g * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if ((mine_c0 >> (g * 8 + k)) & 1u) red_add(dst + k, 1u);
+          }
+        }
+      }
+    }
+  }
+  bar.arrive();
+
+  // ---- day loop (:381): one team barrier per day ------------------------------------------------------------------
+  DayPlan plan = plan_day(a, 0, gw, n_gw);
+  for (int64_t d = 0; d < a.n_days; ++d) {
+    const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
+    bar.wait();
+    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, gw, n_gw);
+    plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
+  }
+  if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
+}
+
+// ward pressure of a finished run -> out[ward-day + ld * simulation] (press_days = n_days + 1)
+__global__ void k_bits_export_pressure(const uint32_t* __restrict__ pressure, const int64_t* __restrict__ day_seg_start, int64_t n_days,
+                                       int64_t max_segs, int64_t press_days, int64_t S, int32_t* __restrict__ out, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_days * max_segs * S) return;
+  const int64_t s = i % S, sl = (i / S) % max_segs, d = i / (S * max_segs);
+  const int64_t seg = day_seg_start[d] + sl;
+  if (seg >= day_seg_start[d + 1]) return;
+  const int64_t team = s / kBitsSims, w = (s % kBitsSims) / 32, lane = s % 32;
+  out[seg + ld * s] = (int32_t)pressure[((team * press_days + d) * max_segs + sl) * (kBW * 32) + w * 32 + lane];
+}
+
+template <int TTD>
+const void* bits_kernel_of(int shape) {
+  return shape == kShapeRoomy   ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1>
+         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks + 2>
+                                : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks>;
+}
+const void* bits_kernel_ptr(int ttd, int shape) {
+  return ttd == 0 ? bits_kernel_of<0>(shape) : ttd == 1 ? bits_kernel_of<1>(shape) : bits_kernel_of<2>(shape);
+}
+
+}  // namespace
+
+int bits_sims_per_team() { return kBitsSims; }
+size_t bits_shared_bytes() { return bits_smem_bytes(kTeamThreads); }
+
+int bits_max_coresident_ctas(int device, int ttd, int shape) {
+  int per_sm = 0, sms = 0;
+  const void* k = bits_kernel_ptr(ttd, shape);
+  const size_t smem = bits_smem_bytes(kTeamThreads);
+  AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kTeamThreads, smem));
+  return per_sm * sms;
+}
+
+int bits_max_coresident_clusters(int ttd, int shape, int cluster_size) {
+  const void* k = bits_kernel_ptr(ttd, shape);
+  const size_t smem = bits_smem_bytes(kTeamThreads);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cluster_size > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cluster_size * 1024u);
+  cfg.blockDim = dim3((unsigned)kTeamThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid) {
+  const void* k = bits_kernel_ptr(a.ttd, shape);
+  const size_t smem = bits_smem_bytes(kTeamThreads);
+  AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {(void*)&a};
+  if (a.cluster_barrier) {
+    if (a.ctas_per_team > 8) AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kTeamThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)a.ctas_per_team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AMRO_CUDA(cudaLaunchKernelExC(&cfg, k, params));
+  } else if (a.ctas_per_team > 1 || a.teams_plus_one > 0) {
+    AMRO_CUDA(cudaLaunchCooperativeKernel(k, dim3((unsigned)grid), dim3((unsigned)kTeamThreads), params, smem, st));
+  } else {
+    AMRO_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)kTeamThreads), params, smem, st));
+  }
+}
+
+void bits_export_pressure(cudaStream_t st, const uint32_t* pressure, const int64_t* day_seg_start, int64_t n_days, int64_t max_segs,
+                          int64_t press_days, int64_t S, int32_t* out, int64_t ld) {
+  const int64_t n = n_days * max_segs * S;
+  if (n <= 0) return;
+  k_bits_export_pressure<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pressure, day_seg_start, n_days, max_segs, press_days, S, out, ld);
+}
+
+}  // namespace amro

@@ -41,6 +41,7 @@
 #include "kernels.hpp"
 #include "rng.cuh"
 #include "topology.hpp"
+#include "team.cuh"
 
 #define AMRO_PRAGMA_STR(x) _Pragma(#x)
 #define AMRO_PRAGMA_UNROLL(n) AMRO_PRAGMA_STR(unroll n)
@@ -72,14 +73,6 @@ constexpr uint32_t kCodeA2 = kCodeA * kHalves, kCodeZero2 = kCodeZero * kHalves,
 constexpr uint32_t kOne2 = 0x3C003C00u;        // half2 (1.0, 1.0)
 constexpr uint32_t kTwo2 = 0x40004000u;        // half2 (2.0, 2.0)
 
-__device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// two adjacent packed words with one 64-bit RED (p is 8-byte aligned; no 16-bit field ever overflows, so nothing carries
-// from the low word into the high one)
-__device__ __forceinline__ void red_add2(uint32_t* p, uint32_t lo, uint32_t hi) {
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"((unsigned long long)lo | ((unsigned long long)hi << 32)) : "memory");
-}
 // packed half-precision compares / adds on 32-bit registers holding two fp16 patterns
 __device__ __forceinline__ uint32_t h2_ge_mask(uint32_t x, uint32_t y) {  // 0xFFFF per half-word where x >= y
   uint32_t m;
@@ -121,18 +114,6 @@ struct SliceParams {  // the 8 simulations' parameter rows (abm_wards.cpp:79-84)
   uint32_t t30[3][2][8];
   uint32_t r16_run[8];   // the run's dither of those thresholds (rng.cuh: kRunDitherIndex)
 };
-
-// Transition probability for unit weight (W = C), force of infection F -- the reference's expression order, one
-// IEEE operation at a time (:95-112).  pc: 0 = uncolonised, 1 = colonised undetected, 2 = colonised detected.
-__device__ __forceinline__ double class_probability(int pc, int h, double F, double alpha, double alpha2, double gamma, double w = 1.0) {
-  const double W = pc ? w : 0.0;   // :95  W = C * w
-  const double det = (pc == 2) ? 1.0 : 0.0;
-  const double coef = __dadd_rn(__dmul_rn(__dsub_rn(1.0, det), __dsub_rn(1.0, alpha)),
-                                __dmul_rn(det, __dsub_rn(1.0, alpha2)));
-  double P = __dadd_rn(__dmul_rn(coef, W), __dmul_rn(__dsub_rn(1.0, W), F));
-  P = __dadd_rn(P, __dmul_rn(h ? 1.0 : 0.0, gamma));
-  return P;
-}
 
 // probability class of a state class: U, U0 -> 0; A, pending -> 1; detected -> 2
 __device__ __forceinline__ int prob_class(uint32_t cls) { return cls == kClsB ? 2 : (cls == kClsA || cls == kClsPn) ? 1 : 0; }
@@ -178,22 +159,6 @@ __device__ __forceinline__ WarpShared carve_shared(unsigned char* raw, int warp)
   if constexpr (REPLAY) v.P = reinterpret_cast<double*>(mine);
   else v.tab = reinterpret_cast<uint4*>(mine);
   return v;
-}
-
-// Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
-__device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a.rk[2 * r];
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ a.rk[2 * r + 1];
-    c1 = (uint32_t)p1;
-    c3 = (uint32_t)p0;
-    c0 = n0;
-    c2 = n2;
-  }
-  return make_uint4(c0, c1, c2, c3);
 }
 
 // The 14-bit daily draws of one record's 16 simulations (a team = one half of a group of 32 simulations): the group's
@@ -292,52 +257,6 @@ __device__ __forceinline__ uint4 step_record_replay(const WarpShared& sh, const 
 }
 
 }  // namespace
-
-// ---- team barrier ------------------------------------------------------------------------------------------------
-// The warps that share a team's slices (all warps of the team's CTAs) meet once per day: a warp may start day d+1 when
-// every warp of the team has finished day d (its successors' states and tomorrow's pressure are then complete).  Arrival
-// is a release increment of the team's counter by lane 0 after __syncwarp (which orders the other lanes' writes before
-// it); waiting is an acquire-load poll by lane 0, then __syncwarp.  Nothing in the day loop synchronises a whole
-// CTA, so the latency of one warp's barrier or table build is covered by the other warps of the SM.  A team of one CTA
-// uses the hardware barrier instead.  The cooperative launch guarantees co-residency.
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
-//   kBarCta      a team of one CTA: __syncthreads
-//   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
-//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, acquire-load poll)
-constexpr int kBarCta = 0, kBarGlobal = 1, kBarCluster = 2;
-struct TeamBarrier {
-  unsigned* ctr;
-  unsigned target;
-  unsigned n_warps;   // warps of the team
-  int mode;
-  __device__ __forceinline__ void arrive() {
-    if (mode == kBarCta) return;
-    __syncwarp();
-    if (mode == kBarCluster) {
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      return;
-    }
-    target += n_warps;
-    if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-  }
-  __device__ __forceinline__ void wait() {
-    if (mode == kBarCta) { __syncthreads(); return; }
-    if (mode == kBarCluster) {
-      __syncwarp();
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-      return;
-    }
-    if ((threadIdx.x & 31) == 0) {
-      while ((int)(ld_acquire(ctr) - target) < 0) {}   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
-    }
-    __syncwarp();
-  }
-};
 
 // Everything a warp needs about its team (kNS adjacent slices of 8 simulations; a lane carries one record x 8*kNS sims).
 struct TeamCtx {
@@ -484,31 +403,6 @@ __device__ __forceinline__ void push_pressure(uint32_t* dst, const uint32_t (&ac
 #pragma unroll
     for (int q = 0; q < kNS * 4; q += 2) red_add2(dst + q, v[q], v[q + 1]);
   }
-}
-
-// What a warp does on one day: its run [w0, w1) of the day's records (day-relative) and where they sit.  Static
-// (topology only), so it is computed BEFORE the warp waits for the previous day to complete.
-struct DayPlan {
-  int64_t da;          // first position of the day
-  int64_t seg0;        // first ward-day of the day
-  uint32_t w0, w1;     // the run; w0 is a multiple of 32
-  uint32_t sl_first, sl_last;   // ward-days (within the day) the run touches
-};
-__device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32_t gw, uint32_t n_gw) {
-  DayPlan p{};
-  if (d >= a.n_days) return p;
-  p.da = __ldg(&a.day_start[d]);
-  const uint32_t n = (uint32_t)(__ldg(&a.day_start[d + 1]) - p.da), n_chunks = (n + 31u) / 32u;
-  p.seg0 = __ldg(&a.day_seg_start[d]);
-  // the warp's run of 32-record chunks: consecutive trips stay in one ward for a while, so what the records add to
-  // tomorrow's pressure is kept in registers across trips
-  p.w0 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * gw) / n_gw));
-  p.w1 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * (gw + 1)) / n_gw));
-  if (p.w0 < p.w1) {
-    p.sl_first = __ldg(&a.meta[p.da + p.w0].x) & kInfoSegMask;
-    p.sl_last = __ldg(&a.meta[p.da + p.w1 - 1].x) & kInfoSegMask;
-  }
-  return p;
 }
 
 // ---- one day of the team's slices: the run of the day's records that belongs to this warp (abm_wards.cpp:384-407) ----
