@@ -419,13 +419,23 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   int cap = bits_max_coresident_ctas(T->device, ttd, shape);
   if (cap <= 0) fail(AMRO_ECUDA, "bit-sliced kernel cannot be made resident on this device");
   if (const char* e = std::getenv("AMRO_BITS_CTAS_PER_SM")) cap = std::min(cap, std::max(1, std::atoi(e)) * sms);
+  // A pair of warps steps a run of records (one warp per word).  Team size: the largest number of whole CTAs-per-SM layers
+  // (the grid then loads every SM alike) that still leaves a warp about `trips` 32-record trips a day -- measured on config 2:
+  // 18 CTAs per team (2 per SM, 8.7 trips) beat 12, 16, 24 and 36 (profiles/sweeps.txt).
   int trips = 8;
   if (const char* e = std::getenv("AMRO_BITS_TRIPS")) trips = std::max(1, std::atoi(e));
   int G = 1, extra = 0;
-  const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day / ((int64_t)trips * kTeamThreads));
+  const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day * bits_words_per_team() / ((int64_t)trips * kTeamThreads));
   if (n_teams <= cap) {
     G = (int)(cap / n_teams); extra = (int)(cap % n_teams);
-    if (G >= useful) { G = (int)useful; extra = 0; }
+    if (G >= useful) {
+      extra = 0;
+      G = 1;
+      for (int layers = cap / sms; layers >= 1; --layers) {
+        const int g = (int)((int64_t)layers * sms / n_teams);
+        if (g >= 1 && g <= useful + useful / 8) { G = g; break; }
+      }
+    }
   }
   if (const char* e = std::getenv("AMRO_BITS_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
   if (!shape_forced && (int64_t)n_teams * G + extra <= (int64_t)(kTeamMinBlocks - 1) * sms) shape = kShapeRoomy;

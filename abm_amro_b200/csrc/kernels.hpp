@@ -146,6 +146,7 @@ void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_s
 // ----------------------------------------------------------------------------------------------------
 constexpr int kBitsMaxTtd = 2;
 int bits_sims_per_team();
+int bits_words_per_team();   // groups of 32 simulations of a team: the warps of a team pair up, one warp per word
 size_t bits_shared_bytes();
 int bits_max_coresident_ctas(int device, int ttd, int shape);
 int bits_max_coresident_clusters(int ttd, int shape, int cluster_size);

@@ -38,6 +38,10 @@ constexpr int kTU = 0, kTA = 16, kTB = 32, kTUh = 48, kTAh = 64;   // word offse
 constexpr int kZeroRowB = kBSegs * 2;               // rows (ward-day, is_new) + one all-zero row: lanes without a record step against it
 constexpr int kXferCap = 96;                        // entries of a warp's transfer list (drained when fewer than 32 are free)
 constexpr int kCntPlanes = 5;                       // vertical counters count to 31
+#ifndef AMRO_BITS_DENSE_BLOCKS
+#define AMRO_BITS_DENSE_BLOCKS 6
+#endif
+constexpr int kBitsDenseBlocks = AMRO_BITS_DENSE_BLOCKS;   // CTAs per SM the dense shape's register budget is sized for
 constexpr int kFlushTrips = (1 << kCntPlanes) - 1;
 static_assert(kDrawBits == 14, "table rows hold 14 planes + the always mask");
 
@@ -90,15 +94,20 @@ struct VCount {
 //   rc    uint32 [is_new][word][48]                   tables A, B, Ah under a finite force of infection (they do not depend on the ward)
 //   tab   uint32 [kZeroRowB + 1 rows][kTabWords]      per warp: rows (ward-day slot, is_new) of the warp's word
 //   xfer  uint2  [kXferCap]                           per warp: (ward-day of the successor within its day, colonised word)
+//   prep  double [kBSegs][32] + uint32 [kBSegs][32]   per warp: beta / N and the dither of the next batch of ward-days (the part
+//                                                     of a table that does not depend on the ward's pressure, computed while
+//                                                     the warp would otherwise wait for the previous day to complete)
 struct BitsShared {
   double* par;
   uint32_t* r16;
   uint32_t* rc;
   uint32_t* tab;
   uint2* xfer;
+  double* prep_bn;
+  uint32_t* prep_r16;
 };
 constexpr size_t kCtaSharedBytes = sizeof(double) * 6 * kBitsSims + sizeof(uint32_t) * kBitsSims + sizeof(uint32_t) * 2 * kBW * 48;
-constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + sizeof(uint2) * kXferCap;
+constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + sizeof(uint2) * kXferCap + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32;
 static_assert(kCtaSharedBytes % 16 == 0 && kWarpSharedBytes % 16 == 0, "table rows are read as uint4");
 __host__ __device__ inline size_t bits_smem_bytes(int threads) { return kCtaSharedBytes + (size_t)(threads / 32) * kWarpSharedBytes; }
 __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
@@ -109,6 +118,8 @@ __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
   unsigned char* mine = raw + kCtaSharedBytes + (size_t)warp * kWarpSharedBytes;
   s.tab = reinterpret_cast<uint32_t*>(mine);
   s.xfer = reinterpret_cast<uint2*>(s.tab + (kZeroRowB + 1) * kTabWords);
+  s.prep_bn = reinterpret_cast<double*>(s.xfer + kXferCap);
+  s.prep_r16 = reinterpret_cast<uint32_t*>(s.prep_bn + kBSegs * 32);
   return s;
 }
 
@@ -124,8 +135,8 @@ struct BitsCtx {
 
 // element (uint4) index of slot q of a team's first word in a state-ring buffer laid out [chunk of 32 slots][word][32]
 __device__ __forceinline__ int64_t ring_slot_b(uint32_t q) { return (int64_t)(q >> 5) * (kBW * 32) + (q & 31u); }
-__device__ __forceinline__ uint32_t* press_of_day(const FastArgs& a, uint32_t* press, int64_t d) {
-  return press + (int64_t)(d % a.press_days) * a.max_segs_per_day * (kBW * 32);
+__device__ __forceinline__ uint32_t* press_of_day(const FastArgs& a, uint32_t* press, int d) {
+  return press + (int64_t)((unsigned)d % (unsigned)a.press_days) * a.max_segs_per_day * (kBW * 32);
 }
 
 // 14-bit thresholds of two tables -> their plane words in a table row: after the transpose lane j holds plane j of the
@@ -140,44 +151,72 @@ __device__ __forceinline__ void store_planes(uint32_t* row, int first, int secon
 // Uncolonised patients feel the ward: P0 = F + gamma h with F = (beta / N) * sum(W) (:98-112), dithered per ward-day.  The
 // colonised classes do not (W = 1: P = coef + 0 F + gamma h) unless F is not finite: their planes are copied from the
 // run-constant tables, or built here for the simulations whose F is inf / NaN (N = 0).
-__device__ __forceinline__ void build_tables_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, const uint32_t* press_day,
-                                                  int64_t seg0, uint32_t b0, uint32_t b1, bool test_h, bool test_a) {
+// Two steps: prepare (beta / N and the dither: topology and parameters only -- done for a day's first batch BEFORE the warp
+// waits for the previous day) and finish (the pressure is known).
+__device__ __forceinline__ void prepare_tables_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int64_t seg0, uint32_t b0, uint32_t b1) {
   const int lane = threadIdx.x & 31;
-  const int sim = c.w * 32 + lane;
-  const double alpha = sh.par[sim], beta = sh.par[kBitsSims + sim], gamma = sh.par[2 * kBitsSims + sim];
-  const double alpha2 = sh.par[4 * kBitsSims + sim];
+  const double beta = sh.par[kBitsSims + c.w * 32 + lane];
   const uint32_t gs = c.gsim0 + (uint32_t)lane;
 #pragma unroll 1
   for (uint32_t sl = b0; sl < b1; ++sl) {
     const int64_t seg = seg0 + sl;
     const int slot = (int)(sl & (kBSegs - 1));
-    const uint32_t cnt = __ldcg(press_day + (int64_t)sl * (kBW * 32) + lane);
-    const double n_seg = __ldg(&a.seg_N[seg]);
-    const double F = __dmul_rn(__ddiv_rn(beta, n_seg), (double)cnt);   // :98-99, sum(W) = the count of colonised records
-    const bool finite = fabs(F) <= 1.7976931348623157e308;
-    const uint32_t r16 = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gs >> 3, kStreamDither, (uint32_t)a.seed,
-                                               (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
-    const bool all_finite = __all_sync(0xFFFFFFFFu, finite);
+    sh.prep_bn[slot * 32 + lane] = __ddiv_rn(beta, __ldg(&a.seg_N[seg]));   // :98
+    sh.prep_r16[slot * 32 + lane] = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gs >> 3, kStreamDither, (uint32_t)a.seed,
+                                                          (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
+  }
+}
+__device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const uint32_t* press_day, uint32_t b0, uint32_t b1,
+                                                   bool test_h, bool test_a) {
+  const int lane = threadIdx.x & 31;
+  const int sim = c.w * 32 + lane;
+  const double alpha = sh.par[sim], gamma = sh.par[2 * kBitsSims + sim], alpha2 = sh.par[4 * kBitsSims + sim];
+  const double rho_h = sh.par[3 * kBitsSims + sim], rho_i = sh.par[5 * kBitsSims + sim];
+  // two ward-days per pass: their dependent chains (pressure load, fp64, transposes) overlap; a short tail is built twice
+#pragma unroll 1
+  for (uint32_t sl0 = b0; sl0 < b1; sl0 += 2) {
+    uint32_t cnt[2], r16[2];
+    double bn[2];
+    int slot[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t sl = min(sl0 + (uint32_t)u, b1 - 1u);
+      slot[u] = (int)(sl & (kBSegs - 1));
+      cnt[u] = __ldcg(press_day + (int64_t)sl * (kBW * 32) + lane);
+      bn[u] = sh.prep_bn[slot[u] * 32 + lane];
+      r16[u] = sh.prep_r16[slot[u] * 32 + lane];
+    }
+    double F[2];
+    bool finite[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      F[u] = __dmul_rn(bn[u], (double)cnt[u]);   // :98-99, sum(W) = the count of colonised records
+      finite[u] = fabs(F[u]) <= 1.7976931348623157e308;
+    }
+    const bool all_finite = __all_sync(0xFFFFFFFFu, finite[0] && finite[1]);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const bool flag = h ? test_a : test_h;
-      const double rho = sh.par[(h ? 5 : 3) * kBitsSims + sim];
-      uint32_t* row = sh.tab + (slot * 2 + h) * kTabWords;
-      const double P0 = class_probability(0, h, F, alpha, alpha2, gamma);
-      const uint32_t bU = (threshold30(P0) + r16) >> 16;
-      const uint32_t bUh = flag ? (threshold30(__dmul_rn(clamp01(P0), rho)) + r16) >> 16 : 0u;   // nobody is tested: never
-      store_planes(row, kTU, kTUh, bU, bUh, lane);
-      if (all_finite) {
-        const uint4* rc = reinterpret_cast<const uint4*>(sh.rc + (h * kBW + c.w) * 48);
-        if (lane < 8) reinterpret_cast<uint4*>(row + kTA)[lane] = rc[lane];
-        else if (lane < 12) reinterpret_cast<uint4*>(row + kTAh)[lane - 8] = flag ? rc[lane] : make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        const uint32_t rd = finite ? sh.r16[sim] : r16;   // rng.cuh: ward-free probabilities take the run's dither
-        const double P1 = class_probability(1, h, F, alpha, alpha2, gamma), P2 = class_probability(2, h, F, alpha, alpha2, gamma);
-        const uint32_t bA = (threshold30(P1) + rd) >> 16, bB = (threshold30(P2) + rd) >> 16;
-        const uint32_t bAh = flag ? (threshold30(__dmul_rn(clamp01(P1), rho)) + rd) >> 16 : 0u;
-        store_planes(row, kTA, kTB, bA, bB, lane);
-        store_planes(row, kTAh, -1, bAh, 0u, lane);
+      const double rho = h ? rho_i : rho_h;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t* row = sh.tab + (slot[u] * 2 + h) * kTabWords;
+        const double P0 = class_probability(0, h, F[u], alpha, alpha2, gamma);
+        const uint32_t bU = (threshold30(P0) + r16[u]) >> 16;
+        const uint32_t bUh = flag ? (threshold30(__dmul_rn(clamp01(P0), rho)) + r16[u]) >> 16 : 0u;   // nobody is tested: never
+        store_planes(row, kTU, kTUh, bU, bUh, lane);
+        if (all_finite) {
+          const uint4* rc = reinterpret_cast<const uint4*>(sh.rc + (h * kBW + c.w) * 48);
+          if (lane < 8) reinterpret_cast<uint4*>(row + kTA)[lane] = rc[lane];
+          else if (lane < 12) reinterpret_cast<uint4*>(row + kTAh)[lane - 8] = flag ? rc[lane] : make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          const uint32_t rd = finite[u] ? sh.r16[sim] : r16[u];   // rng.cuh: ward-free probabilities take the run's dither
+          const double P1 = class_probability(1, h, F[u], alpha, alpha2, gamma), P2 = class_probability(2, h, F[u], alpha, alpha2, gamma);
+          const uint32_t bA = (threshold30(P1) + rd) >> 16, bB = (threshold30(P2) + rd) >> 16;
+          const uint32_t bAh = flag ? (threshold30(__dmul_rn(clamp01(P1), rho)) + rd) >> 16 : 0u;
+          store_planes(row, kTA, kTB, bA, bB, lane);
+          store_planes(row, kTAh, -1, bAh, 0u, lane);
+        }
       }
     }
   }
@@ -196,7 +235,7 @@ __device__ __forceinline__ void emit_day_counts(const FastArgs& a, int64_t d, in
 
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
 template <int TTD>
-__device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int64_t d, const DayPlan& pl,
+__device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
                                                  int64_t seg0_next, TeamBarrier& bar, uint32_t gw, uint32_t n_gw) {
   const int lane = threadIdx.x & 31;
   VCount vcol, vdet;
@@ -205,9 +244,9 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 
   // the pressure buffer of the day after tomorrow is nobody's input or output today: zero this warp's share of it
   if (a.press_days == 3) {
-    uint32_t* z = press_of_day(a, c.press, d + 2);
-    const int64_t n = a.max_segs_per_day, lo = n * gw / n_gw, hi = n * (gw + 1) / n_gw;
-    for (int64_t i = lo; i < hi; ++i) __stcg(z + i * (kBW * 32) + lane, 0u);
+    uint32_t* z = press_of_day(a, c.press, d + 2) + lane;
+    const uint32_t n = (uint32_t)a.max_segs_per_day, per = (n + n_gw - 1u) / n_gw, lo = min(n, per * gw), hi = min(n, lo + per);
+    for (uint32_t i = lo; i < hi; ++i) __stcg(z + (int64_t)i * (kBW * 32), 0u);
   }
 
   if (pl.w0 < pl.w1) {
@@ -225,6 +264,9 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     uint32_t wmain = kNone, wsegl = 0xFFFFFFFFu, since_main = 0;   // warp-uniform
     uint32_t n_xfer = 0;                                            // entries in the transfer list (warp-uniform)
     auto flush_main = [&]() {
+#ifdef AMRO_EXP_NOFLUSH   // timing experiment (wrong results)
+      if (d >= 2) { since_main = 0; return; }
+#endif
       const uint32_t v = vmain.flush(lane, since_main);
       since_main = 0;
       if (wmain != kNone && v) red_add(press_next + (int64_t)(wmain - (uint32_t)seg0_next) * (kBW * 32), v);
@@ -243,7 +285,11 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kBSegs) {
       const uint32_t n_tab = min((uint32_t)kBSegs, pl.sl_last + 1u - sl);
       __syncwarp();   // the previous batch's rows are no longer read
-      build_tables_bits(sh, a, c, press_day, seg0, sl, sl + n_tab, test_h, test_a);
+      if (sl != pl.sl_first) { prepare_tables_bits(sh, a, c, seg0, sl, sl + n_tab); __syncwarp(); }   // the first batch was prepared before the wait
+#ifdef AMRO_EXP_NOTABLES   // timing experiment (wrong results): tables built on the first two days only
+      if (d < 2)
+#endif
+      finish_tables_bits(sh, c, press_day, sl, sl + n_tab, test_h, test_a);
       __syncwarp();
       const int64_t sb = seg0 + sl;
       const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(&a.seg_row_start[sb]) - da)) - pl.w0;
@@ -353,6 +399,9 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     drain_xfer();
   }
   bar.arrive();   // tomorrow's pressure and states are out; the day totals below are nobody's input
+#ifdef AMRO_EXP_NOEMIT   // timing experiment (wrong results)
+  if (d < 2)
+#endif
   emit_day_counts(a, d, c.sim0, vcol, vdet, since);
 }
 
@@ -414,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   {
     const int64_t n = a.n_init, per = ((n + G - 1) / G + 7) / 8 * 8;
     const int64_t lo = rank * per, hi = min(n, lo + per);
-    uint32_t* press0 = press_of_day(a, team_press, 0);
+    uint32_t* press0 = team_press;   // day 0
     const int64_t seg00 = a.n_days > 0 ? __ldg(&a.day_seg_start[0]) : 0;
     for (int64_t r0 = lo + warp * 8; r0 < hi; r0 += kWarps * 8) {
       const int64_t r = r0 + (lane >> 2);
@@ -466,8 +515,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 
   // ---- day loop (:381): one team barrier per day ------------------------------------------------------------------
   DayPlan plan = plan_day(a, 0, gw, n_gw);
-  for (int64_t d = 0; d < a.n_days; ++d) {
+  const int n_days = (int)a.n_days;
+  for (int d = 0; d < n_days; ++d) {
     const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
+    // what does not depend on the previous day's results: the first batch's beta / N and dithers
+    if (plan.w0 < plan.w1) prepare_tables_bits(sh, a, c, plan.seg0, plan.sl_first, min(plan.sl_last + 1u, plan.sl_first + (uint32_t)kBSegs));
+#ifdef AMRO_EXP_NOWAIT   // timing experiment (wrong results)
+    if (d < 2)
+#endif
     bar.wait();
     process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, gw, n_gw);
     plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
@@ -490,7 +545,7 @@ __global__ void k_bits_export_pressure(const uint32_t* __restrict__ pressure, co
 template <int TTD>
 const void* bits_kernel_of(int shape) {
   return shape == kShapeRoomy   ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1>
-         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks + 2>
+         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kBitsDenseBlocks>
                                 : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks>;
 }
 const void* bits_kernel_ptr(int ttd, int shape) {
@@ -500,6 +555,7 @@ const void* bits_kernel_ptr(int ttd, int shape) {
 }  // namespace
 
 int bits_sims_per_team() { return kBitsSims; }
+int bits_words_per_team() { return kBW; }
 size_t bits_shared_bytes() { return bits_smem_bytes(kTeamThreads); }
 
 int bits_max_coresident_ctas(int device, int ttd, int shape) {

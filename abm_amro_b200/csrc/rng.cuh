@@ -1,6 +1,8 @@
 // Counter-based RNG of the free-running mode (DESIGN.md "RNG spec") and the probability -> threshold map.
 //
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11), hand-written; key = 64-bit seed.
+// Philox4x32 (Salmon, Moraes, Dror, Shaw, SC'11), hand-written; key = 64-bit seed.  The bulk stream -- the plane words of the
+// daily draws, four calls per record and 32 simulations -- runs 7 rounds (Philox4x32-7: the smallest round count the authors
+// report as passing BigCrush; 10 is their default with a safety margin); the dither and initial-state calls run 10.
 //
 // Daily step: the uniforms of a patient-day record are BIT-SLICED over groups of 32 consecutive simulations.  Plane word
 // j (0..13) of (record, group g = global sim >> 5) is word (j & 3) of the call with counter (row_lo, row_hi, g, 8 + (j >> 2));
@@ -27,10 +29,12 @@ constexpr uint32_t kStreamInitCol = 2, kStreamInitDet = 4, kStreamDither = 6, kS
 constexpr int kDrawBits = 14;                              // planes of the daily draw
 constexpr uint64_t kRunDitherIndex = ~0ull;                // dither index of ward-independent probabilities
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+constexpr int kPlaneRounds = 7;                            // Philox rounds of the plane words (the dither / initial-state calls: 10)
+
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -43,6 +47,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
 // 16-bit chunk of simulation k (0..7) of the group
@@ -90,7 +98,7 @@ __device__ __forceinline__ uint32_t philox_u14(uint64_t seed, uint64_t row, uint
   uint32_t u = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const uint4 a = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 5), kStreamPlanes + (uint32_t)c, k0, k1);
+    const uint4 a = philox4x32<kPlaneRounds>((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 5), kStreamPlanes + (uint32_t)c, k0, k1);
     u |= ((a.x >> b) & 1u) << (4 * c);
     u |= ((a.y >> b) & 1u) << (4 * c + 1);
     if (c < 3) { u |= ((a.z >> b) & 1u) << (4 * c + 2); u |= ((a.w >> b) & 1u) << (4 * c + 3); }

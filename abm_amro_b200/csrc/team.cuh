@@ -32,10 +32,11 @@ __device__ __forceinline__ double class_probability(int pc, int h, double F, dou
 }
 
 
-// Philox4x32-10 with the round keys taken from the kernel parameters (constant bank operands)
+// The plane words' Philox4x32 (kPlaneRounds rounds, rng.cuh) with the round keys taken from the kernel parameters (constant
+// bank operands)
 __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPlaneRounds; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a.rk[2 * r];
@@ -89,7 +90,11 @@ struct TeamBarrier {
       return;
     }
     if ((threadIdx.x & 31) == 0) {
-      while ((int)(ld_acquire(ctr) - target) < 0) {}   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
+      while ((int)(ld_acquire(ctr) - target) < 0) {   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
+#ifdef AMRO_POLL_SLEEP_NS
+        __nanosleep(AMRO_POLL_SLEEP_NS);
+#endif
+      }
     }
     __syncwarp();
   }

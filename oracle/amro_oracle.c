@@ -61,10 +61,10 @@ static double mt64_uniform(mt64* g) {
 /* scalar arma::randu(): double(rand()) * (1/RAND_MAX)  (armadillo_bits/arma_rng_cxx03.hpp:81-86) */
 static double glibc_randu(void) { return (double)rand() * (1.0 / 2147483647.0); }
 
-/* Philox4x32-10, Salmon/Moraes/Dror/Shaw SC'11 (the published algorithm; constants as in Random123). */
-void amro_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Philox4x32-R, Salmon/Moraes/Dror/Shaw SC'11 (the published algorithm; constants as in Random123). */
+void amro_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < rounds; ++r) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
     uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -73,6 +73,8 @@ void amro_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uin
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void amro_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { amro_oracle_philox4x32(ctr, key, 10, out); }
+#define AMRO_PLANE_ROUNDS 7 /* RNG spec: the plane words of the daily draws run Philox4x32-7, everything else Philox4x32-10 */
 
 /* RNG spec: number of 32-bit integers r with r * 2^-32 < p, i.e. the Bernoulli(p) threshold on a
  * uniform u = r * 2^-32 in [0,1).  p <= 0 or NaN -> 0 (never), p >= 1 -> 2^32 (always). */
@@ -84,7 +86,7 @@ uint64_t amro_oracle_threshold(double p) {
 
 /* RNG spec, daily step (abm_amro_b200/csrc/rng.cuh).  The uniforms of a record are BIT-SLICED over groups of 32
  * consecutive simulations: plane word j (0..13) of (row, group g = sim >> 5) is word (j & 3) of the Philox call with
- * counter (row_lo, row_hi, g, 8 + (j >> 2)); bit (sim & 31) of plane j is bit j of the 14-bit draw u14(row, sim).
+ * counter (row_lo, row_hi, g, 8 + (j >> 2)) and 7 rounds; bit (sim & 31) of plane j is bit j of the 14-bit draw u14(row, sim).
  * Bernoulli(p) fires iff u14 < B(p) with B(p) = (T30(p) + r16) >> 16, T30(p) = ceil(p * 2^30) clamped to [0, 2^30], and
  * r16 a 16-bit DITHER: the 30-bit threshold is rounded to 14 bits so that E[B(p)] = T30(p) / 2^16 exactly.  The dither is
  * the 16-bit chunk of (stream 6, index, sim) with index = the record's ward-day -- or the all-ones index (one dither per
@@ -102,7 +104,7 @@ uint32_t amro_oracle_philox_plane(uint64_t seed, uint64_t row, uint64_t group32,
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)group32, 8u + (j >> 2)};
   uint32_t a[4];
-  amro_oracle_philox4x32_10(ctr, key, a);
+  amro_oracle_philox4x32(ctr, key, AMRO_PLANE_ROUNDS, a);
   return a[j & 3u];
 }
 uint32_t amro_oracle_philox_u14(uint64_t seed, uint64_t row, uint64_t sim) {
@@ -111,7 +113,7 @@ uint32_t amro_oracle_philox_u14(uint64_t seed, uint64_t row, uint64_t sim) {
   for (unsigned c = 0; c < 4; ++c) {
     uint32_t ctr[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(sim >> 5), 8u + c};
     uint32_t a[4];
-    amro_oracle_philox4x32_10(ctr, key, a);
+    amro_oracle_philox4x32(ctr, key, AMRO_PLANE_ROUNDS, a);
     for (unsigned q = 0; q < 4 && 4 * c + q < 14; ++q) u |= ((a[q] >> (sim & 31u)) & 1u) << (4 * c + q);
   }
   return u;

@@ -65,6 +65,7 @@ const char* amro_oracle_last_error(void);
 
 /* Philox4x32-10 (Salmon et al. 2011) and the probability -> 33-bit threshold map of the RNG spec. */
 void     amro_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void     amro_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 uint64_t amro_oracle_threshold(double p);
 /* the 32-bit uniform integer the spec assigns to (row, global sim, draw kind 0=step 1=init-col 2=init-det) */
 uint32_t amro_oracle_philox_u32(uint64_t seed, uint64_t row, uint64_t sim, uint32_t kind);
