@@ -128,18 +128,21 @@ py::array_t<double> simulate_and_collapse(farray wm_, farray tp_, double icp, do
                                           double rho_imported, int64_t n_sims, int64_t ttd, int64_t tsh, int64_t tsa,
                                           int seed, bool bug_compatible) {
   Mat wm(wm_), tp(tp_);
-  int64_t days = 0;
-  check(amro_simulate_and_collapse(wm.data(), wm.rows, wm.cols, wm.ld, tp.data(), tp.rows, tp.cols, tp.ld, icp, idp,
-                                   initial_patients, alpha, beta, gamma, rho_hospital, alpha2, rho_imported, n_sims, ttd,
-                                   tsh, tsa, seed, device(), bug_compatible, &days, nullptr));
-  auto out = fmat(days, 5);
   g_seed = seed;
+  py::array_t<double> out;
+  // the result array is created (with the GIL re-acquired) once the library knows the number of days
+  auto alloc = [](int64_t days, void* ctx) -> double* {
+    py::gil_scoped_acquire gil;
+    auto* o = static_cast<py::array_t<double>*>(ctx);
+    *o = fmat(days, 5);
+    return o->mutable_data();
+  };
   int rc;
   {
     py::gil_scoped_release nogil;
-    rc = amro_simulate_and_collapse(wm.data(), wm.rows, wm.cols, wm.ld, tp.data(), tp.rows, tp.cols, tp.ld, icp, idp,
-                                    initial_patients, alpha, beta, gamma, rho_hospital, alpha2, rho_imported, n_sims, ttd,
-                                    tsh, tsa, seed, device(), bug_compatible, &days, out.mutable_data());
+    rc = amro_simulate_and_collapse_alloc(wm.data(), wm.rows, wm.cols, wm.ld, tp.data(), tp.rows, tp.cols, tp.ld, icp, idp,
+                                          initial_patients, alpha, beta, gamma, rho_hospital, alpha2, rho_imported, n_sims, ttd,
+                                          tsh, tsa, seed, device(), bug_compatible, alloc, &out);
   }
   check(rc);
   return out;

@@ -61,6 +61,16 @@ using namespace amro;
 // --------------------------------------------------------------------------------------------------------
 struct amro_topology {
   HostTopology H;
+  std::mutex mu;   // amro_simulate calls on one handle are serialised: they share the handle's workspaces
+  // CUDA events around the fused kernel of the last kKernelEvents runs (asynchronous runs are timed after the fact:
+  // amro_topology_kernel_times)
+  static constexpr int kKernelEvents = 64;
+  std::unique_ptr<EventPair[]> kernel_events;
+  uint64_t n_fused_runs = 0;
+  EventPair& next_kernel_events() {
+    if (!kernel_events) kernel_events.reset(new EventPair[kKernelEvents]);
+    return kernel_events[n_fused_runs++ % kKernelEvents];
+  }
   int device = -1;
   double compile_ms = 0.0;
   int coresident[2] = {0, 0};  // cooperative-launch capacity of k_fast<false/true>
@@ -81,6 +91,19 @@ struct amro_topology {
   DevBuf<int32_t> ws_counts;
   DevBuf<double> ws_params;
   DevBuf<unsigned int> ws_barrier;
+  // pinned host staging of the per-day counts for host-pointer callers (pageable destinations copy at a fraction of PCIe speed)
+  int32_t* pinned_counts = nullptr;
+  size_t pinned_counts_n = 0;
+  int32_t* pinned(size_t n) {
+    if (n > pinned_counts_n) {
+      if (pinned_counts) cudaFreeHost(pinned_counts);
+      pinned_counts = nullptr; pinned_counts_n = 0;
+      if (cudaMallocHost(&pinned_counts, n * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); pinned_counts = nullptr; return nullptr; }
+      pinned_counts_n = n;
+    }
+    return pinned_counts;
+  }
+  ~amro_topology() { if (pinned_counts) cudaFreeHost(pinned_counts); }
 
   void ensure_general() {
     if (general_ready) return;
@@ -175,6 +198,21 @@ int amro_topology_get_info(const amro_topology* topo, amro_topology_info* info) 
 
 }  // extern "C"
 
+extern "C" int amro_topology_kernel_times(amro_topology* topo, int n, float* ms) {
+  return guarded([&] {
+    if (!topo || !ms || n < 0) fail(AMRO_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lock(topo->mu);
+    if ((uint64_t)n > topo->n_fused_runs || n > amro_topology::kKernelEvents) fail(AMRO_EINVAL, "only %llu fused runs (at most %d) are on record",
+                                                                                 (unsigned long long)topo->n_fused_runs, amro_topology::kKernelEvents);
+    if (topo->device >= 0) AMRO_CUDA(cudaSetDevice(topo->device));
+    for (int i = 0; i < n; ++i) {   // ms[0] = the oldest of the last n
+      EventPair& e = topo->kernel_events[(topo->n_fused_runs - (uint64_t)n + (uint64_t)i) % amro_topology::kKernelEvents];
+      AMRO_CUDA(cudaEventSynchronize(e.b));
+      ms[i] = e.ms();
+    }
+  });
+}
+
 // Host arrays of a compiled topology, for the CPU tests of the compiler (not part of the public header).
 extern "C" int amro_topology_debug_arrays(const amro_topology* topo, const int64_t** order, const int64_t** day_start,
                                           const int64_t** day_seg_start, const int64_t** seg_row_start,
@@ -242,7 +280,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const bool want_traj = A->keep_trajectory || A->state_out;
   bool lean = !replay && !want_traj && !H.has_half && H.identity_order;   // the kernel instance without those cases
   if (std::getenv("AMRO_FAST_NOLEAN")) lean = false;
-  // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, six per SM, G of them per slice) measured equal or better
+  // Launch shape (kernels_fast.cu).  TEAM (128-thread CTAs, four per SM, G of them per pair of slices) measured equal or better
   // than WIDE (one 768-thread CTA per slice) on every configuration tried (profiles/sweeps.txt), so it is the default;
   // AMRO_FAST_SHAPE=w forces WIDE (kept for the tests and for comparison); AMRO_FAST_NOLEAN=1 runs the full instance where the
   // lean one would do and AMRO_FAST_VERBOSE prints the launch shape chosen (development).
@@ -307,7 +345,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
   f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
   f.S = S; f.n_slices = n_slices;
-  f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
+  f.seed = (uint64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
   f.ttd = A->time_to_detect;
   for (int r = 0; r < 10; ++r) {
     f.rk[2 * r] = (uint32_t)f.seed + (uint32_t)r * 0x9E3779B9u;
@@ -332,17 +370,21 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (std::getenv("AMRO_FAST_VERBOSE"))   // development: the launch shape chosen
     std::fprintf(stderr, "[amro] fast launch: shape %d lean %d teams %lld G %d extra %d cluster %d grid %lld threads %d smem %zu\n", shape, (int)lean,
                  (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), fast_threads(shape), fast_shared_bytes(replay, shape));
-  EventPair ev;
+  EventPair& ev = T->next_kernel_events();
   AMRO_CUDA(cudaEventRecord(ev.a, st));
   fast_launch(st, f, replay, lean, shape, (int)(n_teams * G + extra));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
+  A->kernel_kind = AMRO_KERNEL_CODES; A->grid = (int)(n_teams * G + extra); A->ctas_per_team = G;
+  A->team_barrier = (G == 1 && extra == 0) ? 0 : (use_cluster ? 2 : 1);
 
   // ---- outputs ---------------------------------------------------------------------------------------------
   const size_t cbytes = sizeof(int32_t) * (size_t)(H.n_days_out * S);
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
-  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  // host destinations are pageable as a rule: stage through the handle's pinned buffer (full PCIe speed), copy out after the sync
+  int32_t* staged = (!on_device && (A->counts_colonized || A->counts_detected)) ? T->pinned(2 * (size_t)(H.n_days_out * S)) : nullptr;
+  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(staged ? staged : A->counts_colonized, f.counts_col, cbytes, kind, st));
+  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(staged ? staged + H.n_days_out * S : A->counts_detected, f.counts_det, cbytes, kind, st));
   if (A->day_moments) {
     if (on_device) day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, A->day_moments, H.n_days_out);
     else {
@@ -389,9 +431,12 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     A->launches++;
   }
   if (A->p_out && !on_device) AMRO_CUDA(cudaMemcpyAsync(A->p_out, d_p.p, sizeof(double) * H.R * S, cudaMemcpyDeviceToHost, st));
-  AMRO_CUDA(cudaStreamSynchronize(st));
-  A->kernel_ms = ev.ms();
   A->path_used = AMRO_PATH_FAST;
+  if (on_device && A->async) { A->kernel_ms = 0.f; return; }   // everything is enqueued on the caller's stream
+  AMRO_CUDA(cudaStreamSynchronize(st));
+  if (staged && A->counts_colonized) std::memcpy(A->counts_colonized, staged, cbytes);
+  if (staged && A->counts_detected) std::memcpy(A->counts_detected, staged + H.n_days_out * S, cbytes);
+  A->kernel_ms = ev.ms();
 }
 
 // BITS path (kernels_bits.cu): summary runs of unit-weight hospitals in free-running mode with time_to_detect <= 2 -- the
@@ -475,7 +520,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.icp = in.icp; f.icp_rs = in.icp_rs; f.icp_cs = in.icp_cs;
   f.idp = in.idp; f.idp_rs = in.idp_rs; f.idp_cs = in.idp_cs;
   f.S = S; f.n_slices = S_pad / kSimsPerSlice;
-  f.seed = (uint64_t)(int64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
+  f.seed = (uint64_t)A->seed; f.sim_offset = (uint64_t)A->sim_offset;
   f.ttd = ttd;
   for (int r = 0; r < 10; ++r) {
     f.rk[2 * r] = (uint32_t)f.seed + (uint32_t)r * 0x9E3779B9u;
@@ -493,16 +538,20 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (std::getenv("AMRO_FAST_VERBOSE"))
     std::fprintf(stderr, "[amro] bits launch: shape %d ttd %d teams %lld G %d extra %d cluster %d grid %lld threads %d smem %zu\n", shape, ttd,
                  (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), kTeamThreads, bits_shared_bytes());
-  EventPair ev;
+  EventPair& ev = T->next_kernel_events();
   AMRO_CUDA(cudaEventRecord(ev.a, st));
   bits_launch(st, f, shape, (int)(n_teams * G + extra));
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   A->launches = 1;
+  A->kernel_kind = AMRO_KERNEL_BITS; A->grid = (int)(n_teams * G + extra); A->ctas_per_team = G;
+  A->team_barrier = (G == 1 && extra == 0) ? 0 : (use_cluster ? 2 : 1);
 
   const size_t cbytes = sizeof(int32_t) * (size_t)(H.n_days_out * S);
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(A->counts_colonized, f.counts_col, cbytes, kind, st));
-  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(A->counts_detected, f.counts_det, cbytes, kind, st));
+  // host destinations are pageable as a rule: stage through the handle's pinned buffer (full PCIe speed), copy out after the sync
+  int32_t* staged = (!on_device && (A->counts_colonized || A->counts_detected)) ? T->pinned(2 * (size_t)(H.n_days_out * S)) : nullptr;
+  if (A->counts_colonized) AMRO_CUDA(cudaMemcpyAsync(staged ? staged : A->counts_colonized, f.counts_col, cbytes, kind, st));
+  if (A->counts_detected) AMRO_CUDA(cudaMemcpyAsync(staged ? staged + H.n_days_out * S : A->counts_detected, f.counts_det, cbytes, kind, st));
   if (A->day_moments) {
     if (on_device) day_moments(st, f.counts_col, f.counts_det, H.n_days_out, S, H.n_days_out, A->day_moments, H.n_days_out);
     else {
@@ -526,9 +575,12 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     }
     A->launches++;
   }
-  AMRO_CUDA(cudaStreamSynchronize(st));
-  A->kernel_ms = ev.ms();
   A->path_used = AMRO_PATH_FAST;
+  if (on_device && A->async) { A->kernel_ms = 0.f; return; }   // everything is enqueued on the caller's stream
+  AMRO_CUDA(cudaStreamSynchronize(st));
+  if (staged && A->counts_colonized) std::memcpy(A->counts_colonized, staged, cbytes);
+  if (staged && A->counts_detected) std::memcpy(A->counts_detected, staged + H.n_days_out * S, cbytes);
+  A->kernel_ms = ev.ms();
 }
 
 void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
@@ -555,7 +607,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
   g.order = T->order.p; g.seg_of_pos = T->seg_of_pos.p; g.seg_row_start = T->seg_row_start.p; g.seg_N = T->seg_N.p;
   g.params = in.params; g.p_ld = in.p_ld; g.S = S; g.F = F.p; g.ttd = A->time_to_detect;
   g.replay = replay; g.u_col = in.u_col; g.u_det = in.u_det; g.u_ld = in.u_ld;
-  g.seed = (uint64_t)(int64_t)A->seed; g.sim_offset = (uint64_t)A->sim_offset;
+  g.seed = (uint64_t)A->seed; g.sim_offset = (uint64_t)A->sim_offset;
   if (A->p_out) {
     if (on_device) g.p_out = A->p_out;
     else { d_p.alloc((size_t)(R * S)); AMRO_CUDA(cudaMemsetAsync(d_p.p, 0xFF, sizeof(double) * R * S, st)); g.p_out = d_p.p; }
@@ -605,6 +657,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
   A->kernel_ms = ev.ms();
   A->launches = launches;
   A->path_used = AMRO_PATH_GENERAL;
+  A->kernel_kind = AMRO_KERNEL_FLOAT64; A->grid = 0; A->ctas_per_team = 0; A->team_barrier = 0;
 }
 
 }  // namespace
@@ -613,17 +666,25 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
   return guarded([&] {
     if (!T || !A) fail(AMRO_EINVAL, "NULL argument");
     if (T->device < 0) fail(AMRO_ECUDA, "topology was compiled host-only (device < 0); amro_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(T->mu);
     use_device(T->device);
     const HostTopology& H = T->H;
     const int64_t S = A->n_sims;
     if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");  // :365 with zero simulations
     if (!A->parameters || !A->icp || !A->idp) fail(AMRO_EINVAL, "parameters / icp / idp must not be NULL");
     if (A->p_rows < S) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");                // :98 parameters(s, .)
+    if (A->p_ld < S) fail(AMRO_EINVAL, "p_ld (%lld) is smaller than n_sims (%lld)", (long long)A->p_ld, (long long)S);
+    if (A->state_out && A->so_ld < H.R) fail(AMRO_EINVAL, "so_ld (%lld) is smaller than the number of rows (%lld)", (long long)A->so_ld, (long long)H.R);
+    if (A->async && !A->pointers_on_device) fail(AMRO_EINVAL, "async needs pointers_on_device");
+    if (A->async && A->path == AMRO_PATH_GENERAL) fail(AMRO_EINVAL, "async runs need the fused kernels (path AUTO or FAST)");
     if (A->testing_schedule_hospitalized == 0 || A->testing_schedule_arrivals == 0)
       fail(AMRO_EINVAL, "testing schedule of 0: the reference divides by zero here (abm_wards.cpp:391-392)");
     const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
     if (replay && (!A->u_col || !A->u_det || !A->u_icol || !A->u_idet))
       fail(AMRO_EINVAL, "replay mode needs u_col, u_det, u_icol and u_idet");
+    if (replay && (A->u_ld < H.R || A->ui_ld < H.n_init))
+      fail(AMRO_EINVAL, "u_ld / ui_ld (%lld / %lld) are smaller than the rows they stride over (%lld / %lld)", (long long)A->u_ld,
+           (long long)A->ui_ld, (long long)H.R, (long long)H.n_init);
     if ((A->state_out || A->p_out) && (double)H.R * (double)S * 8.0 > 64e9)
       fail(AMRO_EINVAL, "state_out / p_out of %lld x %lld float64 is too large; run a slice of the simulations", (long long)H.R, (long long)S);
 
@@ -633,6 +694,7 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
     if (path == AMRO_PATH_AUTO) path = fast_ok ? AMRO_PATH_FAST : AMRO_PATH_GENERAL;
     if (path == AMRO_PATH_FAST && !fast_ok)
       fail(AMRO_EINVAL, "fast path not available: %s", H.fast_eligible ? "time_to_detect / number of days / sim_offset out of range" : H.why_not_fast.c_str());
+    if (A->async && path != AMRO_PATH_FAST) fail(AMRO_EINVAL, "async runs need the fused kernels; this run takes the float64 path");
     if (path == AMRO_PATH_GENERAL && (double)H.R * (double)S * 16.0 > 120e9)
       fail(AMRO_EINVAL, "general path needs %lld x %lld x 16 bytes of state; too large", (long long)H.R, (long long)S);
 
@@ -671,6 +733,7 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
     if (path == AMRO_PATH_FAST && bits_eligible(T, A)) run_bits(T, A, in, st, on_device);
     else if (path == AMRO_PATH_FAST) run_fast(T, A, in, st, on_device);
     else run_general(T, A, in, st, on_device);
+    if (on_device && A->async) { A->total_ms = 0.f; return; }
     AMRO_CUDA(cudaEventRecord(ev.b, st));
     AMRO_CUDA(cudaEventSynchronize(ev.b));
     A->total_ms = ev.ms();
@@ -736,37 +799,118 @@ struct CachedTopology {
   int64_t n_init = 0;
   int device = -1;
   uint64_t stamp = 0;
-  amro_topology* t = nullptr;
+  size_t bytes = 0;                       // host + device footprint of the compiled hospital (estimate)
+  std::shared_ptr<amro_topology> t;       // a run in progress holds a reference: eviction never frees a hospital in use
 };
 constexpr int kTopoCacheSlots = 4;
-std::mutex g_cache_mutex;
+std::mutex g_cache_mutex;                 // guards the table below, NOT the runs (those lock their own handle)
 CachedTopology g_cache[kTopoCacheSlots];
 uint64_t g_cache_clock = 0;
+int64_t g_cache_hits = 0, g_cache_misses = 0;
 
-// Returns a topology owned by the cache (valid until evicted; calls are serialised by the mutex the caller holds).
-amro_topology* cached_topology(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K,
-                               int64_t t_cols, int64_t t_ld, int64_t n_init, int device) {
+size_t cache_budget_bytes() {             // AMRO_CACHE_BYTES overrides the default of 8 GiB
+  if (const char* e = std::getenv("AMRO_CACHE_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
+  return (size_t)8 << 30;
+}
+size_t topology_bytes(const amro_topology& t) {
+  const HostTopology& H = t.H;
+  // host: order, pos_of (8 B each), h, w (8 B each), count_day, the four meta arrays (4 B each), push lists; device: 16 B of
+  // meta per record + the general path's arrays when uploaded + workspaces that grow with the runs
+  size_t b = (size_t)H.R * (8 + 8 + 8 + 8 + 4) + (size_t)H.Rp * 16 + (H.push_src.size() + H.push_dst.size()) * 8;
+  b += (size_t)H.Rp * 16 + (size_t)H.R * 8;
+  b += t.ws_pre.n * 16 + t.ws_traj.n * 16 + t.ws_pressure.n * 4 + t.ws_counts.n * 4;
+  return b;
+}
+void destroy_topology(amro_topology* t) { amro_topology_destroy(t); }
+
+// Evict least-recently-used hospitals (never the one being inserted / returned) until the footprint fits the budget.
+void enforce_cache_budget(const CachedTopology* keep) {
+  const size_t budget = cache_budget_bytes();
+  for (;;) {
+    size_t total = 0;
+    CachedTopology* victim = nullptr;
+    for (auto& c : g_cache) {
+      if (!c.t) continue;
+      c.bytes = topology_bytes(*c.t);
+      total += c.bytes;
+      if (&c != keep && (!victim || c.stamp < victim->stamp)) victim = &c;
+    }
+    if (total <= budget || !victim) return;
+    *victim = CachedTopology{};
+  }
+}
+
+// Returns a reference to a compiled hospital held by the cache.  The lookup key is the CONTENT of the two tables (a caller
+// that edits its arrays in place gets a new topology), n_init and the device.
+std::shared_ptr<amro_topology> cached_topology(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K,
+                                               int64_t t_cols, int64_t t_ld, int64_t n_init, int device) {
   Hash128 key;
+  Timer th;
   hash_matrix(key, wm, R, w_cols, w_ld);
   hash_matrix(key, tp, K, t_cols, t_ld);
-  CachedTopology* victim = &g_cache[0];
-  for (auto& c : g_cache) {
-    if (c.t && c.key.a == key.a && c.key.b == key.b && c.n_init == n_init && c.device == device) { c.stamp = ++g_cache_clock; return c.t; }
-    if (c.stamp < victim->stamp) victim = &c;
+  if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] cache key of %lld + %lld rows hashed in %.3f ms\n", (long long)R, (long long)K, th.ms());
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto& c : g_cache)
+      if (c.t && c.key.a == key.a && c.key.b == key.b && c.n_init == n_init && c.device == device) {
+        c.stamp = ++g_cache_clock;
+        ++g_cache_hits;
+        return c.t;
+      }
+    ++g_cache_misses;
   }
-  amro_topology* t = nullptr;
-  int rc = amro_topology_create(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device, &t);
+  amro_topology* raw = nullptr;
+  int rc = amro_topology_create(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device, &raw);
+  if (rc == AMRO_ECUDA || (rc == AMRO_ERUNTIME && std::strstr(amro_last_error(), "memory"))) {
+    // out of device / host memory: let go of every cached hospital nobody is running and try once more
+    amro_topology_cache_clear();
+    rc = amro_topology_create(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device, &raw);
+  }
   if (rc) throw Error(rc, amro_last_error());
-  if (victim->t) amro_topology_destroy(victim->t);
-  *victim = CachedTopology{key, n_init, device, ++g_cache_clock, t};
+  std::shared_ptr<amro_topology> t(raw, destroy_topology);
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  CachedTopology* slot = &g_cache[0];
+  for (auto& c : g_cache) {
+    if (!c.t) { slot = &c; break; }
+    if (c.stamp < slot->stamp) slot = &c;
+  }
+  *slot = CachedTopology{key, n_init, device, ++g_cache_clock, 0, t};
+  enforce_cache_budget(slot);
   return t;
+}
+
+// amro_simulate on a cached hospital; on a CUDA failure (typically out of memory: the workspaces of other cached hospitals
+// stay allocated between calls) the other hospitals are dropped and the run is tried once more.
+void simulate_cached(const std::shared_ptr<amro_topology>& topo, amro_sim_args& a) {
+  int rc = amro_simulate(topo.get(), &a);
+  if (rc == AMRO_ECUDA) {
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lock(g_cache_mutex);
+      for (auto& c : g_cache) if (c.t && c.t != topo) c = CachedTopology{};
+    }
+    rc = amro_simulate(topo.get(), &a);
+  }
+  if (rc) throw Error(rc, amro_last_error());
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (auto& c : g_cache) if (c.t == topo) { enforce_cache_budget(&c); break; }
 }
 
 }  // namespace
 
 extern "C" void amro_topology_cache_clear(void) {
   std::lock_guard<std::mutex> lock(g_cache_mutex);
-  for (auto& c : g_cache) { if (c.t) amro_topology_destroy(c.t); c = CachedTopology{}; }
+  for (auto& c : g_cache) c = CachedTopology{};
+}
+
+extern "C" void amro_topology_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries, int64_t* bytes) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  int64_t n = 0, b = 0;
+  for (auto& c : g_cache) if (c.t) { ++n; b += (int64_t)topology_bytes(*c.t); }
+  if (hits) *hits = g_cache_hits;
+  if (misses) *misses = g_cache_misses;
+  if (entries) *entries = n;
+  if (bytes) *bytes = b;
 }
 
 namespace {
@@ -776,32 +920,31 @@ namespace {
 // X: the counts as they come back from the device (int32) or a float64 matrix; every value is converted to double first
 template <class X>
 void row_mean_sd(const X* xs, int64_t n_days, int64_t S, int64_t ld, double* mean, double* sd) {
-  auto x = [xs](int64_t i) { return (double)xs[i]; };
-  for (int64_t d = 0; d < n_days; ++d) {
-    if (mean) {
-      double acc = 0.0;
-      for (int64_t s = 0; s < S; ++s) acc += x(d + ld * s);
-      mean[d] = acc / (double)S;
-    }
-    if (sd) {
-      double var = 0.0;
-      if (S >= 2) {
-        double a1 = 0.0, a2 = 0.0;
-        int64_t i;
-        for (i = 0; i + 1 < S; i += 2) { a1 += x(d + ld * i); a2 += x(d + ld * (i + 1)); }
-        if (i < S) a1 += x(d + ld * i);
-        const double m = (a1 + a2) / (double)S;
-        double q = 0.0, l = 0.0;
-        for (i = 0; i + 1 < S; i += 2) {
-          const double ti = m - x(d + ld * i), tj = m - x(d + ld * (i + 1));
-          q += (ti * ti) + (tj * tj);
-          l += ti + tj;
-        }
-        if (i < S) { const double ti = m - x(d + ld * i); q += ti * ti; l += ti; }
-        var = (q - (l * l) / (double)S) / (double)S;
+  // Simulation-major passes over the column-major counts (contiguous in memory), one accumulator set per day: every day
+  // sees exactly the operation order of the per-day loops of Armadillo (mean: one accumulator; variance: accumulate's two
+  // accumulators for the mean, then op_var's pairwise (q, l) sums).
+  auto x = [xs, ld](int64_t d, int64_t s) { return (double)xs[d + ld * s]; };
+  const size_t n = (size_t)n_days;
+  if (mean) {
+    std::vector<double> acc(n, 0.0);
+    for (int64_t s = 0; s < S; ++s) for (int64_t d = 0; d < n_days; ++d) acc[d] += x(d, s);
+    for (int64_t d = 0; d < n_days; ++d) mean[d] = acc[d] / (double)S;
+  }
+  if (sd) {
+    if (S < 2) { for (int64_t d = 0; d < n_days; ++d) sd[d] = 0.0; return; }
+    std::vector<double> a1(n, 0.0), a2(n, 0.0), m(n), q(n, 0.0), l(n, 0.0);
+    int64_t i;
+    for (i = 0; i + 1 < S; i += 2) for (int64_t d = 0; d < n_days; ++d) { a1[d] += x(d, i); a2[d] += x(d, i + 1); }
+    if (i < S) for (int64_t d = 0; d < n_days; ++d) a1[d] += x(d, i);
+    for (int64_t d = 0; d < n_days; ++d) m[d] = (a1[d] + a2[d]) / (double)S;
+    for (i = 0; i + 1 < S; i += 2)
+      for (int64_t d = 0; d < n_days; ++d) {
+        const double ti = m[d] - x(d, i), tj = m[d] - x(d, i + 1);
+        q[d] += (ti * ti) + (tj * tj);
+        l[d] += ti + tj;
       }
-      sd[d] = std::sqrt(var);
-    }
+    if (i < S) for (int64_t d = 0; d < n_days; ++d) { const double ti = m[d] - x(d, i); q[d] += ti * ti; l[d] += ti; }
+    for (int64_t d = 0; d < n_days; ++d) sd[d] = std::sqrt((q[d] - (l[d] * l[d]) / (double)S) / (double)S);
   }
 }
 
@@ -824,9 +967,7 @@ extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, i
     if (d_rows != i_rows) fail(AMRO_ERUNTIME, "element-wise multiplication: incompatible matrix dimensions: %lldx%lld and %lldx%lld",
                                (long long)d_rows, (long long)S, (long long)i_rows, (long long)S);
     if (p_cols < 6) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
-    amro_topology* topo = cached_topology(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device);
-    int rc;
+    const std::shared_ptr<amro_topology> topo = cached_topology(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device);
     amro_sim_args a{};
     a.n_sims = S; a.sim_offset = 0; a.time_to_detect = time_to_detect;
     a.testing_schedule_hospitalized = tsh; a.testing_schedule_arrivals = tsa; a.seed = seed;
@@ -835,11 +976,61 @@ extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, i
     a.icp = icp; a.icp_rs = 1; a.icp_cs = i_ld;
     a.idp = idp; a.idp_rs = 1; a.idp_cs = d_ld;
     a.state_out = out + 6 * R; a.so_ld = R;
-    rc = amro_simulate(topo, &a);
-    if (rc) throw Error(rc, amro_last_error());
+    simulate_cached(topo, a);
+    {   // the packed trajectory (2 bytes per record and simulation) is of no use to the next call: give it back
+      std::lock_guard<std::mutex> lock(topo->mu);
+      topo->ws_traj.release();
+    }
     for (int64_t c = 0; c < 6; ++c) std::memcpy(out + c * R, ward_matrix + c * w_ld, sizeof(double) * (size_t)R);  // :375
   });
 }
+
+namespace {
+// amro.simulate_and_collapse (abm_wards.cpp:566-631); `alloc(n_days_out, ctx)` supplies the [n_days_out x 5] result buffer once
+// the number of days is known (from the compiled hospital: no separate pass over ward_matrix)
+void collapse_impl(const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
+                   const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                   double icp, double idp, int64_t initial_patients,
+                   double alpha, double beta, double gamma, double rho_hospital,
+                   double alpha2, double rho_imported, int64_t n_sims,
+                   int64_t time_to_detect, int64_t tsh, int64_t tsa, int seed,
+                   int device, int bug_compatible, int64_t* n_days, amro_alloc_fn alloc, void* ctx) {
+  if (n_rows < 1 || w_cols < 1) fail(AMRO_ERUNTIME, "max(): object has no elements");
+  const int64_t S = n_sims;
+  if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
+  const std::shared_ptr<amro_topology> topo = cached_topology(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device);
+  const int64_t Dd = topo->H.n_days_out;
+  std::vector<double> par((size_t)(S * 6));
+  const double v[6] = {alpha, beta, gamma, rho_hospital, alpha2, rho_imported};
+  for (int c = 0; c < 6; ++c) for (int64_t s = 0; s < S; ++s) par[s + S * c] = v[c];     // :584-590
+  std::vector<int32_t> cc((size_t)(Dd * S)), cd((size_t)(Dd * S));
+  amro_sim_args a{};
+  a.n_sims = S; a.time_to_detect = (int)time_to_detect;                                    // uword -> const int& (:606-608)
+  a.testing_schedule_hospitalized = (int)tsh; a.testing_schedule_arrivals = (int)tsa; a.seed = seed;
+  a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 0;
+  a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
+  a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
+  a.counts_colonized = cc.data(); a.counts_detected = cd.data();
+  Timer ts;
+  simulate_cached(topo, a);
+  if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] simulate_and_collapse: run %.3f ms (kernel %.3f)\n", ts.ms(), a.kernel_ms);
+  double* out = alloc(Dd, ctx);
+  if (!out) fail(AMRO_ERUNTIME, "simulate_and_collapse: no result buffer");
+  std::vector<double> mc(Dd), md(Dd), sc(Dd), sd(Dd);
+  row_mean_sd(cc.data(), Dd, S, Dd, mc.data(), sc.data());                                 // :617-620
+  row_mean_sd(cd.data(), Dd, S, Dd, md.data(), sd.data());
+  for (int64_t d = 0; d < Dd; ++d) {
+    out[d] = (double)d;
+    if (bug_compatible) {  // :625-628 write sd over the mean columns and leave 3-4 zero
+      out[d + Dd * 1] = sc[d]; out[d + Dd * 2] = sd[d]; out[d + Dd * 3] = 0.0; out[d + Dd * 4] = 0.0;
+    } else {
+      out[d + Dd * 1] = mc[d]; out[d + Dd * 2] = md[d]; out[d + Dd * 3] = sc[d]; out[d + Dd * 4] = sd[d];
+    }
+  }
+  if (n_days) *n_days = Dd;
+}
+double* alloc_given(int64_t, void* ctx) { return static_cast<double*>(ctx); }
+}  // namespace
 
 extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
                                           const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
@@ -857,37 +1048,22 @@ extern "C" int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_r
       if (n_days) *n_days = (int64_t)m + 1;
       return;
     }
-    const int64_t S = n_sims;
-    if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
-    amro_topology* topo = cached_topology(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device);
-    int rc;
-    const int64_t Dd = topo->H.n_days_out;
-    std::vector<double> par((size_t)(S * 6));
-    const double v[6] = {alpha, beta, gamma, rho_hospital, alpha2, rho_imported};
-    for (int c = 0; c < 6; ++c) for (int64_t s = 0; s < S; ++s) par[s + S * c] = v[c];     // :584-590
-    std::vector<int32_t> cc((size_t)(Dd * S)), cd((size_t)(Dd * S));
-    amro_sim_args a{};
-    a.n_sims = S; a.time_to_detect = (int)time_to_detect;                                    // uword -> const int& (:606-608)
-    a.testing_schedule_hospitalized = (int)tsh; a.testing_schedule_arrivals = (int)tsa; a.seed = seed;
-    a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 0;
-    a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
-    a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
-    a.counts_colonized = cc.data(); a.counts_detected = cd.data();
-    rc = amro_simulate(topo, &a);
-    if (rc) throw Error(rc, amro_last_error());
-    std::vector<double> mc(Dd), md(Dd), sc(Dd), sd(Dd);
-    row_mean_sd(cc.data(), Dd, S, Dd, mc.data(), sc.data());                                 // :617-620
-    row_mean_sd(cd.data(), Dd, S, Dd, md.data(), sd.data());
-    for (int64_t d = 0; d < Dd; ++d) {
-      out[d] = (double)d;
-      if (bug_compatible) {  // :625-628 write sd over the mean columns and leave 3-4 zero
-        out[d + Dd * 1] = sc[d]; out[d + Dd * 2] = sd[d]; out[d + Dd * 3] = 0.0; out[d + Dd * 4] = 0.0;
-      } else {
-        out[d + Dd * 1] = mc[d]; out[d + Dd * 2] = md[d]; out[d + Dd * 3] = sc[d]; out[d + Dd * 4] = sd[d];
-      }
-    }
-    if (n_days) *n_days = Dd;
+    collapse_impl(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, icp, idp, initial_patients, alpha, beta, gamma,
+                  rho_hospital, alpha2, rho_imported, n_sims, time_to_detect, tsh, tsa, seed, device, bug_compatible, n_days, alloc_given, out);
+  });
+}
+
+extern "C" int amro_simulate_and_collapse_alloc(const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
+                                                const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                                                double icp, double idp, int64_t initial_patients,
+                                                double alpha, double beta, double gamma, double rho_hospital,
+                                                double alpha2, double rho_imported, int64_t n_sims,
+                                                int64_t time_to_detect, int64_t tsh, int64_t tsa, int seed,
+                                                int device, int bug_compatible, amro_alloc_fn alloc, void* ctx) {
+  return guarded([&] {
+    if (!alloc) fail(AMRO_EINVAL, "alloc is NULL");
+    collapse_impl(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, icp, idp, initial_patients, alpha, beta, gamma,
+                  rho_hospital, alpha2, rho_imported, n_sims, time_to_detect, tsh, tsa, seed, device, bug_compatible, nullptr, alloc, ctx);
   });
 }
 
@@ -1008,7 +1184,7 @@ extern "C" int amro_summary_of_total_positive(const double* positive, int64_t n_
           const int64_t k = (int64_t)std::floor(N * p + 0.5);
           const double pk = ((double)k - 0.5) / N;
           const double wgt = (p - pk) * N;
-          v = ((1.0 - wgt) * y[k - 1]) + (wgt * y[k]);
+          v = ((1.0 - wgt) * y[k - 1]) + (wgt * y[std::min<int64_t>(k, n_sims - 1)]);   // k == n_sims only with wgt == 0
         }
         out[d + (3 + i) * n_days] = v;
       }

@@ -41,6 +41,10 @@ class SimResult:
     kernel_ms: float
     total_ms: float
     distance: np.ndarray | None = None    # [S] squared distance of the per-day counts to observed series, if asked for
+    kernel_kind: int = 0                  # capi.KERNEL_*: which kernel stepped the records
+    grid: int = 0                         # CTAs of the fused kernel's launch
+    ctas_per_team: int = 0
+    team_barrier: int = 0                 # capi.BARRIER_*
 
 
 class Topology:
@@ -69,6 +73,12 @@ class Topology:
 
     def __exit__(self, *exc):
         self.close()
+
+    def kernel_times(self, n: int) -> np.ndarray:
+        """Device time (ms) of the fused kernel of the last ``n`` runs, oldest first; waits for them (asynchronous runs)."""
+        ms = (C.c_float * n)()
+        capi.check(capi.lib().amro_topology_kernel_times(self._h, n, ms))
+        return np.array(ms[:], dtype=np.float64)
 
     # ---- introspection (host arrays of the compiled form; used by the CPU tests of the compiler) ----
     def debug_arrays(self) -> dict:
@@ -154,6 +164,7 @@ class Topology:
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
         r = SimResult(cc, cd, st, p, pr, mo, a.path_used, a.launches, a.kernel_ms, a.total_ms)
         r.distance = dist
+        r.kernel_kind, r.grid, r.ctas_per_team, r.team_barrier = a.kernel_kind, a.grid, a.ctas_per_team, a.team_barrier
         return r
 
     # ---- device-resident run (inputs already in HBM; nothing crosses PCIe) ---------------------------------
@@ -161,7 +172,8 @@ class Topology:
                         counts_col_ptr: int, counts_det_ptr: int, n_sims: int, time_to_detect: int, tsh: int,
                         tsa: int, seed: int, *, sim_offset: int = 0, stream: int = 0,
                         icp_strides=(0, 0), idp_strides=(0, 0), path: int = capi.PATH_AUTO,
-                        keep_trajectory: bool = False, day_moments_ptr: int = 0) -> SimResult:
+                        keep_trajectory: bool = False, day_moments_ptr: int = 0, asynchronous: bool = False) -> SimResult:
+        """``asynchronous``: enqueue on ``stream`` and return at once (no timings); the caller synchronises the stream."""
         a = capi.SimArgs()
         a.n_sims, a.sim_offset = n_sims, sim_offset
         a.time_to_detect, a.testing_schedule_hospitalized, a.testing_schedule_arrivals, a.seed = time_to_detect, tsh, tsa, seed
@@ -172,5 +184,8 @@ class Topology:
         a.counts_colonized, a.counts_detected = counts_col_ptr, counts_det_ptr
         a.day_moments = day_moments_ptr or None
         a.stream = stream
+        a.async_ = int(asynchronous)
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
-        return SimResult(None, None, None, None, None, None, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        r = SimResult(None, None, None, None, None, None, a.path_used, a.launches, a.kernel_ms, a.total_ms)
+        r.kernel_kind, r.grid, r.ctas_per_team, r.team_barrier = a.kernel_kind, a.grid, a.ctas_per_team, a.team_barrier
+        return r

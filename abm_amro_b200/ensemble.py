@@ -13,11 +13,11 @@ from __future__ import annotations
 
 import math
 
-SIM_ALIGN = 8  # simulations per 16-byte state word; shard boundaries stay on this grid
+SIM_ALIGN = 32  # simulations that share the plane words of the daily draws (rng.cuh); shard boundaries stay on this grid
 
 
 def shard_sims(total_sims: int, world_size: int, rank: int) -> tuple[int, int]:
-    """Contiguous block ``(offset, count)`` of rank ``rank``; offsets are multiples of 8 and the blocks
+    """Contiguous block ``(offset, count)`` of rank ``rank``; offsets are multiples of 32 and the blocks
     tile ``[0, total_sims)`` exactly (trailing ranks may get 0)."""
     groups = math.ceil(total_sims / SIM_ALIGN)
     per = math.ceil(groups / world_size)

@@ -7,14 +7,18 @@
 A "step" is ONE full run of the hot path over the workload: every day of the synthetic hospital for every
 ensemble member resident on the GPU (config 2 of BASELINE.json: 30 wards x 10,000 patients x 365 days,
 1,000 members per GPU; weak scaling: every GPU runs its own 1,000 members, Philox counters offset by the
-global member index).  One JSON line is printed by rank 0.
+global member index; --scaling strong splits the workload's members over the GPUs instead).  One JSON line is
+printed by rank 0.
 
-  value        device-resident: parameters already in HBM, per-day counts stay in HBM (CUDA events)
+  value        device-resident: parameters already in HBM, per-day counts stay in HBM; the runs are enqueued
+               asynchronously, back to back, with the run's one collective (N > 1) on the same stream (CUDA events)
   e2e          the same run through the host-pointer C ABI call a user makes (amro_simulate with pinned host
                buffers): parameters copied host->device and the per-(day, member) counts copied back, every step
   roofline     algorithmic bytes (4 + 20/S_gpu per update) / device time of the fused kernel
   cpu_baseline the reference's own CPU implementation (oracle/_ref, compiled from the unmodified sources) on the
                host cores, on a bounded sample of the same workload
+  e2e_dropin   the reference's own entry point (amro.simulate_and_collapse of the drop-in module), numpy in / out
+  secondary    config 3 (the 64k-particle sweep) timed in the same process, so that its numbers are driver-run too
 """
 from __future__ import annotations
 
@@ -127,8 +131,9 @@ def truncate_hospital(wm, tp, n_days):
 
 
 def cpu_sample(workload: str, sample_days: int = 60, sims_per_proc: int = 32, reps: int = 1):
-    """Run the reference CPU path on `procs` host processes, each with its own slice of `sims_per_proc`
-    ensemble members of the first `sample_days` days of the workload.  Returns (updates/s, procs, kind, text)."""
+    """Run the reference CPU path on `procs` host processes at once, each stepping `sims_per_proc` ensemble members of the
+    first `sample_days` days of the workload (every process gets the same inputs and seed: the reference's cost does not
+    depend on them, and its output is discarded).  Returns (updates/s, procs, kind, text)."""
     from abm_amro_b200 import synth
     from oracle import ref_runner
     wards, census, days, _ = WORKLOADS[workload]
@@ -216,46 +221,29 @@ def run_reference_arm(args, rank, world):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
+def _algorithmic_bytes(S):
+    return 4.0 + 20.0 / S        # 2 B state read + 2 B state write + the record's topology shared by S members
+
+
+def time_workload(topo, par_np, S, sim_offset, dev, steps, warmup, world, dist, flush, local_rank):
+    """`steps` device-resident runs of one compiled hospital, enqueued back to back on the current stream (asynchronous C ABI
+    calls: kernel -> day moments -> all-reduce, no host synchronisation inside the timed region).  Returns a dict."""
     import torch
-    from abm_amro_b200 import capi, engine, ensemble, synth
-
-    wards, census, days, S = WORKLOADS[args.workload]
-    if args.members:
-        S = args.members
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
-    R = wm.shape[0]
-    t0 = time.perf_counter()
-    topo = engine.Topology(wm, tp, n_init, device=local_rank)
-    topo_ms = (time.perf_counter() - t0) * 1e3
-    info = topo.info
-    n_days = info.n_days_out
-    updates_per_step = float(R) * S
-    sim_offset = rank * ((S + 7) // 8 * 8)
-    par_np = synth.tutorial_parameters(S) if not args.workload.startswith("cfg3") else synth.particle_parameters(S)
-
-    # ---- device-resident inputs / outputs ------------------------------------------------------------------
+    from abm_amro_b200 import ensemble
+    n_days = topo.info.n_days_out
     par_d = torch.from_numpy(np.ascontiguousarray(par_np.T)).to(dev)            # [6 x S] row-major == [S x 6] column-major
     icp_d = torch.tensor([ICP], dtype=torch.float64, device=dev)
     idp_d = torch.tensor([IDP], dtype=torch.float64, device=dev)
     cc_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)               # == [n_days x S] column-major
     cd_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)
     mom_d = torch.zeros((4, n_days), dtype=torch.float64, device=dev)            # == [n_days x 4] column-major
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
         flush.zero_()                                                            # evict L2 between steps
         r = topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), idp_d.data_ptr(), cc_d.data_ptr(),
-                                 cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset,
-                                 stream=stream.cuda_stream, day_moments_ptr=mom_d.data_ptr() if world > 1 else 0)
+                                 cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset, stream=stream.cuda_stream,
+                                 day_moments_ptr=mom_d.data_ptr() if world > 1 else 0, asynchronous=True)
         if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members, summed in place
             ensemble.reduce_moments(mom_d)
         return r
@@ -265,35 +253,78 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches = [], 0
+    launches = 0
     with ClockSampler(local_rank) as clocks:
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             r = step_device()
-            kernel_ms.append(r.kernel_ms)
             launches += r.launches
         e1.record(stream)
         barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    path_used = r.path_used
-    if world > 1:  # what simulate_and_collapse reports, from the last step's reduced moments: [n_days x 4], finite
-        stats = ensemble.moments_to_collapse(mom_d.t(), S * world)
-        assert bool(torch.isfinite(stats).all())
+    kernel_ms = topo.kernel_times(min(steps, 64))                               # CUDA events around each run's fused kernel
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    value = updates_per_step * world * args.steps / (elapsed_ms * 1e-3)
+    return dict(elapsed_ms=elapsed_ms, kernel_ms=float(np.mean(kernel_ms)), launches=launches, clocks=clocks.summary(), result=r,
+                cc_d=cc_d, cd_d=cd_d, mom_d=mom_d, par_d=par_d)
 
-    # ---- end to end through the host-pointer C ABI call (pinned host buffers) ---------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes
+    import torch
+    from abm_amro_b200 import capi, engine, ensemble, synth
+
+    wards, census, days, S_total = WORKLOADS[args.workload]
+    if args.members:
+        S_total = args.members
+    strong = args.scaling == "strong"
+    if strong:                       # the workload's members are split over the GPUs (the 64k-particle sweep: 8,192 per GPU on 8)
+        sim_offset, S = ensemble.shard_sims(S_total, world, rank)
+        if S == 0:
+            raise SystemExit("strong scaling: more GPUs than groups of 32 members")
+    else:                            # every GPU runs its own S_total members
+        S = S_total
+        sim_offset = rank * ((S + 63) // 64 * 64)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    sweep = args.workload.startswith("cfg3")
+    wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
+    R = wm.shape[0]
+    t0 = time.perf_counter()
+    topo = engine.Topology(wm, tp, n_init, device=local_rank)
+    topo_ms = (time.perf_counter() - t0) * 1e3
+    n_days = topo.info.n_days_out
+    total_members = S_total if strong else S * world
+    updates_per_step = float(R) * total_members                                  # whole job, all GPUs
+    par_all = synth.particle_parameters(S_total) if sweep else synth.tutorial_parameters(S_total)
+    par_np = par_all[sim_offset:sim_offset + S] if strong else par_all
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                # > 126 MB L2
+
+    m = time_workload(topo, par_np, S, sim_offset, dev, args.steps, args.warmup, world, dist, flush, local_rank)
+    value = updates_per_step * args.steps / (m["elapsed_ms"] * 1e-3)
+    r = m["result"]
+    if world > 1:  # what simulate_and_collapse reports, from the last step's reduced moments: [n_days x 4], finite
+        stats = ensemble.moments_to_collapse(m["mom_d"].t(), total_members)
+        assert bool(torch.isfinite(stats).all())
+
+    # ---- end to end through the host-pointer C ABI call (pinned host buffers), the run's collective included -------------
     par_h = torch.empty((6, S), dtype=torch.float64).pin_memory()
     par_h.copy_(torch.from_numpy(np.ascontiguousarray(par_np.T)))
     cc_h = torch.empty((S, n_days), dtype=torch.int32).pin_memory()
     cd_h = torch.empty((S, n_days), dtype=torch.int32).pin_memory()
+    mom_h = torch.empty((4, n_days), dtype=torch.float64).pin_memory()
+    mom_e = torch.empty((4, n_days), dtype=torch.float64, device=dev)
     a = capi.SimArgs()
     a.n_sims, a.sim_offset = S, sim_offset
     a.time_to_detect, a.testing_schedule_hospitalized, a.testing_schedule_arrivals, a.seed = TTD, TSH, TSA, SEED
@@ -302,11 +333,20 @@ def run_ours(args, rank, world, local_rank):
     icp_h, idp_h = np.array([ICP]), np.array([IDP])
     a.icp, a.idp = icp_h.ctypes.data, idp_h.ctypes.data
     a.counts_colonized, a.counts_detected = cc_h.data_ptr(), cd_h.data_ptr()
-    import ctypes
+    if world > 1:
+        a.day_moments = mom_h.data_ptr()
 
     def step_host():
         flush.zero_()
         capi.check(capi.lib().amro_simulate(topo._h, ctypes.byref(a)))
+        if world > 1:   # the same collective as the device-resident leg: this rank's day moments, summed over the ranks
+            mom_e.copy_(mom_h, non_blocking=True)
+            ensemble.reduce_moments(mom_e)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
@@ -321,39 +361,77 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = updates_per_step * world * e2e_steps / e2e_s
-    same = bool(torch.equal(cc_h, cc_d.cpu()) and torch.equal(cd_h, cd_d.cpu()))
+    e2e_value = updates_per_step * e2e_steps / e2e_s
+    same = bool(torch.equal(cc_h, m["cc_d"].cpu()) and torch.equal(cd_h, m["cd_d"].cpu()))
+
+    # ---- the reference's own entry point (drop-in module, numpy in / numpy out, compiled-hospital cache warm) -------------
+    dropin = None
+    if world == 1 and not sweep and not args.no_dropin:
+        from abm_amro_b200 import amro
+        call = lambda: amro.simulate_and_collapse(wm, tp, ICP, IDP, n_init, .15, .55, .05, .6, .35, .9, S, TTD, TSH, TSA, SEED)  # noqa: E731
+        call()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            call()
+        dt = (time.perf_counter() - t0) / 5
+        dropin = {"value": float(R) * S / dt, "unit": "updates/s", "ms_per_call": dt * 1e3,
+                  "entry_point": "amro.simulate_and_collapse (content-hashed hospital cache warm; hashing the tables is inside)"}
+
+    # ---- the 64k-particle sweep in the same process (config 3), so that its fraction is driver-timed too --------------------
+    secondary = None
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_secondary:
+        w3, c3, d3, S3 = WORKLOADS["cfg3_20w_5kp_180d_65536s"]
+        wm3, tp3, n3 = synth.make_hospital(w3, c3, d3, seed=1)
+        with engine.Topology(wm3, tp3, n3, device=local_rank) as topo3:
+            m3 = time_workload(topo3, synth.particle_parameters(S3), S3, 0, dev, 5, 3, 1, None, flush, local_rank)
+        u3 = float(wm3.shape[0]) * S3
+        peak, _ = measured_peak_gbs()
+        secondary = {"cfg3_20w_5kp_180d_65536s": {
+            "value": u3 * 5 / (m3["elapsed_ms"] * 1e-3), "unit": "updates/s", "ms_per_step": m3["elapsed_ms"] / 5, "steps": 5, "warmup": 3,
+            "kernel_ms": m3["kernel_ms"], "roofline_frac": u3 * _algorithmic_bytes(S3) / (m3["kernel_ms"] * 1e-3) / 1e9 / peak,
+            "traffic": ncu_traffic_bytes("cfg3_20w_5kp_180d_65536s"), "clocks": m3["clocks"],
+            "launch": {"grid": m3["result"].grid, "ctas_per_team": m3["result"].ctas_per_team}}}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        b_alg = 4.0 + 20.0 / S
-        k_ms = float(np.mean(kernel_ms))
-        achieved = updates_per_step * b_alg / (k_ms * 1e-3) / 1e9
+        b_alg = _algorithmic_bytes(S)
+        k_ms = m["kernel_ms"]
+        achieved = float(R) * S * b_alg / (k_ms * 1e-3) / 1e9                    # this GPU's kernel
         traffic = ncu_traffic_bytes(args.workload)
         cpu = None
         if not args.no_cpu_baseline:
             v, procs, kind, text = cpu_sample(args.workload)
             cpu = {"value": v, "unit": "updates/s", "cores": procs, "kind": kind, "sample": text}
+        kinds = {capi.KERNEL_CODES: "16-bit state codes", capi.KERNEL_BITS: "bit-sliced state", capi.KERNEL_FLOAT64: "float64 planes"}
         line = {
             "metric": "patient-day-updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 state / u32 Philox / f64 probabilities",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["elapsed_ms"] / args.steps,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "u32 bit planes (32 members per register) / Philox4x32 / f64 probabilities",
             "data": "synthetic",
             "config": {"workload": args.workload, "wards": wards, "census": census, "days": days, "members_per_gpu": S,
-                       "patient_day_rows": R, "updates_per_step_per_gpu": updates_per_step,
-                       "path": "fast" if path_used == capi.PATH_FAST else "general",
+                       "members_total": total_members, "patient_day_rows": R, "updates_per_step": updates_per_step,
+                       "path": "fast" if r.path_used == capi.PATH_FAST else "general",
+                       "kernel": kinds.get(r.kernel_kind, "?"),
+                       "launch": {"grid": r.grid, "ctas_per_team": r.ctas_per_team, "team_barrier": ["cta", "global", "cluster"][r.team_barrier]},
                        "l2": "256 MB buffer written between steps (inside the timed region)",
+                       "timed_region": "asynchronous runs enqueued back to back: kernel -> day moments -> all-reduce (N > 1), one sync at the end",
                        "topology_compile_ms": topo_ms,
                        "counts_match_between_device_and_host_api": same},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": b_alg,
-                         "kernel_ms": k_ms},
+                         "kernel_ms": k_ms,
+                         "note": "algorithmic bytes per SURVEY.md 8(d); the kernel itself keeps 4 bits per (record, member): it moves about "
+                                 "1 B per update and is bound by the integer ALU pipe, not by HBM (DESIGN.md 3.4)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "updates/s",
-                    "h2d_bytes_per_step": int(S * 6 * 8 + 16), "d2h_bytes_per_step": int(2 * n_days * S * 4),
-                    "steps": e2e_steps},
-            "gpu_launches": launches,
-            "clocks": clocks.summary(),
+                    "h2d_bytes_per_step": int(S * 6 * 8 + 16 + (4 * n_days * 8 if world > 1 else 0)),
+                    "d2h_bytes_per_step": int(2 * n_days * S * 4 + (4 * n_days * 8 if world > 1 else 0)),
+                    "steps": e2e_steps, "collective_inside": world > 1},
+            "e2e_dropin": dropin,
+            "secondary": secondary,
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
         }
         print(json.dumps(line), flush=True)
     topo.close()
@@ -370,6 +448,10 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--members", type=int, default=0, help="override members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-3 block of the default line")
+    ap.add_argument("--no-dropin", action="store_true", help="skip timing the drop-in module's simulate_and_collapse")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU runs the workload's members; strong: the members are split over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

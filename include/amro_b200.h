@@ -83,18 +83,27 @@ int  amro_topology_get_info(const amro_topology* topo, amro_topology_info* info)
  * (abm_wards.cpp:322-414) fused with total_positive_colonized/_detected (:435-509): state stays in HBM
  * across all days, only the per-(day, simulation) counts -- and, if asked, the trajectory -- leave.
  * ---------------------------------------------------------------------------------------------- */
+enum amro_kernel_kind {
+  AMRO_KERNEL_NONE = 0,
+  AMRO_KERNEL_CODES = 1,   /* kernels_fast.cu: 16-bit state codes (trajectories, half weights, replay)   */
+  AMRO_KERNEL_BITS = 2,    /* kernels_bits.cu: state bit-sliced over simulations (summary runs)          */
+  AMRO_KERNEL_FLOAT64 = 3  /* kernels_general.cu: the reference's float64 planes                         */
+};
+
 typedef struct amro_sim_args {
   int64_t n_sims;              /* S: simulations run by THIS call (this GPU's shard)                      */
   int64_t sim_offset;          /* global index of simulation 0 (Philox counters; keeps results independent
                                   of how an ensemble is sharded over GPUs)                               */
+  int64_t seed;                /* the 64-bit Philox key (the reference's `int seed`, sign-extended)       */
   int32_t time_to_detect;
   int32_t testing_schedule_hospitalized;
   int32_t testing_schedule_arrivals;
-  int32_t seed;
   int32_t rng_mode;            /* enum amro_rng_mode                                                      */
   int32_t path;                /* enum amro_path                                                          */
   int32_t keep_trajectory;     /* 0: two-day ring of state (summary runs); 1: keep every record's state   */
   int32_t pointers_on_device;  /* 0: every pointer below is host memory; 1: device memory (no copies)     */
+  int32_t async;               /* with pointers_on_device: 1 = enqueue on `stream` and return without waiting
+                                  (kernel_ms / total_ms are then 0); the caller synchronises the stream      */
 
   /* parameters [>= S x 6], column stride p_ld */
   const double* parameters;  int64_t p_rows;  int64_t p_ld;
@@ -131,9 +140,20 @@ typedef struct amro_sim_args {
   int32_t  launches;           /* kernels launched by this call                                           */
   float    kernel_ms;          /* device time of the simulation kernels (CUDA events)                     */
   float    total_ms;           /* device time incl. copies                                                */
+  int32_t  kernel_kind;        /* enum amro_kernel_kind: which kernel stepped the records                 */
+  int32_t  grid;               /* CTAs of the fused kernel's launch (0 on the float64 path)               */
+  int32_t  ctas_per_team;      /* CTAs that share a group of simulations and meet once per day            */
+  int32_t  team_barrier;       /* 0: __syncthreads (one CTA per team), 1: counter in global memory, 2: cluster barrier */
 } amro_sim_args;
 
+/* Thread safety: calls on ONE handle are serialised by a mutex inside the handle (they share its device workspaces);
+ * different handles are independent.  An asynchronous call (pointers_on_device + async) returns with its work pending on
+ * `stream`: later calls on the same handle must be enqueued on the same stream, or ordered after it by the caller.
+ * FAST needs sim_offset to be a multiple of 32 (a group of 32 simulations shares the plane words of the daily draws). */
 int amro_simulate(amro_topology* topo, amro_sim_args* args);
+/* Device time (CUDA events) of the fused kernel of the last n runs on this handle, oldest first (n <= 64): how an
+ * asynchronous caller times its runs after synchronising.  Waits for those runs to finish. */
+int amro_topology_kernel_times(amro_topology* topo, int n, float* ms);
 
 /* ------------------------------------------------------------------------------------------------
  * One-call equivalents of the reference's Python entry points (host pointers).
@@ -143,6 +163,10 @@ int amro_simulate(amro_topology* topo, amro_sim_args* args);
  * ward_matrix / total_patients_per_ward, so that optimisation loops over the parameters (the use the reference's
  * tutorial recommends simulate_and_collapse for) do not recompile the hospital every call.  This frees them. */
 void amro_topology_cache_clear(void);
+/* The cache keeps at most four hospitals and at most AMRO_CACHE_BYTES (environment, default 8 GiB) of host + device memory,
+ * evicting the least recently used; a hospital is never freed while a call is running on it.  Lookups, compiled hospitals
+ * held and their footprint (any pointer may be NULL). */
+void amro_topology_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries, int64_t* bytes);
 
 /* amro.simulate_discrete_model (amro.cpp:18-91 -> abm_wards.cpp:322).  out is [R x (6+2S)], ld = R. */
 int amro_simulate_discrete_model(const double* icp, int64_t i_rows, int64_t i_cols, int64_t i_ld,
@@ -163,6 +187,16 @@ int amro_simulate_and_collapse(const double* ward_matrix, int64_t n_rows, int64_
                                double alpha2, double rho_imported, int64_t n_sims,
                                int64_t time_to_detect, int64_t tsh, int64_t tsa, int seed,
                                int device, int bug_compatible, int64_t* n_days, double* out);
+/* The same with the result buffer supplied by a callback once the number of days is known (no shape query, no second pass
+ * over ward_matrix): alloc(n_days_out, ctx) returns room for [n_days_out x 5] doubles, or NULL to abort. */
+typedef double* (*amro_alloc_fn)(int64_t n_days_out, void* ctx);
+int amro_simulate_and_collapse_alloc(const double* ward_matrix, int64_t n_rows, int64_t w_cols, int64_t w_ld,
+                                     const double* tppw, int64_t t_rows, int64_t t_cols, int64_t t_ld,
+                                     double icp, double idp, int64_t initial_patients,
+                                     double alpha, double beta, double gamma, double rho_hospital,
+                                     double alpha2, double rho_imported, int64_t n_sims,
+                                     int64_t time_to_detect, int64_t tsh, int64_t tsa, int seed,
+                                     int device, int bug_compatible, amro_alloc_fn alloc, void* ctx);
 
 /* amro.progress_patients_1_timestep (amro.cpp:157-222 -> abm_wards.cpp:219) and
  * amro.progress_patients_probability_ward_1_timestep (amro.cpp:93-155 -> abm_wards.cpp:70) when

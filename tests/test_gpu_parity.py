@@ -373,6 +373,98 @@ def test_full_size_config2_properties():
         assert np.array_equal(col, a.counts_colonized[:, :8]) and np.array_equal(det, a.counts_detected[:, :8])
 
 
+# ---- oracle parity at the benchmarked launch shapes ---------------------------------------------------------------------
+# The throughput claims rest on particular launches: config 2 (16 teams of 18 CTAs on the global-memory barrier, the 3-CTAs-per-SM
+# register budget), config 3 (one CTA per team, more teams than CTA slots: several waves) and a config-4-shaped network
+# (4 teams of 148 CTAs).  Shards are bit-independent of each other (the Philox counters carry the GLOBAL simulation index),
+# so two non-adjacent 32-member shards of the full run are compared bit for bit with the C oracle run on those members alone.
+def _shard_counts_from_oracle(wm, tp, n_init, par, off, n, ttd, tsh, tsa, seed):
+    ref = oracle.simulate_discrete_model(np.full((n_init, n), 0.2), np.full((n_init, n), 0.2), wm, tp, par[off:off + n], ttd, tsh, tsa, seed,
+                                         rng=oracle.Rng(oracle.RNG_PHILOX, sim_offset=off))
+    day, days = wm[:, 0].astype(int), int(wm[:, 0].max()) + 1
+    col = np.stack([np.bincount(day, weights=(ref[:, 6 + s] == 1), minlength=days) for s in range(n)], 1)
+    det = np.stack([np.bincount(day, weights=(ref[:, 6 + n + s] <= 0), minlength=days) for s in range(n)], 1)
+    return col.astype(np.int32), det.astype(np.int32)
+
+
+BENCH_SHAPES = {  # wards, census, days, members, particle sweep?, shard offsets, expected (CTAs per team, barrier, grid)
+    "cfg2": (30, 10_000, 365, 1000, False, (32, 960), (18, capi.BARRIER_GLOBAL, 288)),
+    "cfg3": (20, 5_000, 180, 65_536, True, (64, 40_000), (1, capi.BARRIER_CTA, 1024)),
+    "cfg4_shaped": (500, 200_000, 10, 256, False, (0, 224), (148, capi.BARRIER_GLOBAL, 592)),
+}
+
+
+@pytest.mark.parametrize("name", list(BENCH_SHAPES))
+def test_benchmarked_launch_shapes_match_the_oracle(name):
+    nw, cen, nd, S, sweep, offsets, (g_want, barrier_want, grid_want) = BENCH_SHAPES[name]
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=1)
+    par = synth.particle_parameters(S, seed=100) if sweep else synth.tutorial_parameters(S)
+    with engine.Topology(wm, tp, n_init) as topo:
+        got = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)          # the default launch: what bench.py times
+        assert got.path_used == capi.PATH_FAST and got.kernel_kind == capi.KERNEL_BITS
+        assert (got.ctas_per_team, got.team_barrier, got.grid) == (g_want, barrier_want, grid_want)
+        for off in offsets:
+            col, det = _shard_counts_from_oracle(wm, tp, n_init, par, off, 32, 2, 7, 1, 42)
+            assert np.array_equal(got.counts_colonized[:, off:off + 32], col), f"{name}: colonised counts of members {off}.. differ"
+            assert np.array_equal(got.counts_detected[:, off:off + 32], det), f"{name}: detected counts of members {off}.. differ"
+
+
+def test_ward_sized_ensemble_matches_reference_mean_and_variance(golden):
+    # The daily draws of one ward-day and simulation share a threshold dither (rng.cuh): marginals are exact, and the joint law
+    # is argued to be over-dispersed by at most n * 2^-14.  This checks it where it matters: wards of config 2's size (333
+    # records per ward-day) against the compiled reference's own 512-member ensemble (tools/make_golden_wards.py), on the
+    # colonised count every ward-day starts with -- the reference's sum(W) (:99), i.e. the per-ward counts.
+    z = golden("ward_counts")
+    nw, cen, nd, hseed = (int(x) for x in z["hospital"])
+    ttd, tsh, tsa = (int(x) for x in z["args"])
+    ref = z["counts"].astype(float)                                   # [ward-days of days >= 1 x 512]
+    S = ref.shape[1]
+    wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=hseed)
+    with engine.Topology(wm, tp, n_init) as topo:
+        got = topo.simulate(synth.tutorial_parameters(S), float(z["init"][0]), float(z["init"][1]), ttd, tsh, tsa, 99, want_pressure=True)
+        assert got.kernel_kind == capi.KERNEL_BITS
+    mine = got.pressure[int(z["first_segment"]):].astype(float)
+    assert mine.shape == ref.shape
+    se = np.sqrt(mine.var(1) / S + ref.var(1) / S)
+    assert np.all(np.abs(mine.mean(1) - ref.mean(1)) < 5 * se)        # every ward-day's mean within Monte Carlo error
+    lr = np.log(mine.var(1, ddof=1) / ref.var(1, ddof=1))             # log variance ratio: sd ~ sqrt(2/511 * 2) = 0.09 per ward-day
+    assert np.all(np.abs(lr) < 0.5)
+    assert abs(lr.mean()) < 5 * 0.0885 / np.sqrt(len(lr)), f"per-ward variances are off by {np.expm1(lr.mean()) * 100:.1f} % on average"
+
+
+def test_compiled_hospital_cache_of_the_one_call_entry_points():
+    # amro.simulate_and_collapse / simulate_discrete_model keep compiled hospitals, keyed by content
+    from abm_amro_b200 import amro
+    amro.clear_cache()
+    base = capi.cache_stats()
+    wm, tp, n_init = synth.make_hospital(4, 120, 12, seed=3)
+    args = (0.2, 0.3, n_init, .15, .55, .05, .6, .35, .9, 24, 2, 7, 1, 5)
+    a = amro.simulate_and_collapse(wm, tp, *args)
+    s1 = capi.cache_stats()
+    assert (s1["misses"] - base["misses"], s1["hits"] - base["hits"], s1["entries"]) == (1, 0, 1) and s1["bytes"] > 0
+    b = amro.simulate_and_collapse(wm.copy(), tp.copy(), *args)          # other arrays, same content: a hit
+    s2 = capi.cache_stats()
+    assert (s2["misses"] - base["misses"], s2["hits"] - base["hits"]) == (1, 1) and np.array_equal(a, b)
+    wm2 = wm.copy(order="F")
+    wm2[wm2[:, 0] == 5, 3] = 1.0                                          # edited in place: every record of day 5 is an arrival
+    c = amro.simulate_and_collapse(wm2, tp, *args)
+    s3 = capi.cache_stats()
+    assert (s3["misses"] - base["misses"], s3["entries"]) == (2, 2) and not np.array_equal(a, c)
+    ref = oracle.simulate_and_collapse(wm2, tp, *args, rng=oracle.Rng(oracle.RNG_PHILOX))
+    assert np.array_equal(c, ref)                                          # ... and the edit is what was simulated
+    d = amro.simulate_and_collapse(wm, tp, 0.2, 0.3, n_init - 1, *args[3:])   # same tables, another initial block: another topology
+    assert capi.cache_stats()["misses"] - base["misses"] == 3 and d.shape == a.shape
+    for k in range(4):                                                     # more hospitals than slots: the oldest go
+        w, t, n = synth.make_hospital(3, 50, 6, seed=20 + k)
+        amro.simulate_and_collapse(w, t, 0.2, 0.3, n, *args[3:])
+    s4 = capi.cache_stats()
+    assert s4["entries"] == 4 and s4["misses"] - base["misses"] == 7
+    amro.simulate_and_collapse(wm, tp, *args)                              # evicted meanwhile: compiled again, same numbers
+    assert capi.cache_stats()["misses"] - base["misses"] == 8
+    amro.clear_cache()
+    assert capi.cache_stats()["entries"] == 0
+
+
 def test_device_pointer_api_matches_host_api():
     torch = pytest.importorskip("torch")
     wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=2)

@@ -196,7 +196,7 @@ def test_shard_sims_tiles_the_ensemble():
     for total in [1, 7, 8, 1000, 1001, 65536]:
         for world in [1, 2, 3, 8]:
             blocks = [ensemble.shard_sims(total, world, r) for r in range(world)]
-            assert all(o % 8 == 0 for o, _ in blocks)
+            assert all(o % 32 == 0 for o, _ in blocks)   # a group of 32 simulations shares the plane words of the daily draws
             assert sum(n for _, n in blocks) == total
             live = [b for b in blocks if b[1] > 0]
             assert live[0][0] == 0 and all(live[i][0] + live[i][1] == live[i + 1][0] for i in range(len(live) - 1))
@@ -209,7 +209,7 @@ from abm_amro_b200 import ensemble, synth
 from oracle import oracle
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-S = 24
+S = 80
 wm, tp, n_init = synth.make_hospital(3, 40, 10, seed=2)
 par = synth.tutorial_parameters(S)
 icp = np.full((n_init, S), 0.2); idp = np.full((n_init, S), 0.3)
