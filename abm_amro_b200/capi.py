@@ -29,6 +29,11 @@ class TopologyInfo(C.Structure):
                 ("device", C.c_int32), ("compile_ms", C.c_double), ("why_not_fast", C.c_char * 128)]
 
 
+class HospitalSpec(C.Structure):
+    _fields_ = [("n_wards", _i64), ("census", _i64), ("n_days", _i64), ("seed", _i64),
+                ("p_discharge", C.c_double), ("p_transfer", C.c_double)]
+
+
 class SimArgs(C.Structure):
     _fields_ = [("n_sims", _i64), ("sim_offset", _i64), ("seed", _i64),
                 ("time_to_detect", C.c_int32), ("testing_schedule_hospitalized", C.c_int32),
@@ -50,7 +55,7 @@ class SimArgs(C.Structure):
 
 # every entry point include/amro_b200.h declares (tests/test_host.py checks this list against the header)
 EXPORTS = ["amro_last_error", "amro_version", "amro_device_count", "amro_topology_create", "amro_topology_destroy",
-           "amro_topology_get_info", "amro_topology_kernel_times", "amro_topology_cache_clear", "amro_topology_cache_stats", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse", "amro_simulate_and_collapse_alloc",
+           "amro_topology_get_info", "amro_topology_generate", "amro_hospital_tables", "amro_topology_kernel_times", "amro_topology_cache_clear", "amro_topology_cache_stats", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse", "amro_simulate_and_collapse_alloc",
            "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive"]
 
 _lib = None
@@ -73,6 +78,9 @@ def lib():
         L.amro_topology_get_info.argtypes = [C.c_void_p, C.POINTER(TopologyInfo)]
         L.amro_simulate.argtypes = [C.c_void_p, C.POINTER(SimArgs)]
         L.amro_topology_kernel_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.amro_topology_generate.argtypes = [C.POINTER(HospitalSpec), C.c_int, C.POINTER(C.c_void_p)]
+        L.amro_hospital_tables.argtypes = [C.POINTER(HospitalSpec), C.POINTER(_i64), C.POINTER(_i64), C.c_void_p, C.c_void_p]
+        L.amro_topology_debug_device_arrays.argtypes = [C.c_void_p] * 8
         L.amro_topology_cache_stats.argtypes = [C.POINTER(_i64)] * 4
         L.amro_topology_cache_stats.restype = None
         L.amro_topology_cache_clear.restype = None

@@ -14,6 +14,7 @@
 #include "common.hpp"
 #include "kernels.hpp"
 #include "topology.hpp"
+#include "handle.cuh"
 
 namespace amro {
 
@@ -36,13 +37,6 @@ void use_device(int device) {
   AMRO_CUDA(cudaSetDevice(device));
 }
 
-struct EventPair {
-  cudaEvent_t a = nullptr, b = nullptr;
-  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
-  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
-  float ms() const { float t = 0.f; cudaEventElapsedTime(&t, a, b); return t; }
-};
-
 // strided host matrix -> dense device matrix [rows x cols], ld = rows
 void upload_matrix(DevBuf<double>& dst, const double* src, int64_t rows, int64_t cols, int64_t ld, cudaStream_t st) {
   dst.alloc((size_t)std::max<int64_t>(rows * cols, 1));
@@ -55,72 +49,6 @@ void upload_matrix(DevBuf<double>& dst, const double* src, int64_t rows, int64_t
 }  // namespace amro
 
 using namespace amro;
-
-// --------------------------------------------------------------------------------------------------------
-// Topology handle
-// --------------------------------------------------------------------------------------------------------
-struct amro_topology {
-  HostTopology H;
-  std::mutex mu;   // amro_simulate calls on one handle are serialised: they share the handle's workspaces
-  // CUDA events around the fused kernel of the last kKernelEvents runs (asynchronous runs are timed after the fact:
-  // amro_topology_kernel_times)
-  static constexpr int kKernelEvents = 64;
-  std::unique_ptr<EventPair[]> kernel_events;
-  uint64_t n_fused_runs = 0;
-  EventPair& next_kernel_events() {
-    if (!kernel_events) kernel_events.reset(new EventPair[kKernelEvents]);
-    return kernel_events[n_fused_runs++ % kKernelEvents];
-  }
-  int device = -1;
-  double compile_ms = 0.0;
-  int coresident[2] = {0, 0};  // cooperative-launch capacity of k_fast<false/true>
-  // shared / fast path
-  DevBuf<int64_t> day_start, day_seg_start, seg_row_start, pos_of;
-  DevBuf<double> seg_N;
-  DevBuf<uint4> meta;   // packed per-record words of the fast path (kernels.hpp FastArgs::meta)
-  DevBuf<uint32_t> init_seg, init_slot, seg_main_next;
-  // general path (uploaded on first use)
-  bool general_ready = false;
-  DevBuf<int64_t> order, push_src, push_dst;
-  DevBuf<uint32_t> seg_of_pos;
-  DevBuf<double> h, w;
-  DevBuf<int32_t> count_day;
-  // workspace reused across runs (parameter-inference loops call amro_simulate thousands of times)
-  DevBuf<uint4> ws_pre, ws_traj;
-  DevBuf<uint32_t> ws_pressure;
-  DevBuf<int32_t> ws_counts;
-  DevBuf<double> ws_params;
-  DevBuf<unsigned int> ws_barrier;
-  // pinned host staging of the per-day counts for host-pointer callers (pageable destinations copy at a fraction of PCIe speed)
-  int32_t* pinned_counts = nullptr;
-  size_t pinned_counts_n = 0;
-  int32_t* pinned(size_t n) {
-    if (n > pinned_counts_n) {
-      if (pinned_counts) cudaFreeHost(pinned_counts);
-      pinned_counts = nullptr; pinned_counts_n = 0;
-      if (cudaMallocHost(&pinned_counts, n * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); pinned_counts = nullptr; return nullptr; }
-      pinned_counts_n = n;
-    }
-    return pinned_counts;
-  }
-  ~amro_topology() { if (pinned_counts) cudaFreeHost(pinned_counts); }
-
-  void ensure_general() {
-    if (general_ready) return;
-    order.upload(H.order.data(), H.order.size());
-    push_src.upload(H.push_src.data(), H.push_src.size());
-    push_dst.upload(H.push_dst.data(), H.push_dst.size());
-    std::vector<uint32_t> sop((size_t)H.Rp);
-    for (int64_t s = 0; s < H.n_seg; ++s)
-      for (int64_t p = H.seg_row_start[s]; p < H.seg_row_start[s + 1]; ++p) sop[p] = (uint32_t)s;
-    seg_of_pos.upload(sop.data(), sop.size());
-    h.upload(H.h.data(), H.h.size());
-    w.upload(H.w.data(), H.w.size());
-    count_day.upload(H.count_day.data(), H.count_day.size());
-    AMRO_CUDA(cudaStreamSynchronize(0));
-    general_ready = true;
-  }
-};
 
 template <class T>
 static void ensure_size(DevBuf<T>& b, size_t n) {
@@ -585,6 +513,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 
 void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
   const HostTopology& H = T->H;
+  if (T->generated) fail(AMRO_EINVAL, "a hospital generated on the device has no host tables: it runs the fused kernels only");
   T->ensure_general();
   const bool replay = A->rng_mode == AMRO_RNG_REPLAY;
   const int64_t S = A->n_sims, R = H.R, D = H.total_days + 1;

@@ -123,7 +123,7 @@ struct FastArgs {
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
-inline int64_t fast_ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kSlicesPerTeam * 32) + (q & 31u); }
+__host__ __device__ inline int64_t fast_ring_slot(uint32_t q) { return (int64_t)(q >> 5) * (kSlicesPerTeam * 32) + (q & 31u); }
 size_t fast_shared_bytes(bool replay, int shape);
 int fast_threads(int shape);
 // CTAs of the given launch shape that can be co-resident (bound of a cooperative launch)

@@ -249,7 +249,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     for (uint32_t i = lo; i < hi; ++i) __stcg(z + (int64_t)i * (kBW * 32), 0u);
   }
 
-  if (pl.w0 < pl.w1) {
+  if (pl.w0 < pl.w1 && c.sim0 < a.S) {   // a word beyond the last simulation (a 32-member run: half a team) has nothing to step
     const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
     const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
     const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   for (int d = 0; d < n_days; ++d) {
     const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
     // what does not depend on the previous day's results: the first batch's beta / N and dithers
-    if (plan.w0 < plan.w1) prepare_tables_bits(sh, a, c, plan.seg0, plan.sl_first, min(plan.sl_last + 1u, plan.sl_first + (uint32_t)kBSegs));
+    if (plan.w0 < plan.w1 && c.sim0 < a.S) prepare_tables_bits(sh, a, c, plan.seg0, plan.sl_first, min(plan.sl_last + 1u, plan.sl_first + (uint32_t)kBSegs));
 #ifdef AMRO_EXP_NOWAIT   // timing experiment (wrong results)
     if (d < 2)
 #endif

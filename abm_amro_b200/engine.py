@@ -47,19 +47,54 @@ class SimResult:
     team_barrier: int = 0                 # capi.BARRIER_*
 
 
+def hospital_spec(n_wards: int, census: int, n_days: int, seed: int = 1, p_discharge: float = 0.15, p_transfer: float = 0.10):
+    """The synthetic "bed model" hospital of include/amro_b200.h (amro_hospital_spec)."""
+    return capi.HospitalSpec(int(n_wards), int(census), int(n_days), int(seed), float(p_discharge), float(p_transfer))
+
+
+def hospital_tables(spec):
+    """The hospital of ``spec`` as the reference's float64 tables (small sizes): ``(ward_matrix, tppw, n_init)``."""
+    R, K = capi._i64(), capi._i64()
+    capi.check(capi.lib().amro_hospital_tables(C.byref(spec), C.byref(R), C.byref(K), None, None))
+    wm = np.zeros((R.value, 6), order="F"); tp = np.zeros((K.value, 3), order="F")
+    capi.check(capi.lib().amro_hospital_tables(C.byref(spec), C.byref(R), C.byref(K), _ptr(wm), _ptr(tp)))
+    return wm, tp, int(spec.census)
+
+
 class Topology:
     """A hospital (ward_matrix + total_patients_per_ward) compiled for one GPU."""
 
-    def __init__(self, ward_matrix, total_patients_per_ward, n_init: int, device: int = 0):
-        wm, tp = _f64(ward_matrix), _f64(total_patients_per_ward)
+    def __init__(self, ward_matrix, total_patients_per_ward, n_init: int, device: int = 0, _handle=None):
         self._h = C.c_void_p()
-        capi.check(capi.lib().amro_topology_create(_ptr(wm), wm.shape[0], wm.shape[1], wm.shape[0],
-                                                   _ptr(tp), tp.shape[0], tp.shape[1], tp.shape[0],
-                                                   int(n_init), int(device), C.byref(self._h)))
+        if _handle is not None:
+            self._h = _handle
+        else:
+            wm, tp = _f64(ward_matrix), _f64(total_patients_per_ward)
+            capi.check(capi.lib().amro_topology_create(_ptr(wm), wm.shape[0], wm.shape[1], wm.shape[0],
+                                                       _ptr(tp), tp.shape[0], tp.shape[1], tp.shape[0],
+                                                       int(n_init), int(device), C.byref(self._h)))
         info = capi.TopologyInfo()
         capi.check(capi.lib().amro_topology_get_info(self._h, C.byref(info)))
         self.info = info
         self.device = device
+
+    @classmethod
+    def generate(cls, spec, device: int = 0) -> "Topology":
+        """A synthetic hospital generated on the device straight into the compiled form (no host tables; fused kernels only)."""
+        h = C.c_void_p()
+        capi.check(capi.lib().amro_topology_generate(C.byref(spec), int(device), C.byref(h)))
+        return cls(None, None, 0, device, _handle=h)
+
+    def device_arrays(self) -> dict:
+        """The compiled form as it sits on the device (tests: the generator against the host compiler)."""
+        i = self.info
+        D = i.total_days + 1
+        out = {"meta": np.zeros((i.n_rows_stepped, 4), dtype=np.uint32), "seg_row_start": np.zeros(i.n_segments + 1, dtype=np.int64),
+               "seg_N": np.zeros(i.n_segments), "seg_main_next": np.zeros(i.n_segments, dtype=np.uint32),
+               "day_seg_start": np.zeros(D + 1, dtype=np.int64), "init_seg": np.zeros(i.n_init, dtype=np.uint32),
+               "init_slot": np.zeros(i.n_init, dtype=np.uint32)}
+        capi.check(capi.lib().amro_topology_debug_device_arrays(self._h, *[C.c_void_p(v.ctypes.data) for v in out.values()]))
+        return out
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

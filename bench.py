@@ -40,10 +40,13 @@ WORKLOADS = {
     "cfg1_5w_300p_100d_20s": (5, 300, 100, 20),
     "cfg2_30w_10kp_365d_1000s": (30, 10_000, 365, 1000),
     "cfg3_20w_5kp_180d_65536s": (20, 5_000, 180, 65_536),
-    # regional network at its full size: 3.65e8 patient-day rows (17.5 GB of float64 tables on the host, generated
-    # in ~1.5 min, compiled in ~0.5 min); not a default bench line, run with --workload and a few steps
+    # regional network at its full size: 3.65e8 patient-day rows, and the national network: 7.3e9 rows, 32 members per GPU.
+    # Their hospitals are generated ON THE DEVICE straight into the compiled form (engine.Topology.generate: the tables never
+    # exist on the host); not default bench lines, run with --workload and a few steps
     "cfg4_500w_1Mp_365d_256s": (500, 1_000_000, 365, 256),
+    "cfg5_5kw_10Mp_730d_32s": (5_000, 10_000_000, 730, 32),
 }
+GENERATED = {"cfg4_500w_1Mp_365d_256s", "cfg5_5kw_10Mp_730d_32s"}
 DEFAULT_WORKLOAD = "cfg2_30w_10kp_365d_1000s"
 TTD, TSH, TSA, SEED, ICP, IDP = 2, 7, 1, 42, 0.2, 0.2
 
@@ -294,15 +297,29 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist = None
+    out = sys.stdout
     if world > 1:
+        # libraries write to file descriptor 1 (NCCL prints its version there): keep the real stdout for the ONE JSON line
+        out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
     sweep = args.workload.startswith("cfg3")
-    wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
-    R = wm.shape[0]
+    generated = args.workload in GENERATED
+    if args.days:
+        days = args.days
     t0 = time.perf_counter()
-    topo = engine.Topology(wm, tp, n_init, device=local_rank)
+    if generated:
+        topo = engine.Topology.generate(engine.hospital_spec(wards, census, days, seed=1), device=local_rank)
+        wm = tp = None
+        n_init = census
+        R = topo.info.n_rows
+    else:
+        wm, tp, n_init = synth.make_hospital(wards, census, days, seed=1)
+        R = wm.shape[0]
+        t0 = time.perf_counter()
+        topo = engine.Topology(wm, tp, n_init, device=local_rank)
     topo_ms = (time.perf_counter() - t0) * 1e3
     n_days = topo.info.n_days_out
     total_members = S_total if strong else S * world
@@ -366,7 +383,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the reference's own entry point (drop-in module, numpy in / numpy out, compiled-hospital cache warm) -------------
     dropin = None
-    if world == 1 and not sweep and not args.no_dropin:
+    if world == 1 and not sweep and not generated and not args.no_dropin:
         from abm_amro_b200 import amro
         call = lambda: amro.simulate_and_collapse(wm, tp, ICP, IDP, n_init, .15, .55, .05, .6, .35, .9, S, TTD, TSH, TSA, SEED)  # noqa: E731
         call()
@@ -417,6 +434,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "256 MB buffer written between steps (inside the timed region)",
                        "timed_region": "asynchronous runs enqueued back to back: kernel -> day moments -> all-reduce (N > 1), one sync at the end",
                        "topology_compile_ms": topo_ms,
+                       "hospital": "generated on the device (amro_topology_generate)" if generated else "numpy tables through the C ABI (synth.make_hospital)",
                        "counts_match_between_device_and_host_api": same},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": b_alg,
@@ -433,7 +451,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": m["launches"],
             "clocks": m["clocks"],
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     topo.close()
     if world > 1:
         dist.destroy_process_group()
@@ -447,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--members", type=int, default=0, help="override members per GPU")
+    ap.add_argument("--days", type=int, default=0, help="override the number of days (generated workloads: what fits in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-3 block of the default line")
     ap.add_argument("--no-dropin", action="store_true", help="skip timing the drop-in module's simulate_and_collapse")

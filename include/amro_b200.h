@@ -79,6 +79,25 @@ void amro_topology_destroy(amro_topology* topo);
 int  amro_topology_get_info(const amro_topology* topo, amro_topology_info* info);
 
 /* ------------------------------------------------------------------------------------------------
+ * Synthetic hospitals generated on the device, straight into the compiled form (no float64 tables: configs 4 and 5 of
+ * BASELINE.json have 3.65e8 and 7.3e9 patient-day records).  "Bed model": `census` beds, always occupied; after every day the
+ * patient of a bed is discharged with probability p_discharge and replaced by a new patient (is_new = 1) in a uniformly
+ * drawn ward, otherwise moves to a uniformly drawn ward with probability p_transfer.  Records of a day are ordered by
+ * (ward, bed); total_patients_per_ward is the bed count of every occupied ward; the initial block is day 0.
+ * A generated handle runs the fused kernels (AMRO_PATH_FAST) only.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct amro_hospital_spec {
+  int64_t n_wards, census, n_days;
+  int64_t seed;
+  double  p_discharge, p_transfer;
+} amro_hospital_spec;
+int amro_topology_generate(const amro_hospital_spec* spec, int device, amro_topology** out);
+/* The same hospital as the reference's float64 tables, on the host (small sizes; what the parity tests compile and hand to
+ * the oracle).  First call with ward_matrix = tppw = NULL for the sizes; then with ward_matrix [n_rows x 6] and tppw
+ * [t_rows x 3] (column-major, ld = rows, *t_rows as returned). */
+int amro_hospital_tables(const amro_hospital_spec* spec, int64_t* n_rows, int64_t* t_rows, double* ward_matrix, double* tppw);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole-run simulation on a compiled topology.  Replaces simulate_discrete_model_internal_one
  * (abm_wards.cpp:322-414) fused with total_positive_colonized/_detected (:435-509): state stays in HBM
  * across all days, only the per-(day, simulation) counts -- and, if asked, the trajectory -- leave.

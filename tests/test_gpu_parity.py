@@ -465,6 +465,36 @@ def test_compiled_hospital_cache_of_the_one_call_entry_points():
     assert capi.cache_stats()["entries"] == 0
 
 
+# ---- hospitals generated on the device against the host compiler and the oracle ---------------------------
+@pytest.mark.parametrize("shape", [(5, 300, 12), (40, 100, 8), (3, 2000, 5), (1, 33, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_device_generated_hospital_matches_host_compile_and_oracle(shape):
+    spec = engine.hospital_spec(*shape, seed=7)
+    wm, tp, n_init = engine.hospital_tables(spec)           # the same hospital as the reference's float64 tables
+    S = 40
+    par = synth.particle_parameters(S, seed=2)
+    with engine.Topology.generate(spec) as g, engine.Topology(wm, tp, n_init) as h:
+        assert h.info.fast_eligible and h.info.identity_order
+        for f in ("n_rows", "n_rows_stepped", "n_init", "total_days", "n_days_out", "n_segments", "max_rows_per_day"):
+            assert getattr(g.info, f) == getattr(h.info, f), f
+        ga, ha = g.device_arrays(), h.device_arrays()        # what the kernels read: generated on the device == compiled by topology.cpp
+        for k in ga:
+            assert np.array_equal(ga[k], ha[k]), k
+        a = g.simulate(par, 0.2, 0.3, 2, 7, 1, 5)
+        b = h.simulate(par, 0.2, 0.3, 2, 7, 1, 5)
+        assert a.kernel_kind == capi.KERNEL_BITS
+        assert np.array_equal(a.counts_colonized, b.counts_colonized) and np.array_equal(a.counts_detected, b.counts_detected)
+        ref = oracle.simulate_discrete_model(np.full((n_init, S), 0.2), np.full((n_init, S), 0.3), wm, tp, par, 2, 7, 1, 5,
+                                             rng=oracle.Rng(oracle.RNG_PHILOX))
+        assert np.array_equal(a.counts_colonized, oracle.total_positive_colonized(ref, S))
+        assert np.array_equal(a.counts_detected, oracle.total_positive_detected(ref, S))
+        traj = g.simulate(par, 0.2, 0.3, 5, 2, 1, 5, want_state=True)     # the trajectory kernel on a generated handle
+        ref5 = oracle.simulate_discrete_model(np.full((n_init, S), 0.2), np.full((n_init, S), 0.3), wm, tp, par, 5, 2, 1, 5,
+                                              rng=oracle.Rng(oracle.RNG_PHILOX))
+        assert traj.kernel_kind == capi.KERNEL_CODES and np.array_equal(traj.state, ref5[:, 6:])
+        with pytest.raises(ValueError, match="fused kernels only"):
+            g.simulate(par, 0.2, 0.3, 2, 7, 1, 5, path=capi.PATH_GENERAL)
+
+
 def test_device_pointer_api_matches_host_api():
     torch = pytest.importorskip("torch")
     wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=2)

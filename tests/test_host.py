@@ -241,3 +241,27 @@ def test_ensemble_collapse_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "gloo ok" in outs[0][0]
+
+
+def test_synthetic_hospital_tables_are_a_valid_fast_hospital():
+    # amro_hospital_tables: the "bed model" hospital the device generator builds, as the reference's float64 tables
+    spec = engine.hospital_spec(6, 120, 9, seed=11, p_discharge=0.2, p_transfer=0.3)
+    wm, tp, n_init = engine.hospital_tables(spec)
+    wm2, tp2, _ = engine.hospital_tables(spec)
+    assert np.array_equal(wm, wm2) and np.array_equal(tp, tp2) and n_init == 120 and wm.shape == (120 * 9, 6)
+    assert not np.array_equal(wm, engine.hospital_tables(engine.hospital_spec(6, 120, 9, seed=12, p_discharge=0.2, p_transfer=0.3))[0])
+    nd = wm[:, 5].astype(np.int64)
+    src = np.nonzero(nd > 0)[0]
+    assert np.all(wm[nd[src], 0] == wm[src, 0] + 1) and np.all(wm[nd[src], 2] == wm[src, 2])     # the same patient, the next day
+    assert len(np.unique(nd[src])) == len(src)                                                      # one predecessor at most
+    targets = np.zeros(wm.shape[0], dtype=bool); targets[nd[src]] = True
+    assert np.array_equal(wm[:, 3] == 1, ~targets)                                                  # is_new <=> no predecessor
+    assert np.all(np.diff(wm[:, 0] * 1000 + wm[:, 1]) >= 0) and np.all(wm[:, 4] == 1.0)            # rows in (day, ward) order
+    for d, w, c in tp:
+        assert np.sum((wm[:, 0] == d) & (wm[:, 1] == w)) == c
+    stay = len(src) / (120 * 8)
+    assert abs(stay - 0.8) < 0.05                                                                   # 1 - p_discharge of the records have a successor
+    with engine.Topology(wm, tp, n_init, device=-1) as topo:
+        assert topo.info.fast_eligible and topo.info.identity_order
+    with pytest.raises(ValueError):
+        engine.hospital_tables(engine.hospital_spec(0, 10, 3))
