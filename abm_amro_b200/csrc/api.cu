@@ -328,23 +328,70 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   const int64_t* pos_of = H.identity_order ? nullptr : T->pos_of.p;
   if (A->state_out) {
     if (on_device) {
-      fast_expand(st, f.traj, pos_of, f.day_start, f.n_days, H.R, S, 0, S, A->state_out, A->state_out + A->so_ld * S, A->so_ld);
+      fast_expand(st, f.traj, pos_of, H.R, S, 0, H.R, 0, S, A->state_out, A->state_out + A->so_ld * S, A->so_ld);
       A->launches++;
     } else {
-      // expand a block of simulations at a time into the reference's float64 columns, then copy them out
-      const int64_t chunk = std::max<int64_t>(8, std::min<int64_t>(S_pad, ((int64_t)1 << 28) / std::max<int64_t>(H.R, 1) / 8 * 8));
-      DevBuf<double> buf;
-      buf.alloc((size_t)(2 * H.R * chunk));
-      for (int64_t s0 = 0; s0 < S; s0 += chunk) {
-        const int64_t ns = std::min(chunk, S - s0);
-        fast_expand(st, f.traj, pos_of, f.day_start, f.n_days, H.R, S, s0, ns, buf.p, buf.p + H.R * chunk, H.R);
-        A->launches++;
-        AMRO_CUDA(cudaMemcpy2DAsync(A->state_out + A->so_ld * s0, A->so_ld * sizeof(double), buf.p, H.R * sizeof(double),
-                                    H.R * sizeof(double), ns, cudaMemcpyDeviceToHost, st));
-        AMRO_CUDA(cudaMemcpy2DAsync(A->state_out + A->so_ld * (S + s0), A->so_ld * sizeof(double), buf.p + H.R * chunk,
-                                    H.R * sizeof(double), H.R * sizeof(double), ns, cudaMemcpyDeviceToHost, st));
-        AMRO_CUDA(cudaStreamSynchronize(st));
-      }
+      // The reference's float64 columns leave in tiles of (a block of rows) x (8 simulations): a tile is expanded on the device,
+      // copied into one of two PINNED staging buffers on a second stream, and copied from there into the caller's (pageable)
+      // matrix by the host while the next tile is in flight -- expansion, PCIe transfer and the host copy overlap.
+      AMRO_CUDA(cudaStreamSynchronize(st));   // the trajectory is complete
+      const int64_t tile_rows = std::max<int64_t>(1, std::min<int64_t>(H.R, ((int64_t)1 << 20)));
+      const size_t tile_elems = (size_t)tile_rows * 16;   // 8 C columns + 8 D columns
+      DevBuf<double> dbuf[2];
+      double* hbuf[2] = {nullptr, nullptr};
+      cudaStream_t s_copy = nullptr;
+      cudaEvent_t expanded[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+      struct Tile { int64_t r0, nr, s0, ns; };
+      auto cleanup = [&] {
+        for (int b = 0; b < 2; ++b) { if (hbuf[b]) cudaFreeHost(hbuf[b]); if (expanded[b]) cudaEventDestroy(expanded[b]); if (copied[b]) cudaEventDestroy(copied[b]); }
+        if (s_copy) cudaStreamDestroy(s_copy);
+      };
+      try {
+        AMRO_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+          dbuf[b].alloc(tile_elems);
+          AMRO_CUDA(cudaMallocHost(&hbuf[b], tile_elems * sizeof(double)));
+          AMRO_CUDA(cudaEventCreateWithFlags(&expanded[b], cudaEventDisableTiming));
+          AMRO_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        }
+        std::vector<Tile> tiles;
+        for (int64_t s0 = 0; s0 < S; s0 += 8)
+          for (int64_t r0 = 0; r0 < H.R; r0 += tile_rows) tiles.push_back(Tile{r0, std::min(tile_rows, H.R - r0), s0, std::min<int64_t>(8, S - s0)});
+        // staging [16][nr] -> the caller's C and D columns, one host thread per simulation of the tile (a freshly allocated
+        // result matrix is first touched here: the page faults spread over the threads)
+        auto to_caller = [&](const Tile& t, int b) {
+          auto one = [&, b](int64_t k) {
+            std::memcpy(A->state_out + A->so_ld * (t.s0 + k) + t.r0, hbuf[b] + k * t.nr, sizeof(double) * (size_t)t.nr);
+            std::memcpy(A->state_out + A->so_ld * (S + t.s0 + k) + t.r0, hbuf[b] + (8 + k) * t.nr, sizeof(double) * (size_t)t.nr);
+          };
+          if (t.nr * t.ns < (1 << 16)) { for (int64_t k = 0; k < t.ns; ++k) one(k); return; }
+          std::vector<std::thread> pool;
+          for (int64_t k = 1; k < t.ns; ++k) pool.emplace_back(one, k);
+          one(0);
+          for (auto& th : pool) th.join();
+        };
+        for (size_t k = 0; k < tiles.size(); ++k) {
+          const int b = (int)(k & 1);
+          const Tile& t = tiles[k];
+          if (k >= 2) AMRO_CUDA(cudaStreamWaitEvent(st, copied[b], 0));      // the device buffer has been read
+          fast_expand(st, f.traj, pos_of, H.R, S, t.r0, t.nr, t.s0, t.ns, dbuf[b].p, dbuf[b].p + 8 * t.nr, t.nr);
+          A->launches++;
+          AMRO_CUDA(cudaEventRecord(expanded[b], st));
+          AMRO_CUDA(cudaStreamWaitEvent(s_copy, expanded[b], 0));   // hbuf[b] was handed to the caller one iteration ago
+          AMRO_CUDA(cudaMemcpyAsync(hbuf[b], dbuf[b].p, sizeof(double) * 16 * (size_t)t.nr, cudaMemcpyDeviceToHost, s_copy));
+          AMRO_CUDA(cudaEventRecord(copied[b], s_copy));
+          if (k >= 1) {   // the previous tile: wait for its transfer, hand it to the caller while this tile is in flight
+            AMRO_CUDA(cudaEventSynchronize(copied[b ^ 1]));
+            to_caller(tiles[k - 1], b ^ 1);
+          }
+        }
+        if (!tiles.empty()) {
+          const int b = (int)((tiles.size() - 1) & 1);
+          AMRO_CUDA(cudaEventSynchronize(copied[b]));
+          to_caller(tiles.back(), b);
+        }
+      } catch (...) { cleanup(); throw; }
+      cleanup();
     }
   }
   if (A->pressure_out) {

@@ -132,9 +132,9 @@ int fast_max_coresident_clusters(int device, bool replay, bool lean, int shape, 
 // lean: no trajectory, unit weights, rows already in (day, ward) order: the instance compiled without the other cases
 void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, bool lean, int shape, int grid);
 
-// Cout[(orig row) + ld*(s - s0)] = C, Dout[...] = D for sims [s0, s0+ns) of the run
-void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,
-                 int64_t R, int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld);
+// rows [r0, r0 + nr) x sims [s0, s0 + ns) of the run (s0 a multiple of 8): Cout[(row - r0) + ld*(s - s0)] = C, Dout[...] = D
+void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, int64_t R, int64_t S, int64_t r0, int64_t nr, int64_t s0,
+                 int64_t ns, double* Cout, double* Dout, int64_t ld);
 // out[seg + ld*sim] = colonised count the ward-day started with
 void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld);
 

@@ -697,12 +697,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
 
 // ---- packed trajectory -> the reference's float64 columns ------------------------------------------------------
 namespace {
+// rows [r0, r0 + nr) x simulations [s0, s0 + ns) of the run -> Cout / Dout [nr x ns], element (r - r0) + ld * (s - s0)
 __global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __restrict__ pos_of, int64_t R, int64_t S,
-                              int64_t s0, int64_t ns, double* __restrict__ Cout, double* __restrict__ Dout, int64_t ld) {
+                              int64_t r0, int64_t nr, int64_t s0, int64_t ns, double* __restrict__ Cout, double* __restrict__ Dout, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n_sl = (ns + 7) / 8;  // s0 is a multiple of 8
-  if (i >= R * n_sl) return;
-  const int64_t r = i % R, sl = i / R;
+  if (i >= nr * n_sl) return;
+  const int64_t rr = i % nr, sl = i / nr, r = r0 + rr;
   const int64_t slice = s0 / 8 + sl, team = slice / kNS, in_team = slice % kNS;
   const int64_t p = pos_of ? pos_of[r] : r;
   const uint4 v = __ldg(&traj[(team * R + p) * kNS + in_team]);
@@ -712,8 +713,8 @@ __global__ void k_fast_expand(const uint4* __restrict__ traj, const int64_t* __r
     const int64_t s = sl * 8 + k;
     if (s >= ns || s0 + s >= S) break;
     const uint32_t x = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-    Cout[r + ld * s] = (x >= kCodeA) ? 1.0 : 0.0;
-    Dout[r + ld * s] = (x >= kCodeCnt) ? (double)((int)kCodeZero - (int)x) : __longlong_as_double(0x7FF0000000000000ll);
+    Cout[rr + ld * s] = (x >= kCodeA) ? 1.0 : 0.0;
+    Dout[rr + ld * s] = (x >= kCodeCnt) ? (double)((int)kCodeZero - (int)x) : __longlong_as_double(0x7FF0000000000000ll);
   }
 }
 
@@ -810,12 +811,11 @@ void fast_launch(cudaStream_t st, const FastArgs& a, bool replay, bool lean, int
   }
 }
 
-void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, const int64_t* day_start, int64_t n_days,
-                 int64_t R, int64_t S, int64_t s0, int64_t ns, double* Cout, double* Dout, int64_t ld) {
-  (void)day_start; (void)n_days;
-  const int64_t n = R * ((ns + 7) / 8);
+void fast_expand(cudaStream_t st, const uint4* traj, const int64_t* pos_of, int64_t R, int64_t S, int64_t r0, int64_t nr, int64_t s0,
+                 int64_t ns, double* Cout, double* Dout, int64_t ld) {
+  const int64_t n = nr * ((ns + 7) / 8);
   if (n <= 0) return;
-  k_fast_expand<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(traj, pos_of, R, S, s0, ns, Cout, Dout, ld);
+  k_fast_expand<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(traj, pos_of, R, S, r0, nr, s0, ns, Cout, Dout, ld);
 }
 
 void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_seg, int64_t S, int32_t* out, int64_t ld) {
