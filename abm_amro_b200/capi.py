@@ -48,7 +48,9 @@ class SimArgs(C.Structure):
                 ("counts_colonized", C.c_void_p), ("counts_detected", C.c_void_p),
                 ("state_out", C.c_void_p), ("so_ld", _i64),
                 ("p_out", C.c_void_p), ("day_moments", C.c_void_p), ("pressure_out", C.c_void_p),
-                ("observed_colonized", C.c_void_p), ("observed_detected", C.c_void_p), ("distance", C.c_void_p), ("stream", C.c_void_p),
+                ("observed_colonized", C.c_void_p), ("observed_detected", C.c_void_p), ("distance", C.c_void_p),
+                ("quantiles", C.c_void_p), ("n_quantiles", _i64), ("summary_colonized", C.c_void_p), ("summary_detected", C.c_void_p),
+                ("stream", C.c_void_p),
                 ("path_used", C.c_int32), ("launches", C.c_int32), ("kernel_ms", C.c_float), ("total_ms", C.c_float),
                 ("kernel_kind", C.c_int32), ("grid", C.c_int32), ("ctas_per_team", C.c_int32), ("team_barrier", C.c_int32)]
 
@@ -56,7 +58,7 @@ class SimArgs(C.Structure):
 # every entry point include/amro_b200.h declares (tests/test_host.py checks this list against the header)
 EXPORTS = ["amro_last_error", "amro_version", "amro_device_count", "amro_topology_create", "amro_topology_destroy",
            "amro_topology_get_info", "amro_topology_generate", "amro_hospital_tables", "amro_topology_kernel_times", "amro_topology_cache_clear", "amro_topology_cache_stats", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse", "amro_simulate_and_collapse_alloc",
-           "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive"]
+           "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive", "amro_summary_of_total_positive_device"]
 
 _lib = None
 
@@ -93,6 +95,7 @@ def lib():
         L.amro_total_positive.argtypes = [C.c_void_p, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.POINTER(_i64),
                                           C.POINTER(_i64), C.c_void_p]
         L.amro_summary_of_total_positive.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_void_p]
+        L.amro_summary_of_total_positive_device.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_int, C.c_void_p]
         L.amro_topology_debug_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 11 + [C.POINTER(_i64)]
         _lib = L
     return _lib

@@ -119,7 +119,11 @@ py::array_t<double> summary_of_total_positive(farray pos_, farray q_) {
   Mat pos(pos_), q(q_);
   const int64_t nq = q.rows * q.cols;
   auto out = fmat(pos.rows, 3 + nq);
-  check(amro_summary_of_total_positive(pos.data(), pos.rows, pos.cols, pos.ld, q.data(), nq, out.mutable_data()));
+  // from a few hundred thousand values on, the per-day sort across the simulations runs on the device (bit-identical results)
+  if (pos.rows * pos.cols >= (int64_t)1 << 18 && amro_device_count() > 0)
+    check(amro_summary_of_total_positive_device(pos.data(), pos.rows, pos.cols, pos.ld, q.data(), nq, device(), out.mutable_data()));
+  else
+    check(amro_summary_of_total_positive(pos.data(), pos.rows, pos.cols, pos.ld, q.data(), nq, out.mutable_data()));
   return out;
 }
 

@@ -197,6 +197,31 @@ void emit_distance(amro_topology* T, amro_sim_args* A, const int32_t* col, const
   launches++;
 }
 
+// amro_sim_args::summary_*: summary_of_total_positive (abm_wards.cpp:526-540) of this run's counts, on the device (summary.cu)
+void emit_summaries(amro_topology* T, amro_sim_args* A, const int32_t* col, const int32_t* det, int64_t S, bool on_device, cudaStream_t st,
+                    int& launches) {
+  if (!A->summary_colonized && !A->summary_detected) return;
+  if (A->n_quantiles < 0 || (A->n_quantiles > 0 && !A->quantiles)) fail(AMRO_EINVAL, "summary: quantiles is NULL");
+  const int64_t Dd = T->H.n_days_out, nq = A->n_quantiles, cols = 3 + nq;
+  DevBuf<double> q, x, out;
+  if (nq) q.upload(A->quantiles, (size_t)nq, st);
+  x.alloc((size_t)(Dd * S));
+  if (!on_device) out.alloc((size_t)(Dd * cols));
+  const int32_t* src[2] = {col, det};
+  double* dst[2] = {A->summary_colonized, A->summary_detected};
+  for (int k = 0; k < 2; ++k) {
+    if (!dst[k]) continue;
+    counts_to_double(st, src[k], x.p, Dd * S);
+    device_summary(st, x.p, Dd, S, Dd, q.p, nq, on_device ? dst[k] : out.p, Dd);
+    launches += 2 + (nq ? 4 : 0);
+    if (!on_device) {
+      AMRO_CUDA(cudaMemcpyAsync(dst[k], out.p, sizeof(double) * Dd * cols, cudaMemcpyDeviceToHost, st));
+      AMRO_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  AMRO_CUDA(cudaStreamSynchronize(st));   // the scratch buffers die here
+}
+
 uint64_t schedule_u64(int v) { return (uint64_t)(int64_t)v; }  // int -> unsigned 64-bit, as `uword % int` does (:391-392)
 
 void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaStream_t st, bool on_device) {
@@ -325,6 +350,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     A->launches++;
   }
   emit_distance(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
+  emit_summaries(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
   const int64_t* pos_of = H.identity_order ? nullptr : T->pos_of.p;
   if (A->state_out) {
     if (on_device) {
@@ -539,6 +565,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     A->launches++;
   }
   emit_distance(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
+  emit_summaries(T, A, f.counts_col, f.counts_det, S, on_device, st, A->launches);
   if (A->pressure_out) {
     if (on_device) bits_export_pressure(st, f.pressure, f.day_seg_start, n_days, max_segs, press_days, S, A->pressure_out, H.n_seg);
     else {
@@ -607,8 +634,9 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     const int64_t pa = H.day_push_start[d], pb = H.day_push_start[d + 1];
     if (pb > pa) { gen_propagate(st, C, Dp, ld, S, T->push_src.p + pa, T->push_dst.p + pa, pb - pa, tmp.p); launches += 2; }
   }
-  if (A->counts_colonized || A->day_moments || A->distance) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
-  if (A->counts_detected || A->day_moments || A->distance) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
+  const bool want_sum = A->summary_colonized || A->summary_detected;
+  if (A->counts_colonized || A->day_moments || A->distance || want_sum) { gen_count(st, C, ld, R, S, T->count_day.p, 1, counts.p, H.n_days_out); launches++; }
+  if (A->counts_detected || A->day_moments || A->distance || want_sum) { gen_count(st, Dp, ld, R, S, T->count_day.p, 0, counts.p + H.n_days_out * S, H.n_days_out); launches++; }
   DevBuf<double> dm;
   if (A->day_moments) {
     double* dst = A->day_moments;
@@ -617,6 +645,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
     launches++;
   }
   emit_distance(T, A, counts.p, counts.p + H.n_days_out * S, S, on_device, st, launches);
+  emit_summaries(T, A, counts.p, counts.p + H.n_days_out * S, S, on_device, st, launches);
   AMRO_CUDA(cudaEventRecord(ev.b, st));
   AMRO_CUDA(cudaGetLastError());
 
@@ -652,6 +681,7 @@ extern "C" int amro_simulate(amro_topology* T, amro_sim_args* A) {
     if (A->p_ld < S) fail(AMRO_EINVAL, "p_ld (%lld) is smaller than n_sims (%lld)", (long long)A->p_ld, (long long)S);
     if (A->state_out && A->so_ld < H.R) fail(AMRO_EINVAL, "so_ld (%lld) is smaller than the number of rows (%lld)", (long long)A->so_ld, (long long)H.R);
     if (A->async && !A->pointers_on_device) fail(AMRO_EINVAL, "async needs pointers_on_device");
+    if (A->async && (A->summary_colonized || A->summary_detected)) fail(AMRO_EINVAL, "summaries are not available in async runs (their scratch is per call)");
     if (A->async && A->path == AMRO_PATH_GENERAL) fail(AMRO_EINVAL, "async runs need the fused kernels (path AUTO or FAST)");
     if (A->testing_schedule_hospitalized == 0 || A->testing_schedule_arrivals == 0)
       fail(AMRO_EINVAL, "testing schedule of 0: the reference divides by zero here (abm_wards.cpp:391-392)");
@@ -1131,6 +1161,24 @@ extern "C" int amro_total_positive(const double* model, int64_t n_rows, int64_t 
     counts_to_double(st, cnt.p, dout.p, Dd * nc);
     AMRO_CUDA(cudaGetLastError());
     AMRO_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * Dd * nc, cudaMemcpyDeviceToHost, st));
+    AMRO_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+extern "C" int amro_summary_of_total_positive_device(const double* positive, int64_t n_days, int64_t n_sims, int64_t ld,
+                                                     const double* quantiles, int64_t n_q, int device, double* out) {
+  return guarded([&] {
+    if (n_days < 0 || n_sims < 0 || n_q < 0) fail(AMRO_EINVAL, "negative size");
+    if (n_days == 0) return;
+    if (n_sims == 0) fail(AMRO_ERUNTIME, "copy into submatrix: incompatible matrix dimensions");
+    use_device(device);
+    cudaStream_t st = 0;
+    DevBuf<double> x, q, o;
+    upload_matrix(x, positive, n_days, n_sims, ld, st);
+    if (n_q) q.upload(quantiles, (size_t)n_q, st);
+    o.alloc((size_t)(n_days * (3 + n_q)));
+    device_summary(st, x.p, n_days, n_sims, n_days, q.p, n_q, o.p, n_days);
+    AMRO_CUDA(cudaMemcpyAsync(out, o.p, sizeof(double) * n_days * (3 + n_q), cudaMemcpyDeviceToHost, st));
     AMRO_CUDA(cudaStreamSynchronize(st));
   });
 }

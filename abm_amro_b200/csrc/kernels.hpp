@@ -51,6 +51,10 @@ void counts_to_double(cudaStream_t st, const int32_t* counts, double* out, int64
 // out[s] = sum over days with data (non-NaN) of (col - obs_col)^2 + (det - obs_det)^2; either series may be nullptr
 void distance_to_data(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
                       const double* obs_col, const double* obs_det, double* out);
+// summary.cu: X [n_days x S] (device, column-major, ld) -> out [n_days x (3 + nq)] (device, ld_out): day, mean, population sd, quantiles
+// (arma::quantile, Hyndman & Fan 5) over the simulations; the same operation order as the host routine (bit-identical)
+void device_summary(cudaStream_t st, const double* X, int64_t n_days, int64_t S, int64_t ld, const double* q_dev, int64_t nq, double* out,
+                    int64_t ld_out);
 void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld);
 
 // ----------------------------------------------------------------------------------------------------

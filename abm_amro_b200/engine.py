@@ -45,6 +45,8 @@ class SimResult:
     grid: int = 0                         # CTAs of the fused kernel's launch
     ctas_per_team: int = 0
     team_barrier: int = 0                 # capi.BARRIER_*
+    summary_colonized: np.ndarray | None = None   # [n_days_out x (3 + nq)]: day, mean, sd, quantiles over the simulations
+    summary_detected: np.ndarray | None = None
 
 
 def hospital_spec(n_wards: int, census: int, n_days: int, seed: int = 1, p_discharge: float = 0.15, p_transfer: float = 0.10):
@@ -145,7 +147,7 @@ class Topology:
                  path: int = capi.PATH_AUTO, keep_trajectory: bool = False, want_counts: bool = True,
                  want_state: bool = False, want_p: bool = False, want_pressure: bool = False,
                  want_moments: bool = False, u_col=None, u_det=None, u_icol=None, u_idet=None,
-                 observed_colonized=None, observed_detected=None) -> SimResult:
+                 observed_colonized=None, observed_detected=None, quantiles=None) -> SimResult:
         """``observed_*``: per-day series (NaN = no data); the result then carries ``distance`` [S], the per-simulation sum
         of squared differences between the simulated per-day counts and the data, computed on the device."""
         i = self.info
@@ -196,9 +198,17 @@ class Topology:
                         raise RuntimeError(f"{name}: expected shape ({i.n_days_out},), got {arr.shape}")
                     keep.append(arr)
                     setattr(a, name, arr.ctypes.data)
+        sc = sd = None
+        if quantiles is not None:   # summary_of_total_positive of the run's counts, computed on the device
+            qs = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+            sc = np.zeros((i.n_days_out, 3 + qs.size), order="F"); sd = np.zeros_like(sc)
+            keep.append(qs)
+            a.quantiles, a.n_quantiles = qs.ctypes.data, qs.size
+            a.summary_colonized, a.summary_detected = sc.ctypes.data, sd.ctypes.data
         capi.check(capi.lib().amro_simulate(self._h, C.byref(a)))
         r = SimResult(cc, cd, st, p, pr, mo, a.path_used, a.launches, a.kernel_ms, a.total_ms)
         r.distance = dist
+        r.summary_colonized, r.summary_detected = sc, sd
         r.kernel_kind, r.grid, r.ctas_per_team, r.team_barrier = a.kernel_kind, a.grid, a.ctas_per_team, a.team_barrier
         return r
 

@@ -152,6 +152,12 @@ typedef struct amro_sim_args {
   const double* observed_colonized;   /* [n_days_out] or NULL                                             */
   const double* observed_detected;    /* [n_days_out] or NULL                                             */
   double*  distance;           /* [S] or NULL                                                              */
+  /* summaries on the device (summary_of_total_positive, abm_wards.cpp:526-540, of this run's counts): per day,
+     over the simulations of this call: day, mean, population sd and the given quantiles (arma::quantile) */
+  const double* quantiles;     /* [n_quantiles] (host memory, also with pointers_on_device) or NULL        */
+  int64_t  n_quantiles;
+  double*  summary_colonized;  /* [n_days_out x (3 + n_quantiles)] column-major, ld = n_days_out, or NULL  */
+  double*  summary_detected;
   void*    stream;             /* cudaStream_t when pointers_on_device, else ignored                      */
 
   /* filled on return */
@@ -237,6 +243,11 @@ int amro_progress_patients(double* ward_matrix, int64_t n_rows, int64_t n_cols, 
 int amro_total_positive(const double* model, int64_t n_rows, int64_t n_cols, int64_t ld,
                         int64_t n_sims, int mode, int device,
                         int64_t* n_days, int64_t* n_out_cols, double* out);
+
+/* The same on the device (per-day segmented sort across the simulations; bit-identical to the host routine): worth it from a
+ * few hundred thousand values on. */
+int amro_summary_of_total_positive_device(const double* positive, int64_t n_days, int64_t n_sims, int64_t ld,
+                                          const double* quantiles, int64_t n_q, int device, double* out);
 
 /* amro.summary_of_total_positive (amro.cpp:254-271 -> abm_wards.cpp:526-540): day, mean, population sd and
  * Armadillo-definition quantiles across simulations.  Host arithmetic (tiny post-processing of

@@ -495,6 +495,37 @@ def test_device_generated_hospital_matches_host_compile_and_oracle(shape):
             g.simulate(par, 0.2, 0.3, 2, 7, 1, 5, path=capi.PATH_GENERAL)
 
 
+# ---- summary_of_total_positive on the device ------------------------------------------------------------
+def test_device_summary_matches_the_host_routine_and_the_reference_golden(golden):
+    z = golden("summary")
+    n_days, S = z["col"].shape
+    out = np.zeros((n_days, 3 + len(z["q"])), order="F")
+    col = np.asfortranarray(z["col"])
+    capi.check(capi.lib().amro_summary_of_total_positive_device(col.ctypes.data, n_days, S, n_days, z["q"].ctypes.data, len(z["q"]), 0, out.ctypes.data))
+    assert np.array_equal(out, z["summ"])                               # the compiled reference's own output
+    g = np.random.default_rng(5)
+    qs = np.array([-0.1, 0.0, 1e-6, 0.025, 0.25, 0.5, 0.75, 0.975, 1.0 - 1e-6, 1.0, 1.2])
+    for n_days, S, kind in ((7, 65_536, "counts"), (5, 1000, "reals"), (3, 2, "counts"), (4, 1, "reals"), (181, 4096, "counts")):
+        x = g.integers(0, 5000, (n_days, S)).astype(float) if kind == "counts" else g.normal(size=(n_days, S)) * 1e3
+        x = np.asfortranarray(x)
+        host = np.zeros((n_days, 3 + len(qs)), order="F"); dev = np.zeros_like(host)
+        capi.check(capi.lib().amro_summary_of_total_positive(x.ctypes.data, n_days, S, n_days, qs.ctypes.data, len(qs), host.ctypes.data))
+        capi.check(capi.lib().amro_summary_of_total_positive_device(x.ctypes.data, n_days, S, n_days, qs.ctypes.data, len(qs), 0, dev.ctypes.data))
+        assert np.array_equal(host, dev), (n_days, S, kind)             # the same IEEE operations in the same order
+    from abm_amro_b200 import amro
+    big = np.asfortranarray(g.integers(0, 9000, (180, 8192)).astype(float))     # large enough for the module to take the device path
+    want = np.zeros((180, 3 + 3), order="F")
+    capi.check(capi.lib().amro_summary_of_total_positive(big.ctypes.data, 180, 8192, 180, np.array([0.025, 0.5, 0.975]).ctypes.data, 3, want.ctypes.data))
+    assert np.array_equal(amro.summary_of_total_positive(big, np.array([0.025, 0.5, 0.975])), want)
+    # fused with a run: the summaries of the run's own counts never leave the device as counts
+    wm, tp, n_init = synth.make_hospital(4, 200, 15, seed=6)
+    par = synth.particle_parameters(300, seed=1)
+    with engine.Topology(wm, tp, n_init) as topo:
+        r = topo.simulate(par, 0.2, 0.3, 2, 7, 1, 9, quantiles=[0.05, 0.5, 0.95])
+        assert np.array_equal(r.summary_colonized, oracle.summary_of_total_positive(r.counts_colonized.astype(float), np.array([0.05, 0.5, 0.95])))
+        assert np.array_equal(r.summary_detected, oracle.summary_of_total_positive(r.counts_detected.astype(float), np.array([0.05, 0.5, 0.95])))
+
+
 def test_device_pointer_api_matches_host_api():
     torch = pytest.importorskip("torch")
     wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=2)
