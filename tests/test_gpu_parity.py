@@ -526,6 +526,32 @@ def test_device_summary_matches_the_host_routine_and_the_reference_golden(golden
         assert np.array_equal(r.summary_detected, oracle.summary_of_total_positive(r.counts_detected.astype(float), np.array([0.05, 0.5, 0.95])))
 
 
+# ---- parameter-inference sweep ---------------------------------------------------------------------------
+def test_abc_sweep_returns_one_distance_per_particle_and_finds_the_truth():
+    from abm_amro_b200 import inference
+    wm, tp, n_init = synth.make_hospital(6, 600, 40, seed=5)
+    truth = np.array([[0.12, 0.75, 0.04, 0.7, 0.3, 0.8]])
+    with engine.Topology(wm, tp, n_init) as topo:
+        data = topo.simulate(np.repeat(truth, 32, 0), 0.2, 0.2, 2, 7, 1, 7)                 # "observed" series: the mean of 32 runs of the truth
+        obs_c, obs_d = data.counts_colonized.mean(1), data.counts_detected.mean(1)
+        obs_d[::9] = np.nan                                                                  # days without data
+        n = 8192
+        res = inference.abc_sweep(topo, obs_c, obs_d, n_particles=n, seed=11, keep=0.02)
+        assert res.distance.shape == (n,) and res.particles.shape == (n, 6) and len(res.accepted) == round(0.02 * n)
+        assert np.array_equal(res.particles, synth.particle_parameters(n, seed=100))         # the priors of SURVEY.md 8(d)
+        # the distance of a block of particles, recomputed from their counts
+        blk = slice(4096, 4096 + 64)
+        r = topo.simulate(res.particles[blk], 0.2, 0.2, 2, 7, 1, 11, sim_offset=4096)
+        c, d = r.counts_colonized.astype(float), r.counts_detected.astype(float)
+        want = np.nansum((c - obs_c[:, None]) ** 2, 0) + np.nansum((d - obs_d[:, None]) ** 2, 0)
+        assert np.allclose(res.distance[blk], want, rtol=1e-12, atol=0)
+        # the accepted particles concentrate around the truth where the data are informative (beta: the force of infection)
+        prior_err = abs(res.particles[:, 1].mean() - truth[0, 1])
+        assert abs(res.posterior_mean[1] - truth[0, 1]) < 0.5 * prior_err
+        assert res.posterior_sd[1] < 0.7 * res.particles[:, 1].std()
+        assert np.all(np.diff(res.distance[res.accepted]) >= 0)
+
+
 def test_device_pointer_api_matches_host_api():
     torch = pytest.importorskip("torch")
     wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=2)

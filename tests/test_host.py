@@ -265,3 +265,37 @@ def test_synthetic_hospital_tables_are_a_valid_fast_hospital():
         assert topo.info.fast_eligible and topo.info.identity_order
     with pytest.raises(ValueError):
         engine.hospital_tables(engine.hospital_spec(0, 10, 3))
+
+
+_SWEEP_WORKER = r"""
+import os, sys, types, numpy as np, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from abm_amro_b200 import capi, inference
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+class FakeTopology:   # stands in for the GPU: the distance of a particle is a known function of its parameters and global index
+    def simulate(self, par, icp, idp, ttd, tsh, tsa, seed, sim_offset=0, want_counts=True, observed_colonized=None, observed_detected=None):
+        n = par.shape[0]
+        d = ((par[:, 1] - 0.6) ** 2) * 100 + (np.arange(sim_offset, sim_offset + n) % 7) * 1e-6
+        return types.SimpleNamespace(distance=d, path_used=capi.PATH_FAST, kernel_ms=1.0)
+n = 1000
+res = inference.abc_sweep(FakeTopology(), np.zeros(3), None, n_particles=n, keep=0.05)
+par = inference.UniformPrior().sample(n, 100)
+want = ((par[:, 1] - 0.6) ** 2) * 100 + (np.arange(n) % 7) * 1e-6
+assert np.array_equal(res.distance, want) and np.array_equal(res.particles, par)
+assert np.array_equal(res.accepted, np.argsort(want, kind="stable")[:50])
+assert abs(res.posterior_mean[1] - 0.6) < 0.02
+if rank == 0: print("sweep ok")
+dist.destroy_process_group()
+"""
+
+
+def test_abc_sweep_shards_particles_world_size_2_gloo(tmp_path):
+    script = tmp_path / "s.py"
+    script.write_text(_SWEEP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "sweep ok" in outs[0][0]
