@@ -118,7 +118,7 @@ int amro_topology_get_info(const amro_topology* topo, amro_topology_info* info) 
     std::memset(info, 0, sizeof *info);
     info->n_rows = H.R; info->n_rows_stepped = H.Rp; info->n_init = H.n_init; info->total_days = H.total_days;
     info->n_days_out = H.n_days_out; info->n_segments = H.n_seg; info->max_rows_per_day = H.max_rows_per_day;
-    info->fast_eligible = H.fast_eligible; info->ring_eligible = H.ring_eligible; info->identity_order = H.identity_order;
+    info->fast_eligible = H.fast_eligible; info->ring_eligible = H.fast_eligible; info->identity_order = H.identity_order;
     info->device = topo->device; info->compile_ms = topo->compile_ms;
     snprintf(info->why_not_fast, sizeof info->why_not_fast, "%s", H.why_not_fast.c_str());
   });

@@ -272,7 +272,7 @@ extern "C" int amro_topology_generate(const amro_hospital_spec* spec, int device
     H.n_seg = s3[0]; H.max_seg_rows = s3[1]; H.max_segs_per_day = s3[2]; H.max_rows_per_day = B;
     H.identity_order = H.unit_weights = H.binary_h = H.simple_final = H.dyadic_weights = true;
     H.has_half = false;
-    H.fast_eligible = H.ring_eligible = true;
+    H.fast_eligible = true;
     t->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = t.release();
   });

@@ -267,7 +267,6 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
     }
   }
   T.fast_eligible = T.why_not_fast.empty();
-  T.ring_eligible = T.fast_eligible;
   if (!T.fast_eligible) {
     T.meta_info.clear(); T.meta_next.clear(); T.meta_nseg.clear(); T.init_seg.clear(); T.init_slot.clear(); T.seg_main_next.clear();
   }

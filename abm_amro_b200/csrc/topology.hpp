@@ -27,7 +27,7 @@ struct HostTopology {
   bool identity_order = false, unit_weights = false, binary_h = false, simple_final = false;
   bool dyadic_weights = false;   // every stepped row weighs 1 or 1/2 (the FAST path counts ward pressure in halves then)
   bool has_half = false;         // ... and some weigh 1/2
-  bool fast_eligible = false, ring_eligible = false;
+  bool fast_eligible = false;
   std::string why_not_fast;
 
   // position p in [0,R): stepped rows first, sorted by (day, ward, original index) -- the order the

@@ -65,7 +65,7 @@ typedef struct amro_topology_info {
   int64_t n_segments;        /* (day, ward) groups                                             */
   int64_t max_rows_per_day;
   int32_t fast_eligible;     /* 1 if AMRO_PATH_FAST can run this hospital                      */
-  int32_t ring_eligible;     /* 1 if every predecessor link spans exactly one day              */
+  int32_t ring_eligible;     /* same as fast_eligible (every predecessor link spans exactly one day); kept for layout */
   int32_t identity_order;    /* 1 if the input rows are already grouped by (day, ward)         */
   int32_t device;
   double  compile_ms;        /* host time spent compiling + uploading                          */
