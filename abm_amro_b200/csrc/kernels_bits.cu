@@ -46,18 +46,29 @@ constexpr int kFlushTrips = (1 << kCntPlanes) - 1;
 static_assert(kDrawBits == 14, "table rows hold 14 planes + the always mask");
 
 // 32 x 32 bit transpose across the warp: lane i holds row i; afterwards lane j holds column j (bit i = row i's bit j).
-// Per stage the lanes of a pair exchange the blocks they do not keep (rotated into place before the shuffle).
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+// Per stage the lanes of a pair exchange the blocks they do not keep (rotated into place before the shuffle).  K matrices
+// at once: a stage's K shuffles are independent, so their latencies overlap (the per-day code is latency-bound: two
+// warps per scheduler on config 2).
+template <int K>
+__device__ __forceinline__ void warp_transpose32_multi(uint32_t (&x)[K], int lane) {
 #pragma unroll
   for (int st = 0; st < 5; ++st) {
     const int k = 16 >> st;
     const uint32_t m = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u : 0x55555555u;
     const bool upper = (lane & k) != 0;
-    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, __funnelshift_l(x, x, upper ? k : 32 - k), k);
+    const int rot = upper ? k : 32 - k;
     const uint32_t keep = upper ? ~m : m;
-    x = (x & keep) | (y & ~keep);
+    uint32_t y[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) y[i] = __shfl_xor_sync(0xFFFFFFFFu, __funnelshift_l(x[i], x[i], rot), k);
+#pragma unroll
+    for (int i = 0; i < K; ++i) x[i] = (x[i] & keep) | (y[i] & ~keep);
   }
-  return x;
+}
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+  uint32_t t[1] = {x};
+  warp_transpose32_multi<1>(t, lane);
+  return t[0];
 }
 
 // Vertical counter: plane b holds bit b of a per-simulation count (32 simulations per register)
@@ -75,17 +86,34 @@ struct VCount {
       x = t;
     }
   }
-  // lane s <- the warp's total of simulation s after n_adds (warp-uniform) increments; the counter is cleared
-  __device__ __forceinline__ uint32_t flush(int lane, uint32_t n_adds) {
+};
+// lane s <- the warp's totals of simulation s of N counters after n_adds (warp-uniform) increments each; the counters are
+// cleared.  All planes that can be non-zero are transposed together (one latency chain instead of one per plane).
+template <int N, int NP>
+__device__ __forceinline__ void vflush_planes(VCount* const (&vc)[N], uint32_t (&out)[N], int lane) {
+  uint32_t t[N * NP];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int b = 0; b < NP; ++b) t[i * NP + b] = vc[i]->v[b];
+  warp_transpose32_multi<N * NP>(t, lane);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
     uint32_t c = 0u;
 #pragma unroll
-    for (int b = 0; b < kCntPlanes; ++b) {
-      if ((n_adds >> b) != 0u) c += (uint32_t)__popc(warp_transpose32(v[b], lane)) << b;
-      v[b] = 0u;
-    }
-    return c;
+    for (int b = 0; b < NP; ++b) c += (uint32_t)__popc(t[i * NP + b]) << b;
+    out[i] = c;
+    vc[i]->clear();
   }
-};
+}
+template <int N>
+__device__ __forceinline__ void vflush(VCount* const (&vc)[N], uint32_t (&out)[N], int lane, uint32_t n_adds) {
+  if (n_adds == 0u) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = 0u;
+  } else if (n_adds < 16u) vflush_planes<N, kCntPlanes - 1>(vc, out, lane);
+  else vflush_planes<N, kCntPlanes>(vc, out, lane);
+}
 
 // Shared memory (dynamic): per CTA the team's parameters and the run-constant tables, per warp a ring of table rows and
 // the transfer list.
@@ -135,9 +163,6 @@ struct BitsCtx {
 
 // element (uint4) index of slot q of a team's first word in a state-ring buffer laid out [chunk of 32 slots][word][32]
 __device__ __forceinline__ int64_t ring_slot_b(uint32_t q) { return (int64_t)(q >> 5) * (kBW * 32) + (q & 31u); }
-__device__ __forceinline__ uint32_t* press_of_day(const FastArgs& a, uint32_t* press, int d) {
-  return press + (int64_t)((unsigned)d % (unsigned)a.press_days) * a.max_segs_per_day * (kBW * 32);
-}
 
 // 14-bit thresholds of two tables -> their plane words in a table row: after the transpose lane j holds plane j of the
 // first table and lane 16 + j plane j of the second (bit 14 = "always": B = 2^14)
@@ -157,13 +182,26 @@ __device__ __forceinline__ void prepare_tables_bits(const BitsShared& sh, const 
   const int lane = threadIdx.x & 31;
   const double beta = sh.par[kBitsSims + c.w * 32 + lane];
   const uint32_t gs = c.gsim0 + (uint32_t)lane;
+  // two ward-days per pass (the division and the ten Philox rounds are two independent chains); a short tail is done twice
 #pragma unroll 1
-  for (uint32_t sl = b0; sl < b1; ++sl) {
-    const int64_t seg = seg0 + sl;
-    const int slot = (int)(sl & (kBSegs - 1));
-    sh.prep_bn[slot * 32 + lane] = __ddiv_rn(beta, __ldg(&a.seg_N[seg]));   // :98
-    sh.prep_r16[slot * 32 + lane] = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gs >> 3, kStreamDither, (uint32_t)a.seed,
-                                                          (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
+  for (uint32_t sl0 = b0; sl0 < b1; sl0 += 2) {
+    double bn[2];
+    uint32_t r16[2];
+    int slot[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t sl = min(sl0 + (uint32_t)u, b1 - 1u);
+      const int64_t seg = seg0 + sl;
+      slot[u] = (int)(sl & (kBSegs - 1));
+      bn[u] = __ddiv_rn(beta, __ldg(&a.seg_N[seg]));   // :98
+      r16[u] = chunk16(philox4x32_10((uint32_t)seg, (uint32_t)((uint64_t)seg >> 32), gs >> 3, kStreamDither, (uint32_t)a.seed,
+                                     (uint32_t)(a.seed >> 32)), (int)(gs & 7u));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      sh.prep_bn[slot[u] * 32 + lane] = bn[u];
+      sh.prep_r16[slot[u] * 32 + lane] = r16[u];
+    }
   }
 }
 __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const uint32_t* press_day, uint32_t b0, uint32_t b1,
@@ -194,6 +232,21 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
       finite[u] = fabs(F[u]) <= 1.7976931348623157e308;
     }
     const bool all_finite = __all_sync(0xFFFFFFFFu, finite[0] && finite[1]);
+    // the uncolonised classes of both ward-days and both is_new classes: four pairs of 14-bit thresholds, transposed together
+    uint32_t tw[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool flag = h ? test_a : test_h;
+      const double rho = h ? rho_i : rho_h;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const double P0 = class_probability(0, h, F[u], alpha, alpha2, gamma);
+        const uint32_t bU = (threshold30(P0) + r16[u]) >> 16;
+        const uint32_t bUh = flag ? (threshold30(__dmul_rn(clamp01(P0), rho)) + r16[u]) >> 16 : 0u;   // nobody is tested: never
+        tw[h * 2 + u] = bU | (bUh << 16);
+      }
+    }
+    warp_transpose32_multi<4>(tw, lane);   // lane j: plane j of U, lane 16 + j: plane j of Uh (bit 14 = "always": B = 2^14)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const bool flag = h ? test_a : test_h;
@@ -201,10 +254,7 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         uint32_t* row = sh.tab + (slot[u] * 2 + h) * kTabWords;
-        const double P0 = class_probability(0, h, F[u], alpha, alpha2, gamma);
-        const uint32_t bU = (threshold30(P0) + r16[u]) >> 16;
-        const uint32_t bUh = flag ? (threshold30(__dmul_rn(clamp01(P0), rho)) + r16[u]) >> 16 : 0u;   // nobody is tested: never
-        store_planes(row, kTU, kTUh, bU, bUh, lane);
+        row[(lane < 16 ? kTU : kTUh - 16) + lane] = tw[h * 2 + u];
         if (all_finite) {
           const uint4* rc = reinterpret_cast<const uint4*>(sh.rc + (h * kBW + c.w) * 48);
           if (lane < 8) reinterpret_cast<uint4*>(row + kTA)[lane] = rc[lane];
@@ -223,9 +273,8 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
 }
 
 // per-simulation day totals (:445-459 fused): lane s adds the count of simulation s of the warp's word
-__device__ __forceinline__ void emit_day_counts(const FastArgs& a, int64_t d, int64_t sim0, VCount& vcol, VCount& vdet, uint32_t n_adds) {
+__device__ __forceinline__ void add_day_counts(const FastArgs& a, int64_t d, int64_t sim0, uint32_t cc, uint32_t cd) {
   const int lane = threadIdx.x & 31;
-  const uint32_t cc = vcol.flush(lane, n_adds), cd = vdet.flush(lane, n_adds);
   if (d < a.counts_ld) {
     const int64_t at = d + a.counts_ld * (sim0 + lane);
     if (cc && a.counts_col) atomicAdd(&a.counts_col[at], (int)cc);
@@ -233,21 +282,37 @@ __device__ __forceinline__ void emit_day_counts(const FastArgs& a, int64_t d, in
   }
 }
 
+// What a warp keeps across the days of a run: its share of the pressure buffer it zeroes every day, and the ring positions
+// of today's pressure buffer (d mod press_days, kept without the division)
+struct DayState {
+  uint32_t z_lo, z_hi;      // ward-day slots [z_lo, z_hi) of the buffer being zeroed
+  uint32_t p0;              // d % press_days
+  __device__ __forceinline__ static uint32_t wrap(uint32_t i, uint32_t press_days) { return i >= press_days ? i - press_days : i; }
+  __device__ __forceinline__ void next(uint32_t press_days) { p0 = wrap(p0 + 1u, press_days); }
+};
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
 template <int TTD>
 __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
-                                                 int64_t seg0_next, TeamBarrier& bar, uint32_t gw, uint32_t n_gw) {
+                                                 int64_t seg0_next, TeamBarrier& bar, const DayState& ds) {
   const int lane = threadIdx.x & 31;
   VCount vcol, vdet;
   vcol.clear(); vdet.clear();
   uint32_t since = 0;   // trips since the day counters were flushed
+  const int64_t press_stride = a.max_segs_per_day * (kBW * 32);
 
   // the pressure buffer of the day after tomorrow is nobody's input or output today: zero this warp's share of it
   if (a.press_days == 3) {
-    uint32_t* z = press_of_day(a, c.press, d + 2) + lane;
-    const uint32_t n = (uint32_t)a.max_segs_per_day, per = (n + n_gw - 1u) / n_gw, lo = min(n, per * gw), hi = min(n, lo + per);
-    for (uint32_t i = lo; i < hi; ++i) __stcg(z + (int64_t)i * (kBW * 32), 0u);
+    uint32_t* z = c.press + DayState::wrap(ds.p0 + 2u, 3u) * press_stride + lane;
+    for (uint32_t i = ds.z_lo; i < ds.z_hi; ++i) __stcg(z + (int64_t)i * (kBW * 32), 0u);
   }
+
+  VCount vmain;            // colonised records that feed the warp's current main ward-day of tomorrow
+  vmain.clear();
+  uint32_t wmain = kNone;  // warp-uniform
+  uint32_t* press_next = c.press + DayState::wrap(ds.p0 + 1u, (uint32_t)a.press_days) * press_stride + lane;
+  auto add_main = [&](uint32_t v) {
+    if (wmain != kNone && v) red_add(press_next + (int64_t)(wmain - (uint32_t)seg0_next) * (kBW * 32), v);
+  };
 
   if (pl.w0 < pl.w1 && c.sim0 < a.S) {   // a word beyond the last simulation (a 32-member run: half a team) has nothing to step
     const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
@@ -255,27 +320,20 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
     const uint4* pm = a.meta + da + pl.w0 + lane;
-    const uint32_t* press_day = press_of_day(a, c.press, d);
-    uint32_t* press_next = press_of_day(a, c.press, d + 1) + lane;
+    const uint32_t* press_day = c.press + ds.p0 * press_stride;
     const uint32_t g32 = c.gsim0 >> 5;
 
-    VCount vmain;            // colonised records that feed the warp's current main ward-day of tomorrow
-    vmain.clear();
-    uint32_t wmain = kNone, wsegl = 0xFFFFFFFFu, since_main = 0;   // warp-uniform
-    uint32_t n_xfer = 0;                                            // entries in the transfer list (warp-uniform)
-    auto flush_main = [&]() {
-#ifdef AMRO_EXP_NOFLUSH   // timing experiment (wrong results)
-      if (d >= 2) { since_main = 0; return; }
-#endif
-      const uint32_t v = vmain.flush(lane, since_main);
-      since_main = 0;
-      if (wmain != kNone && v) red_add(press_next + (int64_t)(wmain - (uint32_t)seg0_next) * (kBW * 32), v);
-    };
+    uint32_t wsegl = 0xFFFFFFFFu;   // warp-uniform: the ward-day (within the day) wmain was looked up for
+    uint32_t n_xfer = 0;            // entries in the transfer list (warp-uniform)
     auto drain_xfer = [&]() {   // records that move to another ward: lane s adds simulation s to the successor's ward-day
       __syncwarp();
-      for (uint32_t e = 0; e < n_xfer; ++e) {
-        const uint2 x = sh.xfer[e];
-        if ((x.y >> lane) & 1u) red_add(press_next + (int64_t)x.x * (kBW * 32), 1u);
+      for (uint32_t e = 0; e < n_xfer; e += 4u) {   // four entries in flight; reads past the end of the list are (0, 0): no add
+        uint2 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = e + (uint32_t)j < n_xfer ? sh.xfer[e + j] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)   // (a predicated RED without the divergent section measured slower: profiles/sweeps.txt)
+          if ((x[j].y >> lane) & 1u) red_add(press_next + (int64_t)x[j].x * (kBW * 32), 1u);
       }
       __syncwarp();
       n_xfer = 0;
@@ -354,29 +412,35 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 
           // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) ----
           // Most records of a run feed the same ward-day (same ward, tomorrow): a vertical counter for it, flushed when the
-          // ward changes.  A trip that straddles two wards is added in two parts; records that go elsewhere are listed.
+          // ward changes.  A trip that straddles two wards is added in two parts (the second pass of the loop below: the
+          // trip's last ward starts the next counter); records that go elsewhere are listed.
           const uint32_t seg_lo = max(sl, __shfl_sync(0xFFFFFFFFu, segl, 0));
-          if (__builtin_expect(seg_lo != wsegl, 0)) {
-            wsegl = seg_lo;
-            const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_lo]);
-            if (m != wmain) { flush_main(); wmain = m; }
-          }
-          const bool has = nseg != kNone;
-          bool mine = has && nseg == wmain;
-          vmain.add(mine ? col : 0u);
-          ++since_main;
           const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, on ? segl : 0u);
-          if (__builtin_expect(seg_hi > seg_lo, 0)) {   // the trip's last ward: its records start the next counter
-            const uint32_t m = __ldg(&a.seg_main_next[seg0 + seg_hi]);
-            wsegl = seg_hi;
-            if (m != wmain) {
-              flush_main();
-              wmain = m;
-              const bool mine2 = has && nseg == wmain;
-              vmain.add(mine2 ? col : 0u);
-              ++since_main;
-              mine = mine || mine2;
+          const bool has = nseg != kNone;
+          bool mine = false;
+          uint32_t sg = seg_lo;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+            bool count = pass == 0;
+            if (__builtin_expect(sg != wsegl, 0)) {
+              wsegl = sg;
+              const uint32_t m = __ldg(&a.seg_main_next[seg0 + sg]);
+              if (m != wmain) {
+                VCount* const vc[1] = {&vmain};
+                uint32_t v[1];
+                vflush_planes<1, kCntPlanes>(vc, v, lane);
+                add_main(v[0]);
+                wmain = m;
+                count = true;
+              }
             }
+            if (count) {
+              const bool mine_p = has && nseg == wmain;
+              vmain.add(mine_p ? col : 0u);
+              mine = mine || mine_p;
+            }
+            if (__builtin_expect(seg_hi <= sg, 1)) break;
+            sg = seg_hi;
           }
           const bool is_x = has && !mine;
           const uint32_t xm = __ballot_sync(0xFFFFFFFFu, is_x);
@@ -388,21 +452,27 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
         }
         since += te - tb;
         tb = te;
-        if (since == (uint32_t)kFlushTrips) {   // since_main <= since: the main counter cannot overflow either
-          flush_main();
-          emit_day_counts(a, d, c.sim0, vcol, vdet, since);
+        if (since == (uint32_t)kFlushTrips) {   // the counters are full (the main counter was cleared since at most as long ago)
+          VCount* const vc[3] = {&vmain, &vcol, &vdet};
+          uint32_t v[3];
+          vflush_planes<3, kCntPlanes>(vc, v, lane);
+          add_main(v[0]);
+          add_day_counts(a, d, c.sim0, v[1], v[2]);
           since = 0;
         }
       }
     }
-    flush_main();
     drain_xfer();
   }
-  bar.arrive();   // tomorrow's pressure and states are out; the day totals below are nobody's input
-#ifdef AMRO_EXP_NOEMIT   // timing experiment (wrong results)
-  if (d < 2)
-#endif
-  emit_day_counts(a, d, c.sim0, vcol, vdet, since);
+  // The transposes of the last main counter and of the day totals run together (one latency chain), and while the transfer
+  // REDs and the last state stores are on their way to L2 -- the release below waits for those anyway.  The totals' atomics
+  // are nobody's input: after the arrive.
+  VCount* const vc[3] = {&vmain, &vcol, &vdet};
+  uint32_t v[3];
+  vflush<3>(vc, v, lane, since);
+  add_main(v[0]);
+  bar.arrive();   // tomorrow's pressure and states are out
+  add_day_counts(a, d, c.sim0, v[1], v[2]);
 }
 
 template <int TTD, int THREADS, int MINB>
@@ -514,7 +584,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   bar.arrive();
 
   // ---- day loop (:381): one team barrier per day ------------------------------------------------------------------
-  DayPlan plan = plan_day(a, 0, gw, n_gw);
+  DayPlan plan = plan_day(a, 0, gw, n_gw, DayPlan{});
+  DayState ds;
+  {
+    const uint32_t n = (uint32_t)a.max_segs_per_day, per = (n + n_gw - 1u) / n_gw;
+    ds.z_lo = min(n, per * gw); ds.z_hi = min(n, ds.z_lo + per);
+    ds.p0 = 0u;
+  }
   const int n_days = (int)a.n_days;
   for (int d = 0; d < n_days; ++d) {
     const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
@@ -524,8 +600,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     if (d < 2)
 #endif
     bar.wait();
-    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, gw, n_gw);
-    plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
+    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, ds);
+    ds.next((uint32_t)a.press_days);
+    plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
 }

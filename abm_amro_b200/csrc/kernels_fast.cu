@@ -684,13 +684,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fast(const __grid_constant__ 
 
   // ---- day loop (abm_wards.cpp:381): one team barrier per day ----------------------------------------------
   PHASE_T0();
-  DayPlan plan = plan_day(a, 0, gw, n_gw);
+  DayPlan plan = plan_day(a, 0, gw, n_gw, DayPlan{});
   for (int64_t d = 0; d < a.n_days; ++d) {
     bar.wait();
     PHASE_ADD(3);  // team barrier wait
     if (d == 0) process_day<REPLAY, true, LEAN, kRed64>(PHASE_ARG sh, par, a, c, d, plan, bar);   // initial rows sit on day 0 (fast-path condition)
     else process_day<REPLAY, false, LEAN, kRed64>(PHASE_ARG sh, par, a, c, d, plan, bar);
-    plan = plan_day(a, d + 1, gw, n_gw);   // static: ready before the next wait ends
+    plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
 }

@@ -108,17 +108,36 @@ struct DayPlan {
   int64_t seg0;        // first ward-day of the day
   uint32_t w0, w1;     // the run; w0 is a multiple of 32
   uint32_t sl_first, sl_last;   // ward-days (within the day) the run touches
+  uint32_t n;          // records of the day
 };
-__device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32_t gw, uint32_t n_gw) {
+// chunks [floor(n_chunks * gw / n_gw), floor(n_chunks * (gw + 1) / n_gw)) without 64-bit division: with n_chunks = q n_gw + r,
+// floor(n_chunks * g / n_gw) = q g + floor(r g / n_gw), and r g < n_gw^2 fits 32 bits for every team this library launches
+__device__ __forceinline__ void split_chunks(uint32_t n_chunks, uint32_t gw, uint32_t n_gw, uint32_t& c0, uint32_t& c1) {
+  if (n_gw < 65536u) {
+    const uint32_t q = n_chunks / n_gw, r = n_chunks - q * n_gw;
+    c0 = q * gw + (r * gw) / n_gw;
+    c1 = q * (gw + 1u) + (r * (gw + 1u)) / n_gw;
+  } else {
+    c0 = (uint32_t)(((uint64_t)n_chunks * gw) / n_gw);
+    c1 = (uint32_t)(((uint64_t)n_chunks * (gw + 1)) / n_gw);
+  }
+}
+// `prev`: the warp's plan of the day before (or DayPlan{}): a day with as many records splits the same way
+__device__ __forceinline__ DayPlan plan_day(const FastArgs& a, int64_t d, uint32_t gw, uint32_t n_gw, const DayPlan& prev) {
   DayPlan p{};
   if (d >= a.n_days) return p;
   p.da = __ldg(&a.day_start[d]);
-  const uint32_t n = (uint32_t)(__ldg(&a.day_start[d + 1]) - p.da), n_chunks = (n + 31u) / 32u;
+  p.n = (uint32_t)(__ldg(&a.day_start[d + 1]) - p.da);
   p.seg0 = __ldg(&a.day_seg_start[d]);
   // the warp's run of 32-record chunks: consecutive trips stay in one ward for a while, so what the records add to
   // tomorrow's pressure is kept in registers across trips
-  p.w0 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * gw) / n_gw));
-  p.w1 = min(n, 32u * (uint32_t)(((uint64_t)n_chunks * (gw + 1)) / n_gw));
+  if (p.n == prev.n) { p.w0 = prev.w0; p.w1 = prev.w1; }
+  else {
+    uint32_t c0, c1;
+    split_chunks((p.n + 31u) / 32u, gw, n_gw, c0, c1);
+    p.w0 = min(p.n, 32u * c0);
+    p.w1 = min(p.n, 32u * c1);
+  }
   if (p.w0 < p.w1) {
     p.sl_first = __ldg(&a.meta[p.da + p.w0].x) & kInfoSegMask;
     p.sl_last = __ldg(&a.meta[p.da + p.w1 - 1].x) & kInfoSegMask;

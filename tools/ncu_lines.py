@@ -15,5 +15,6 @@ for r in rows:
     except ValueError: pass
 tot = sum(x[2] for x in lines); ts = sum(x[3] for x in lines)
 print(f"total warp instructions {tot:.3e} = {tot / trips:.1f} per trip; samples {ts}")
-for ln, s, e, m in sorted(lines, key=lambda x: -x[2])[:top]:
+key = 3 if "--by-samples" in sys.argv else 2
+for ln, s, e, m in sorted(lines, key=lambda x: -x[key])[:top]:
     print(f"{ln:>22} {e / trips:8.1f}/trip {e / tot * 100:5.1f}%  samples {m / ts * 100:5.1f}%  {s.strip()[:110]}")
