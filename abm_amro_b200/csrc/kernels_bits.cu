@@ -287,8 +287,13 @@ __device__ __forceinline__ void add_day_counts(const FastArgs& a, int64_t d, int
 struct DayState {
   uint32_t z_lo, z_hi;      // ward-day slots [z_lo, z_hi) of the buffer being zeroed
   uint32_t p0;              // d % press_days
+  uint64_t th, ta;          // d % tsh, d % tsa (:391-392; the schedules are 64-bit the way the reference's unsigned % reads them)
   __device__ __forceinline__ static uint32_t wrap(uint32_t i, uint32_t press_days) { return i >= press_days ? i - press_days : i; }
-  __device__ __forceinline__ void next(uint32_t press_days) { p0 = wrap(p0 + 1u, press_days); }
+  __device__ __forceinline__ void next(const FastArgs& a) {
+    p0 = wrap(p0 + 1u, (uint32_t)a.press_days);
+    th = th + 1u == a.tsh ? 0u : th + 1u;
+    ta = ta + 1u == a.tsa ? 0u : ta + 1u;
+  }
 };
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
 template <int TTD>
@@ -316,7 +321,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 
   if (pl.w0 < pl.w1 && c.sim0 < a.S) {   // a word beyond the last simulation (a 32-member run: half a team) has nothing to step
     const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
-    const bool test_h = ((uint64_t)d % a.tsh) == 0, test_a = ((uint64_t)d % a.tsa) == 0;  // :391-392
+    const bool test_h = ds.th == 0u, test_a = ds.ta == 0u;  // :391-392
     const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
     const uint4* pm = a.meta + da + pl.w0 + lane;
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   {
     const uint32_t n = (uint32_t)a.max_segs_per_day, per = (n + n_gw - 1u) / n_gw;
     ds.z_lo = min(n, per * gw); ds.z_hi = min(n, ds.z_lo + per);
-    ds.p0 = 0u;
+    ds.p0 = 0u; ds.th = 0u; ds.ta = 0u;
   }
   const int n_days = (int)a.n_days;
   for (int d = 0; d < n_days; ++d) {
@@ -601,7 +606,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 #endif
     bar.wait();
     process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, ds);
-    ds.next((uint32_t)a.press_days);
+    ds.next(a);
     plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait

@@ -54,7 +54,7 @@ __device__ __forceinline__ uint4 philox_rk(const FastArgs& a, uint32_t c0, uint3
 // The warps that share a team's slices (all warps of the team's CTAs) meet once per day: a warp may start day d+1 when
 // every warp of the team has finished day d (its successors' states and tomorrow's pressure are then complete).  Arrival
 // is a release increment of the team's counter by lane 0 after __syncwarp (which orders the other lanes' writes before
-// it); waiting is an acquire-load poll by lane 0, then __syncwarp.  Nothing in the day loop synchronises a whole
+// it); waiting is a relaxed-load poll by lane 0 closed by one acquire load, then __syncwarp.  Nothing in the day loop synchronises a whole
 // CTA, so the latency of one warp's barrier or table build is covered by the other warps of the SM.  A team of one CTA
 // uses the hardware barrier instead.  The cooperative launch guarantees co-residency.
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -65,8 +65,13 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 // Three mechanisms, same protocol (arrive after the day's last write, wait before the next day's first read):
 //   kBarCta      a team of one CTA: __syncthreads
 //   kBarCluster  the team is a thread-block cluster: barrier.cluster arrive.release / wait.acquire (hardware, split-phase)
-//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, acquire-load poll)
+//   kBarGlobal   any team size: a counter in global memory (release RED by lane 0 of each warp, relaxed poll + acquire load)
 constexpr int kBarCta = 0, kBarGlobal = 1, kBarCluster = 2;
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 struct TeamBarrier {
   unsigned* ctr;
   unsigned target;
@@ -90,11 +95,14 @@ struct TeamBarrier {
       return;
     }
     if ((threadIdx.x & 31) == 0) {
-      while ((int)(ld_acquire(ctr) - target) < 0) {   // acquire load = load + L1 invalidate, without the MEMBAR of a fence
-#ifdef AMRO_POLL_SLEEP_NS
-        __nanosleep(AMRO_POLL_SLEEP_NS);
+#ifdef AMRO_POLL_ACQUIRE   // round 1 / first half of round 2: every poll an acquire load (LDG + CCTL.IVALL)
+      while ((int)(ld_acquire(ctr) - target) < 0) {}
+#else
+      // relaxed polls (no L1 invalidate per poll: the SM's other warps keep their cached topology lines), then ONE acquire
+      // load, which synchronises with the releases it observes (acquire load = load + L1 invalidate, without the MEMBAR of a fence)
+      while ((int)(ld_relaxed(ctr) - target) < 0) {}
+      (void)ld_acquire(ctr);
 #endif
-      }
     }
     __syncwarp();
   }
