@@ -272,6 +272,8 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
   }
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // per-simulation day totals (:445-459 fused): lane s adds the count of simulation s of the warp's word
 __device__ __forceinline__ void add_day_counts(const FastArgs& a, int64_t d, int64_t sim0, uint32_t cc, uint32_t cd) {
   const int lane = threadIdx.x & 31;
@@ -321,6 +323,19 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 
   if (pl.w0 < pl.w1 && c.sim0 < a.S) {   // a word beyond the last simulation (a 32-member run: half a team) has nothing to step
     const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
+#ifndef AMRO_BITS_NO_PREFETCH
+    // Topology lines this warp will ask for one after the other when the day is over (tomorrow's plan: the ward-days at the ends
+    // of its run, their N and row ranges -- tomorrow's run is today's when the census is steady) and in today's first ward change:
+    // requested now, into L1, without registers; they arrive while the trips run.  Wrong guesses cost nothing but the request.
+    if (lane == 0 && d + 1 < (int)a.n_days) {
+      const int64_t da_next = da + pl.n, sn = min(seg0_next + pl.sl_first, a.n_seg - 1);
+      prefetch_l1(&a.meta[min(da_next + pl.w0, a.R - 1)]);
+      prefetch_l1(&a.meta[min(da_next + pl.w1 - 1, a.R - 1)]);
+      prefetch_l1(&a.seg_N[sn]);
+      prefetch_l1(&a.seg_row_start[sn]);
+      prefetch_l1(&a.seg_main_next[seg0 + pl.sl_first]);
+    }
+#endif
     const bool test_h = ds.th == 0u, test_a = ds.ta == 0u;  // :391-392
     const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
