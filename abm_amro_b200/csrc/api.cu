@@ -468,7 +468,9 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // A pair of warps steps a run of records (one warp per word).  Team size: the largest number of whole CTAs-per-SM layers
   // (the grid then loads every SM alike) that still leaves a warp about `trips` 32-record trips a day -- measured on config 2:
   // 18 CTAs per team (2 per SM, 8.7 trips) beat 12, 16, 24 and 36 (profiles/sweeps.txt).
-  int trips = 8;
+  // A ward-day's pressure is counted by every run that touches it: runs much shorter than the wards would spend their day counting,
+  // so a run is at least a quarter of the largest ward-day.
+  int trips = (int)std::max<int64_t>(8, (H.max_seg_rows + 127) / 128);
   if (const char* e = std::getenv("AMRO_BITS_TRIPS")) trips = std::max(1, std::atoi(e));
   int G = 1, extra = 0;
   const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day * bits_words_per_team() / ((int64_t)trips * kTeamThreads));
@@ -498,10 +500,11 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (ring_chunks * 32 * kSlicesPerTeam * (int64_t)sizeof(uint4) >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: day too large for 32-bit slot offsets");
   const int64_t n_days = H.total_days + 1;
   const int64_t max_segs = std::max<int64_t>(H.max_segs_per_day, 1);
-  const int64_t press_days = A->pressure_out ? n_days + 1 : 3;
+  const int64_t press_days = n_days + 1;   // the export buffer's days (only when pressure_out is asked for)
 
+  T->ensure_pull();
   ensure_size(T->ws_pre, (size_t)(n_teams * 2 * ring_chunks * 32 * kSlicesPerTeam));
-  ensure_size(T->ws_pressure, (size_t)(n_teams * press_days * max_segs * kTeamSims));
+  if (A->pressure_out) ensure_size(T->ws_pressure, (size_t)(n_teams * press_days * max_segs * kTeamSims));
   ensure_size(T->ws_counts, (size_t)(2 * H.n_days_out * S_pad));
   ensure_size(T->ws_params, (size_t)(S_pad * 6));
   AMRO_CUDA(cudaMemsetAsync(T->ws_counts.p, 0, sizeof(int32_t) * 2 * H.n_days_out * S_pad, st));
@@ -529,7 +532,8 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   }
   f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
   f.pre = T->ws_pre.p; f.traj = nullptr;
-  f.pressure = T->ws_pressure.p;
+  f.pressure = A->pressure_out ? T->ws_pressure.p : nullptr;
+  f.src_mask = T->src_mask.p; f.day_chunk_start = T->day_chunk_start.p;
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
   ensure_size(T->ws_barrier, (size_t)n_teams);
   AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));

@@ -40,6 +40,22 @@ struct amro_topology {
   amro::DevBuf<double> seg_N;
   amro::DevBuf<uint4> meta;   // packed per-record words of the fast path (kernels.hpp FastArgs::meta)
   amro::DevBuf<uint32_t> init_seg, init_slot, seg_main_next;
+  // bit-sliced kernel (built on first use from the device arrays above: the same for compiled and generated hospitals)
+  bool pull_ready = false;
+  amro::DevBuf<uint32_t> src_mask;
+  amro::DevBuf<int64_t> day_chunk_start;
+  void ensure_pull() {
+    if (pull_ready) return;
+    const int64_t n_days = H.total_days + 1;
+    std::vector<int64_t> ds((size_t)(n_days + 1)), dc((size_t)(n_days + 1), 0);
+    AMRO_CUDA(cudaMemcpy(ds.data(), day_start.p, sizeof(int64_t) * (n_days + 1), cudaMemcpyDeviceToHost));
+    for (int64_t d = 0; d < n_days; ++d) dc[d + 1] = dc[d] + (ds[d + 1] - ds[d] + 31) / 32;
+    day_chunk_start.upload(dc.data(), dc.size());
+    src_mask.alloc((size_t)std::max<int64_t>(dc[n_days], 1));
+    amro::bits_build_src_mask(0, meta.p, day_start.p, day_chunk_start.p, n_days, H.max_rows_per_day, src_mask.p);
+    AMRO_CUDA(cudaStreamSynchronize(0));
+    pull_ready = true;
+  }
   // general path (uploaded on first use)
   bool general_ready = false;
   amro::DevBuf<int64_t> order, push_src, push_dst;

@@ -121,9 +121,12 @@ struct FastArgs {
   int ctas_per_team;             // CTAs that share a team's slices (1 = no inter-CTA barrier) ...
   int teams_plus_one;            // ... the first teams_plus_one teams have one more, so that the grid fills the SMs evenly
   int cluster_barrier;           // 1: every team is a thread-block cluster and meets at the hardware cluster barrier
-  // bit-sliced kernel (kernels_bits.cu): pressure is [n_teams][press_days][max_segs_per_day][words per team][32] 32-bit counts
+  // bit-sliced kernel (kernels_bits.cu): ward pressure is pulled from the state ring; `pressure` is nullptr or the export buffer
+  // [n_teams][press_days = n_days + 1][max_segs_per_day][words per team][32] of 32-bit counts
   int64_t max_segs_per_day;
-  int press_days;                // 3 (ring: today, tomorrow, the buffer being zeroed) or n_days + 1 (kept for export)
+  int press_days;
+  const uint32_t* src_mask;        // one bit per record: it has a source (a predecessor or an initial row); word = 32-record chunk of a day
+  const int64_t* day_chunk_start;  // [n_days + 1] first chunk of every day in src_mask
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]
@@ -156,6 +159,9 @@ int bits_max_coresident_ctas(int device, int ttd, int shape);
 int bits_max_coresident_clusters(int ttd, int shape, int cluster_size);
 void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid);
 // out[ward-day + ld*sim] = colonised count the ward-day started with (press_days = n_days + 1 runs only)
+// src_mask / day_chunk_start of a compiled hospital (device arrays; day_chunk_start from the host copy of day_start)
+void bits_build_src_mask(cudaStream_t st, const uint4* meta, const int64_t* day_start, const int64_t* day_chunk_start, int64_t n_days,
+                         int64_t max_rows_per_day, uint32_t* src_mask);
 void bits_export_pressure(cudaStream_t st, const uint32_t* pressure, const int64_t* day_seg_start, int64_t n_days, int64_t max_segs,
                           int64_t press_days, int64_t S, int32_t* out, int64_t ld);
 

@@ -19,8 +19,12 @@
 //   counts       per-lane VERTICAL counters (bit-sliced ripple adders over the trips of a warp), turned into per-simulation
 //                integers by a 32 x 32 bit transpose across the warp (five shuffle stages) + POPC when a ward-day / the day ends
 // Data layout (HBM): the two-day state ring and the per-record meta words of kernels_fast.cu (same slots, same byte
-// offsets: a slot holds kBW 16-byte words = kBW x 32 simulations); ward pressure as 32-bit counts
-// [team][day mod press_days][ward-day of the day][word][32 simulations] (three days in flight; all days when exported).
+// offsets: a slot holds kBW 16-byte words = kBW x 32 simulations), plus one bit per record "has a source" (src_mask).
+// Ward pressure (the reference's sum(W), :99) is PULLED: the warp that builds a ward-day's tables counts the colonised
+// plane of the ward-day's records in the state ring -- the states they start the day from, written by their predecessors
+// yesterday -- with a vertical counter.  Nothing is added to a successor's ward when a record is stepped: no atomics, no
+// transfer lists, no pressure buffers (kernels_fast.cu pushes; round 2 measured the push at a fifth of this kernel's
+// instructions).  A ward-day that spans several runs is counted by each of them (config 2: 2.2 times).
 // Work decomposition, team barrier and day plan: team.cuh, as in kernels_fast.cu; a team = 32 * kBW simulations.
 #include "team.cuh"
 
@@ -36,7 +40,6 @@ constexpr int kBSegs = AMRO_BITS_SEGS;              // ring of ward-day tables p
 constexpr int kTabWords = 80;                       // a table row: 5 tables x 16 words (14 planes, the "always" mask, a zero)
 constexpr int kTU = 0, kTA = 16, kTB = 32, kTUh = 48, kTAh = 64;   // word offsets of the tables in a row
 constexpr int kZeroRowB = kBSegs * 2;               // rows (ward-day, is_new) + one all-zero row: lanes without a record step against it
-constexpr int kXferCap = 96;                        // entries of a warp's transfer list (drained when fewer than 32 are free)
 constexpr int kCntPlanes = 5;                       // vertical counters count to 31
 #ifndef AMRO_BITS_DENSE_BLOCKS
 #define AMRO_BITS_DENSE_BLOCKS 6
@@ -115,13 +118,11 @@ __device__ __forceinline__ void vflush(VCount* const (&vc)[N], uint32_t (&out)[N
   else vflush_planes<N, kCntPlanes>(vc, out, lane);
 }
 
-// Shared memory (dynamic): per CTA the team's parameters and the run-constant tables, per warp a ring of table rows and
-// the transfer list.
+// Shared memory (dynamic): per CTA the team's parameters and the run-constant tables, per warp a ring of table rows.
 //   par   double [6][kBitsSims]                      alpha, beta, gamma, rho_hospital, alpha2, rho_imported (:79-84)
 //   r16   uint32 [kBitsSims]                          the run's dither (rng.cuh: kRunDitherIndex)
 //   rc    uint32 [is_new][word][48]                   tables A, B, Ah under a finite force of infection (they do not depend on the ward)
 //   tab   uint32 [kZeroRowB + 1 rows][kTabWords]      per warp: rows (ward-day slot, is_new) of the warp's word
-//   xfer  uint2  [kXferCap]                           per warp: (ward-day of the successor within its day, colonised word)
 //   prep  double [kBSegs][32] + uint32 [kBSegs][32]   per warp: beta / N and the dither of the next batch of ward-days (the part
 //                                                     of a table that does not depend on the ward's pressure, computed while
 //                                                     the warp would otherwise wait for the previous day to complete)
@@ -130,12 +131,11 @@ struct BitsShared {
   uint32_t* r16;
   uint32_t* rc;
   uint32_t* tab;
-  uint2* xfer;
   double* prep_bn;
   uint32_t* prep_r16;
 };
 constexpr size_t kCtaSharedBytes = sizeof(double) * 6 * kBitsSims + sizeof(uint32_t) * kBitsSims + sizeof(uint32_t) * 2 * kBW * 48;
-constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + sizeof(uint2) * kXferCap + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32;
+constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32;
 static_assert(kCtaSharedBytes % 16 == 0 && kWarpSharedBytes % 16 == 0, "table rows are read as uint4");
 __host__ __device__ inline size_t bits_smem_bytes(int threads) { return kCtaSharedBytes + (size_t)(threads / 32) * kWarpSharedBytes; }
 __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
@@ -145,8 +145,7 @@ __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
   s.rc = s.r16 + kBitsSims;
   unsigned char* mine = raw + kCtaSharedBytes + (size_t)warp * kWarpSharedBytes;
   s.tab = reinterpret_cast<uint32_t*>(mine);
-  s.xfer = reinterpret_cast<uint2*>(s.tab + (kZeroRowB + 1) * kTabWords);
-  s.prep_bn = reinterpret_cast<double*>(s.xfer + kXferCap);
+  s.prep_bn = reinterpret_cast<double*>(s.tab + (kZeroRowB + 1) * kTabWords);
   s.prep_r16 = reinterpret_cast<uint32_t*>(s.prep_bn + kBSegs * 32);
   return s;
 }
@@ -155,7 +154,7 @@ __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
 // one warp per group of 32 simulations (word w of the 16-byte-word ring slots).
 struct BitsCtx {
   uint4* pre;          // [2][ring_chunks][kBW][32], offset to the warp's word
-  uint32_t* press;     // [press_days][max_segs][kBW][32], offset to the warp's word
+  uint32_t* press;     // nullptr, or [n_days + 1][max_segs][kBW][32] offset to the warp's word: the pulled counts, kept for export
   uint32_t gsim0;      // global index of the first simulation of the warp's word (a multiple of 32)
   int64_t sim0;        // first simulation of the warp's word (run-relative)
   int w;               // the word
@@ -204,23 +203,66 @@ __device__ __forceinline__ void prepare_tables_bits(const BitsShared& sh, const 
     }
   }
 }
-__device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const uint32_t* press_day, uint32_t b0, uint32_t b1,
-                                                   bool test_h, bool test_a) {
+// sum(W) of a ward-day (:95-99) for the 32 simulations of the warp's word: the colonised plane of the states its records
+// [rs, re) (positions within the day) start the day from, counted with a vertical counter -- lane = record while counting,
+// lane = simulation in the result.  Records without a source (admitted today) have no state yet: their ring slot holds
+// somebody else's old state and is masked out (src_mask: one bit per record, static).
+__device__ __forceinline__ uint32_t pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, uint32_t rs, uint32_t re, int lane) {
+  VCount vc;
+  vc.clear();
+  uint32_t total = 0u;
+  const uint32_t k1 = (re + 31u) >> 5;
+  uint32_t k = rs >> 5;
+  while (k < k1) {
+    const uint32_t ke = min(k1, k + (uint32_t)kFlushTrips);
+    const uint32_t n = ke - k;
+#pragma unroll 4
+    for (; k < ke; ++k) {
+      const uint32_t pos = k * 32u + (uint32_t)lane;
+      const uint32_t m = __ldg(mask_day + k);
+      const uint32_t x = __ldcg(pre_x + (int64_t)k * (kBW * 32 * 4));
+      vc.add(pos >= rs && pos < re && ((m >> lane) & 1u) ? x : 0u);
+    }
+    VCount* const v1[1] = {&vc};
+    uint32_t o[1];
+    vflush<1>(v1, o, lane, n);
+    total += o[0];
+  }
+  return total;
+}
+
+// What finish_tables_bits needs about the day
+struct DayIn {
+  const uint32_t* pre_x;      // colonised plane of the day's state-ring buffer: word .x of slot 0 of the warp's word, + 4 * lane
+  const uint32_t* mask_day;   // src_mask of the day's first chunk
+  const int64_t* seg_rows;    // seg_row_start of the day's first ward-day
+  int64_t da;                 // first position of the day
+  uint32_t* press_out;        // nullptr, or where the day's counts go ([ward-day of the day][kBW][32], + lane)
+  bool test_h, test_a;
+};
+__device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const DayIn& in, uint32_t b0, uint32_t b1) {
   const int lane = threadIdx.x & 31;
   const int sim = c.w * 32 + lane;
+  const bool test_h = in.test_h, test_a = in.test_a;
   const double alpha = sh.par[sim], gamma = sh.par[2 * kBitsSims + sim], alpha2 = sh.par[4 * kBitsSims + sim];
   const double rho_h = sh.par[3 * kBitsSims + sim], rho_i = sh.par[5 * kBitsSims + sim];
-  // two ward-days per pass: their dependent chains (pressure load, fp64, transposes) overlap; a short tail is built twice
+  // two ward-days per pass: their dependent chains (fp64, transposes) overlap; a short tail is built twice
 #pragma unroll 1
   for (uint32_t sl0 = b0; sl0 < b1; sl0 += 2) {
     uint32_t cnt[2], r16[2];
     double bn[2];
     int slot[2];
+    uint32_t rows[3];
+    if (lane < 3) rows[0] = (uint32_t)(__ldg(in.seg_rows + min(sl0 + (uint32_t)lane, b1)) - in.da);
+    rows[2] = __shfl_sync(0xFFFFFFFFu, rows[0], 2); rows[1] = __shfl_sync(0xFFFFFFFFu, rows[0], 1); rows[0] = __shfl_sync(0xFFFFFFFFu, rows[0], 0);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const uint32_t sl = min(sl0 + (uint32_t)u, b1 - 1u);
       slot[u] = (int)(sl & (kBSegs - 1));
-      cnt[u] = __ldcg(press_day + (int64_t)sl * (kBW * 32) + lane);
+      if (u == 0 || sl0 + 1u < b1) {
+        cnt[u] = pull_pressure(in.pre_x, in.mask_day, rows[u], rows[u + 1], lane);
+        if (in.press_out) in.press_out[(int64_t)sl * (kBW * 32)] = cnt[u];   // every run that touches the ward-day writes the same count
+      } else cnt[u] = cnt[0];
       bn[u] = sh.prep_bn[slot[u] * 32 + lane];
       r16[u] = sh.prep_r16[slot[u] * 32 + lane];
     }
@@ -284,15 +326,11 @@ __device__ __forceinline__ void add_day_counts(const FastArgs& a, int64_t d, int
   }
 }
 
-// What a warp keeps across the days of a run: its share of the pressure buffer it zeroes every day, and the ring positions
-// of today's pressure buffer (d mod press_days, kept without the division)
+// What a warp keeps across the days of a run: d % tsh, d % tsa (:391-392; the schedules are 64-bit the way the reference's
+// unsigned % reads them), kept without the division
 struct DayState {
-  uint32_t z_lo, z_hi;      // ward-day slots [z_lo, z_hi) of the buffer being zeroed
-  uint32_t p0;              // d % press_days
-  uint64_t th, ta;          // d % tsh, d % tsa (:391-392; the schedules are 64-bit the way the reference's unsigned % reads them)
-  __device__ __forceinline__ static uint32_t wrap(uint32_t i, uint32_t press_days) { return i >= press_days ? i - press_days : i; }
+  uint64_t th, ta;
   __device__ __forceinline__ void next(const FastArgs& a) {
-    p0 = wrap(p0 + 1u, (uint32_t)a.press_days);
     th = th + 1u == a.tsh ? 0u : th + 1u;
     ta = ta + 1u == a.tsa ? 0u : ta + 1u;
   }
@@ -305,59 +343,33 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
   VCount vcol, vdet;
   vcol.clear(); vdet.clear();
   uint32_t since = 0;   // trips since the day counters were flushed
-  const int64_t press_stride = a.max_segs_per_day * (kBW * 32);
-
-  // the pressure buffer of the day after tomorrow is nobody's input or output today: zero this warp's share of it
-  if (a.press_days == 3) {
-    uint32_t* z = c.press + DayState::wrap(ds.p0 + 2u, 3u) * press_stride + lane;
-    for (uint32_t i = ds.z_lo; i < ds.z_hi; ++i) __stcg(z + (int64_t)i * (kBW * 32), 0u);
-  }
-
-  VCount vmain;            // colonised records that feed the warp's current main ward-day of tomorrow
-  vmain.clear();
-  uint32_t wmain = kNone;  // warp-uniform
-  uint32_t* press_next = c.press + DayState::wrap(ds.p0 + 1u, (uint32_t)a.press_days) * press_stride + lane;
-  auto add_main = [&](uint32_t v) {
-    if (wmain != kNone && v) red_add(press_next + (int64_t)(wmain - (uint32_t)seg0_next) * (kBW * 32), v);
-  };
 
   if (pl.w0 < pl.w1 && c.sim0 < a.S) {   // a word beyond the last simulation (a 32-member run: half a team) has nothing to step
     const int64_t ring = a.ring_chunks * (kBW * 32), da = pl.da, seg0 = pl.seg0;
 #ifndef AMRO_BITS_NO_PREFETCH
     // Topology lines this warp will ask for one after the other when the day is over (tomorrow's plan: the ward-days at the ends
-    // of its run, their N and row ranges -- tomorrow's run is today's when the census is steady) and in today's first ward change:
-    // requested now, into L1, without registers; they arrive while the trips run.  Wrong guesses cost nothing but the request.
+    // of its run, their N and row ranges -- tomorrow's run is today's when the census is steady): requested now, into L1,
+    // without registers; they arrive while the trips run.  Wrong guesses cost nothing but the request.
     if (lane == 0 && d + 1 < (int)a.n_days) {
       const int64_t da_next = da + pl.n, sn = min(seg0_next + pl.sl_first, a.n_seg - 1);
       prefetch_l1(&a.meta[min(da_next + pl.w0, a.R - 1)]);
       prefetch_l1(&a.meta[min(da_next + pl.w1 - 1, a.R - 1)]);
       prefetch_l1(&a.seg_N[sn]);
       prefetch_l1(&a.seg_row_start[sn]);
-      prefetch_l1(&a.seg_main_next[seg0 + pl.sl_first]);
     }
 #endif
-    const bool test_h = ds.th == 0u, test_a = ds.ta == 0u;  // :391-392
-    const uint4* pc = c.pre + (d & 1) * ring + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
+    const uint4* pday = c.pre + (d & 1) * ring;
+    const uint4* pc = pday + (int64_t)(pl.w0 >> 5) * (kBW * 32) + lane;
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
     const uint4* pm = a.meta + da + pl.w0 + lane;
-    const uint32_t* press_day = c.press + ds.p0 * press_stride;
     const uint32_t g32 = c.gsim0 >> 5;
-
-    uint32_t wsegl = 0xFFFFFFFFu;   // warp-uniform: the ward-day (within the day) wmain was looked up for
-    uint32_t n_xfer = 0;            // entries in the transfer list (warp-uniform)
-    auto drain_xfer = [&]() {   // records that move to another ward: lane s adds simulation s to the successor's ward-day
-      __syncwarp();
-      for (uint32_t e = 0; e < n_xfer; e += 4u) {   // four entries in flight; reads past the end of the list are (0, 0): no add
-        uint2 x[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = e + (uint32_t)j < n_xfer ? sh.xfer[e + j] : make_uint2(0u, 0u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)   // (a predicated RED without the divergent section measured slower: profiles/sweeps.txt)
-          if ((x[j].y >> lane) & 1u) red_add(press_next + (int64_t)x[j].x * (kBW * 32), 1u);
-      }
-      __syncwarp();
-      n_xfer = 0;
-    };
+    DayIn in;
+    in.pre_x = reinterpret_cast<const uint32_t*>(pday) + 4 * lane;
+    in.mask_day = a.src_mask + __ldg(&a.day_chunk_start[d]);
+    in.seg_rows = a.seg_row_start + seg0;
+    in.da = da;
+    in.press_out = c.press ? c.press + (int64_t)d * a.max_segs_per_day * (kBW * 32) + lane : nullptr;
+    in.test_h = ds.th == 0u; in.test_a = ds.ta == 0u;
 
     const uint32_t n_run = pl.w1 - pl.w0;
     for (uint32_t sl = pl.sl_first; sl <= pl.sl_last; sl += kBSegs) {
@@ -367,11 +379,10 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 #ifdef AMRO_EXP_NOTABLES   // timing experiment (wrong results): tables built on the first two days only
       if (d < 2)
 #endif
-      finish_tables_bits(sh, c, press_day, sl, sl + n_tab, test_h, test_a);
+      finish_tables_bits(sh, c, in, sl, sl + n_tab);
       __syncwarp();
-      const int64_t sb = seg0 + sl;
-      const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(&a.seg_row_start[sb]) - da)) - pl.w0;
-      const uint32_t re = min(pl.w1, (uint32_t)(__ldg(&a.seg_row_start[sb + n_tab]) - da)) - pl.w0;
+      const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(in.seg_rows + sl) - da)) - pl.w0;
+      const uint32_t re = min(pl.w1, (uint32_t)(__ldg(in.seg_rows + sl + n_tab) - da)) - pl.w0;
       uint32_t tb = rb >> 5;
       const uint32_t t_end = (re + 31u) >> 5;
       while (tb < t_end) {
@@ -392,7 +403,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
           const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
           const bool on = i < n_run && segl - sl < n_tab;   // this batch's records
           const uint4* tr = reinterpret_cast<const uint4*>(sh.tab + (on ? (int)(segl & (kBSegs - 1)) * 2 + h : kZeroRowB) * kTabWords);
-          const uint32_t next = on ? meta.y : kNone, nseg = on ? meta.z : kNone;
+          const uint32_t next = on ? meta.y : kNone;
           if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);   // (C = 0, D = inf) x 32, :359-360
 
           // ---- draws: u < t per probability class, least significant plane first; four planes per Philox call (rng.cuh) ----
@@ -426,73 +437,30 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
           if (TTD == 0) post.y |= tested;
           if (TTD == 1) post.z = tested;
           if (TTD == 2) { post.z = col & q2; post.w = tested; }
-          if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next), post);         // :402-407 the successor starts from this state
+          // :402-407 the successor starts from this state -- and its ward counts it tomorrow (pull_pressure)
+          if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next), post);
           vcol.add(col);
           vdet.add(post.y);
-
-          // ---- feed the successor's ward-day (its sum(W) of tomorrow, :95-99) ----
-          // Most records of a run feed the same ward-day (same ward, tomorrow): a vertical counter for it, flushed when the
-          // ward changes.  A trip that straddles two wards is added in two parts (the second pass of the loop below: the
-          // trip's last ward starts the next counter); records that go elsewhere are listed.
-          const uint32_t seg_lo = max(sl, __shfl_sync(0xFFFFFFFFu, segl, 0));
-          const uint32_t seg_hi = __reduce_max_sync(0xFFFFFFFFu, on ? segl : 0u);
-          const bool has = nseg != kNone;
-          bool mine = false;
-          uint32_t sg = seg_lo;
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            bool count = pass == 0;
-            if (__builtin_expect(sg != wsegl, 0)) {
-              wsegl = sg;
-              const uint32_t m = __ldg(&a.seg_main_next[seg0 + sg]);
-              if (m != wmain) {
-                VCount* const vc[1] = {&vmain};
-                uint32_t v[1];
-                vflush_planes<1, kCntPlanes>(vc, v, lane);
-                add_main(v[0]);
-                wmain = m;
-                count = true;
-              }
-            }
-            if (count) {
-              const bool mine_p = has && nseg == wmain;
-              vmain.add(mine_p ? col : 0u);
-              mine = mine || mine_p;
-            }
-            if (__builtin_expect(seg_hi <= sg, 1)) break;
-            sg = seg_hi;
-          }
-          const bool is_x = has && !mine;
-          const uint32_t xm = __ballot_sync(0xFFFFFFFFu, is_x);
-          if (xm) {
-            if (is_x) sh.xfer[n_xfer + (uint32_t)__popc(xm & ((1u << lane) - 1u))] = make_uint2(nseg - (uint32_t)seg0_next, col);
-            n_xfer += (uint32_t)__popc(xm);
-            if (n_xfer > (uint32_t)(kXferCap - 32)) drain_xfer();
-          }
         }
         since += te - tb;
         tb = te;
-        if (since == (uint32_t)kFlushTrips) {   // the counters are full (the main counter was cleared since at most as long ago)
-          VCount* const vc[3] = {&vmain, &vcol, &vdet};
-          uint32_t v[3];
-          vflush_planes<3, kCntPlanes>(vc, v, lane);
-          add_main(v[0]);
-          add_day_counts(a, d, c.sim0, v[1], v[2]);
+        if (since == (uint32_t)kFlushTrips) {   // the counters are full
+          VCount* const vc[2] = {&vcol, &vdet};
+          uint32_t v[2];
+          vflush_planes<2, kCntPlanes>(vc, v, lane);
+          add_day_counts(a, d, c.sim0, v[0], v[1]);
           since = 0;
         }
       }
     }
-    drain_xfer();
   }
-  // The transposes of the last main counter and of the day totals run together (one latency chain), and while the transfer
-  // REDs and the last state stores are on their way to L2 -- the release below waits for those anyway.  The totals' atomics
-  // are nobody's input: after the arrive.
-  VCount* const vc[3] = {&vmain, &vcol, &vdet};
-  uint32_t v[3];
-  vflush<3>(vc, v, lane, since);
-  add_main(v[0]);
-  bar.arrive();   // tomorrow's pressure and states are out
-  add_day_counts(a, d, c.sim0, v[1], v[2]);
+  // The transposes of the day totals (registers and shuffles only) run while the last state stores are on their way to L2 --
+  // the release below waits for those anyway.  The totals' atomics are nobody's input: after the arrive.
+  VCount* const vc[2] = {&vcol, &vdet};
+  uint32_t v[2];
+  vflush<2>(vc, v, lane, since);
+  bar.arrive();   // tomorrow's states are out
+  add_day_counts(a, d, c.sim0, v[0], v[1]);
 }
 
 template <int TTD, int THREADS, int MINB>
@@ -513,24 +481,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   const int64_t ring = a.ring_chunks * (kBW * 32);
 
   uint4* team_pre = a.pre + team * 2 * ring;
-  uint32_t* team_press = a.pressure + team * a.press_days * a.max_segs_per_day * (kBW * 32);
+  // the pulled counts of every ward-day are kept only when the caller asked for them (pressure_out): [team][n_days][max_segs][kBW][32]
+  uint32_t* team_press = a.pressure ? a.pressure + team * a.press_days * a.max_segs_per_day * (kBW * 32) : nullptr;
   const uint32_t team_gsim0 = (uint32_t)(a.sim_offset + (uint64_t)team * kBitsSims);
   const int64_t team_sim0 = team * kBitsSims;
   BitsCtx c;
   c.w = (int)(gw_all % kBW);
   c.pre = team_pre + c.w * 32;
-  c.press = team_press + c.w * 32;
+  c.press = team_press ? team_press + c.w * 32 : nullptr;
   c.gsim0 = team_gsim0 + (uint32_t)c.w * 32u;
   c.sim0 = team_sim0 + c.w * 32;
 
-  // ---- team setup: parameters, run-constant tables and the all-zero rows to shared memory, pressure zeroed ------------
+  // ---- team setup: parameters, run-constant tables and the all-zero rows to shared memory --------------------------------
   for (int q = tid; q < 6 * kBitsSims; q += THREADS) sh.par[q] = a.params[(team_sim0 + q % kBitsSims) + a.p_ld * (q / kBitsSims)];
   for (int q = lane; q < kTabWords; q += 32) sh.tab[kZeroRowB * kTabWords + q] = 0u;
-  {
-    const int64_t n = (int64_t)a.press_days * a.max_segs_per_day * (kBW * 32), per = (n + G - 1) / G;
-    const int64_t lo = rank * per, hi = min(n, lo + per);
-    for (int64_t i = lo + tid; i < hi; i += THREADS) __stcg(&team_press[i], 0u);
-  }
   __syncthreads();
   for (int it = warp; it < 2 * kBW; it += kWarps) {   // (is_new, word): lane = simulation
     const int h = it / kBW, w = it % kBW, sim = w * 32 + lane;
@@ -546,21 +510,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     store_planes(rc, 32, -1, (threshold30(__dmul_rn(clamp01(P1), rho)) + rd) >> 16, 0u, lane);
   }
   __syncthreads();
-  bar.arrive();
-  bar.wait();
 
   // ---- initial state (:363-372) into the day-0 buffer: a lane draws 8 simulations of a row, four lanes make a word -----
+  // (the ward pressure of day 0 is pulled from these states like any other day's)
   {
     const int64_t n = a.n_init, per = ((n + G - 1) / G + 7) / 8 * 8;
     const int64_t lo = rank * per, hi = min(n, lo + per);
-    uint32_t* press0 = team_press;   // day 0
-    const int64_t seg00 = a.n_days > 0 ? __ldg(&a.day_seg_start[0]) : 0;
     for (int64_t r0 = lo + warp * 8; r0 < hi; r0 += kWarps * 8) {
       const int64_t r = r0 + (lane >> 2);
       const int g = lane & 3;
       const bool live = r < hi;
       const uint32_t slot = live ? __ldg(&a.init_slot[r]) : kNone;   // kNone: overwritten by a predecessor before it is ever read
-      const uint32_t iseg = live ? __ldg(&a.init_seg[r]) : kNone;
 #pragma unroll 1
       for (int w = 0; w < kBW; ++w) {
         uint32_t c0 = 0u, d0 = 0u, valid = 0u;
@@ -582,7 +542,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
             }
           }
         }
-        const uint32_t mine_c0 = c0;
         c0 |= __shfl_xor_sync(0xFFFFFFFFu, c0, 1); c0 |= __shfl_xor_sync(0xFFFFFFFFu, c0, 2);
         d0 |= __shfl_xor_sync(0xFFFFFFFFu, d0, 1); d0 |= __shfl_xor_sync(0xFFFFFFFFu, d0, 2);
         valid |= __shfl_xor_sync(0xFFFFFFFFu, valid, 1); valid |= __shfl_xor_sync(0xFFFFFFFFu, valid, 2);
@@ -592,11 +551,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
           // detected (it is re-tested like D = inf)
           const uint32_t flag1 = c0 & d0;
           if (g == 0) __stcg(&team_pre[ring_slot_b(slot) + w * 32], make_uint4(c0, valid & ~flag1, TTD >= 1 ? flag1 : 0u, 0u));
-          if (iseg != kNone) {
-            uint32_t* dst = press0 + ((int64_t)(iseg - (uint32_t)seg00) * kBW + w) * 32 + g * 8;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if ((mine_c0 >> (g * 8 + k)) & 1u) red_add(dst + k, 1u);
-          }
         }
       }
     }
@@ -605,12 +559,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 
   // ---- day loop (:381): one team barrier per day ------------------------------------------------------------------
   DayPlan plan = plan_day(a, 0, gw, n_gw, DayPlan{});
-  DayState ds;
-  {
-    const uint32_t n = (uint32_t)a.max_segs_per_day, per = (n + n_gw - 1u) / n_gw;
-    ds.z_lo = min(n, per * gw); ds.z_hi = min(n, ds.z_lo + per);
-    ds.p0 = 0u; ds.th = 0u; ds.ta = 0u;
-  }
+  DayState ds{0u, 0u};
   const int n_days = (int)a.n_days;
   for (int d = 0; d < n_days; ++d) {
     const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
@@ -625,6 +574,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
   if (bar.mode == kBarCluster) bar.wait();   // every arrive of a cluster barrier is paired with a wait
+}
+
+// src_mask: bit j of word day_chunk_start[d] + k <=> record 32 k + j of day d has a source (a predecessor or an initial row).
+// One warp per chunk (grid.y = day).
+__global__ void k_bits_src_mask(const uint4* __restrict__ meta, const int64_t* __restrict__ day_start, const int64_t* __restrict__ day_chunk_start,
+                                int64_t n_days, uint32_t* __restrict__ src_mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_x = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t d = blockIdx.y; d < n_days; d += gridDim.y) {
+    const int64_t da = day_start[d], n = day_start[d + 1] - da, n_chunks = (n + 31) / 32;
+    for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < n_chunks; k += warps_x) {
+      const int64_t i = k * 32 + lane;
+      const bool has = i < n && ((__ldg(&meta[da + i].x) >> kInfoSrcShift) & 3u) != kSrcNone;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+      if (lane == 0) src_mask[day_chunk_start[d] + k] = m;
+    }
+  }
 }
 
 // ward pressure of a finished run -> out[ward-day + ld * simulation] (press_days = n_days + 1)
@@ -705,6 +671,16 @@ void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid) {
   } else {
     AMRO_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)kTeamThreads), params, smem, st));
   }
+}
+
+void bits_build_src_mask(cudaStream_t st, const uint4* meta, const int64_t* day_start, const int64_t* day_chunk_start, int64_t n_days,
+                         int64_t max_rows_per_day, uint32_t* src_mask) {
+  if (n_days <= 0) return;
+  const int64_t chunks = (max_rows_per_day + 31) / 32;
+  const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>((chunks + 7) / 8, 1), 4096);
+  const unsigned gy = (unsigned)std::min<int64_t>(n_days, 65535);
+  k_bits_src_mask<<<dim3(gx, gy), 256, 0, st>>>(meta, day_start, day_chunk_start, n_days, src_mask);
+  AMRO_CUDA(cudaGetLastError());
 }
 
 void bits_export_pressure(cudaStream_t st, const uint32_t* pressure, const int64_t* day_seg_start, int64_t n_days, int64_t max_segs,
