@@ -203,32 +203,80 @@ __device__ __forceinline__ void prepare_tables_bits(const BitsShared& sh, const 
     }
   }
 }
-// sum(W) of a ward-day (:95-99) for the 32 simulations of the warp's word: the colonised plane of the states its records
-// [rs, re) (positions within the day) start the day from, counted with a vertical counter -- lane = record while counting,
+// carry-save adder on bit planes: (hi, lo) = a + b + c per simulation
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t u = a ^ b;
+  hi = (a & b) | (u & c);
+  lo = u ^ c;
+}
+// four planes of weight one into a vertical counter: three carry-save adders and a three-plane ripple (11 LOP3 instead of
+// the 40 of four increments); the counter must stay below 32
+__device__ __forceinline__ void vadd4(VCount& vc, const uint32_t (&x)[4]) {
+  static_assert(kCntPlanes == 5, "planes 0..1 take the carry-save sums, planes 2..4 the ripple");
+  uint32_t t0, t1, f;
+  csa(t0, vc.v[0], vc.v[0], x[0], x[1]);
+  csa(t1, vc.v[0], vc.v[0], x[2], x[3]);
+  csa(f, vc.v[1], vc.v[1], t0, t1);
+  const uint32_t c2 = vc.v[2] & f;
+  vc.v[2] ^= f;
+  const uint32_t c3 = vc.v[3] & c2;
+  vc.v[3] ^= c2;
+  vc.v[4] ^= c3;
+}
+
+// sum(W) of ward-days (:95-99) for the 32 simulations of the warp's word: the colonised plane of the states the records
+// [rs, re) (positions within the day) start the day from, counted with vertical counters -- lane = record while counting,
 // lane = simulation in the result.  Records without a source (admitted today) have no state yet: their ring slot holds
-// somebody else's old state and is masked out (src_mask: one bit per record, static).
-__device__ __forceinline__ uint32_t pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, uint32_t rs, uint32_t re, int lane) {
-  VCount vc;
-  vc.clear();
-  uint32_t total = 0u;
-  const uint32_t k1 = (re + 31u) >> 5;
-  uint32_t k = rs >> 5;
-  while (k < k1) {
-    const uint32_t ke = min(k1, k + (uint32_t)kFlushTrips);
-    const uint32_t n = ke - k;
-#pragma unroll 4
-    for (; k < ke; ++k) {
-      const uint32_t pos = k * 32u + (uint32_t)lane;
-      const uint32_t m = __ldg(mask_day + k);
-      const uint32_t x = __ldcg(pre_x + (int64_t)k * (kBW * 32 * 4));
-      vc.add(pos >= rs && pos < re && ((m >> lane) & 1u) ? x : 0u);
+// somebody else's old state and is masked out (src_mask: one bit per record, static).  Four 32-record chunks per step and
+// ward-day (their loads in flight together), seven steps per flush of the counter.
+constexpr int kPullGroup = 4, kPullGroupsPerFlush = 7;
+__device__ __forceinline__ void pull_load(uint32_t (&x)[kPullGroup], const uint32_t* pre_x, const uint32_t* mask_day, uint32_t k, uint32_t k1,
+                                          uint32_t rs, uint32_t re, int lane) {
+#pragma unroll
+  for (int j = 0; j < kPullGroup; ++j) {
+    const uint32_t kk = k + (uint32_t)j, pos = kk * 32u + (uint32_t)lane;
+    x[j] = 0u;
+    if (kk < k1) {   // warp-uniform
+      const uint32_t m = __ldg(mask_day + kk);
+      const uint32_t v = __ldcg(pre_x + (int64_t)kk * (kBW * 32 * 4));   // loaded by every lane of the chunk (no divergent section), then masked
+      x[j] = pos >= rs && pos < re && ((m >> lane) & 1u) ? v : 0u;
     }
-    VCount* const v1[1] = {&vc};
-    uint32_t o[1];
-    vflush<1>(v1, o, lane, n);
-    total += o[0];
   }
-  return total;
+}
+// N ward-days at once: their counters are flushed together (one chain of transposes)
+template <int N>
+__device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, const uint32_t (&rows)[N + 1], uint32_t (&cnt)[N], int lane) {
+  VCount vc[N];
+  uint32_t k[N], k1[N], groups = 0u;
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    vc[u].clear();
+    cnt[u] = 0u;
+    k[u] = rows[u] >> 5; k1[u] = (rows[u + 1] + 31u) >> 5;
+    groups = max(groups, (k1[u] - k[u] + (uint32_t)kPullGroup - 1u) / (uint32_t)kPullGroup);
+  }
+  VCount* vp[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) vp[u] = &vc[u];
+  while (groups > 0u) {
+    const uint32_t g = min(groups, (uint32_t)kPullGroupsPerFlush);
+    for (uint32_t i = 0; i < g; ++i) {
+      uint32_t x[N][kPullGroup];   // all the loads of the step first, then the adders
+#pragma unroll
+      for (int u = 0; u < N; ++u) pull_load(x[u], pre_x, mask_day, k[u], k1[u], rows[u], rows[u + 1], lane);
+#pragma unroll
+      for (int u = 0; u < N; ++u) {
+        vadd4(vc[u], x[u]);
+        k[u] += (uint32_t)kPullGroup;
+      }
+    }
+    groups -= g;
+    uint32_t o[N];
+    VCount* const (&vr)[N] = vp;
+    vflush<N>(vr, o, lane, g * (uint32_t)kPullGroup);
+#pragma unroll
+    for (int u = 0; u < N; ++u) cnt[u] += o[u];
+  }
 }
 
 // What finish_tables_bits needs about the day
@@ -255,14 +303,18 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
     uint32_t rows[3];
     if (lane < 3) rows[0] = (uint32_t)(__ldg(in.seg_rows + min(sl0 + (uint32_t)lane, b1)) - in.da);
     rows[2] = __shfl_sync(0xFFFFFFFFu, rows[0], 2); rows[1] = __shfl_sync(0xFFFFFFFFu, rows[0], 1); rows[0] = __shfl_sync(0xFFFFFFFFu, rows[0], 0);
+    if (sl0 + 1u < b1) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
+    else {   // a single ward-day: its tables are built twice
+      const uint32_t r1[2] = {rows[0], rows[1]};
+      uint32_t c1[1];
+      pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
+      cnt[0] = cnt[1] = c1[0];
+    }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const uint32_t sl = min(sl0 + (uint32_t)u, b1 - 1u);
       slot[u] = (int)(sl & (kBSegs - 1));
-      if (u == 0 || sl0 + 1u < b1) {
-        cnt[u] = pull_pressure(in.pre_x, in.mask_day, rows[u], rows[u + 1], lane);
-        if (in.press_out) in.press_out[(int64_t)sl * (kBW * 32)] = cnt[u];   // every run that touches the ward-day writes the same count
-      } else cnt[u] = cnt[0];
+      if (in.press_out) in.press_out[(int64_t)sl * (kBW * 32)] = cnt[u];   // every run that touches the ward-day writes the same count
       bn[u] = sh.prep_bn[slot[u] * 32 + lane];
       r16[u] = sh.prep_r16[slot[u] * 32 + lane];
     }
