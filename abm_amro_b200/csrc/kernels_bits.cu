@@ -228,10 +228,86 @@ __device__ __forceinline__ void vadd4(VCount& vc, const uint32_t (&x)[4]) {
 // [rs, re) (positions within the day) start the day from, counted with vertical counters -- lane = record while counting,
 // lane = simulation in the result.  Records without a source (admitted today) have no state yet: their ring slot holds
 // somebody else's old state and is masked out (src_mask: one bit per record, static).  Four 32-record chunks per step and
-// ward-day (their loads in flight together), seven steps per flush of the counter.
-constexpr int kPullGroup = 4, kPullGroupsPerFlush = 7;
+// ward-day through the carry-save adders.
+constexpr int kPullGroup = 4;
 __device__ __forceinline__ void pull_load(uint32_t (&x)[kPullGroup], const uint32_t* pre_x, const uint32_t* mask_day, uint32_t k, uint32_t k1,
                                           uint32_t rs, uint32_t re, int lane) {
+  // no branches: chunks past the ward-day's end load its last chunk again and are masked out (pos >= re), so that all the
+  // loads of a step issue back to back and the selects wait once
+  uint32_t m[kPullGroup], v[kPullGroup];
+#pragma unroll
+  for (int j = 0; j < kPullGroup; ++j) {
+    const uint32_t kk = min(k + (uint32_t)j, k1 - 1u);
+    m[j] = __ldg(mask_day + kk);
+    v[j] = __ldcg(pre_x + (int64_t)kk * (kBW * 32 * 4));
+  }
+#pragma unroll
+  for (int j = 0; j < kPullGroup; ++j) {
+    const uint32_t pos = (k + (uint32_t)j) * 32u + (uint32_t)lane;
+    x[j] = pos >= rs && pos < re && ((m[j] >> lane) & 1u) ? v[j] : 0u;
+  }
+}
+// A step of D groups for each of N ward-days: all the loads first (one round trip to L2), then the adders
+template <int N, int D>
+__device__ __forceinline__ void pull_step(VCount (&vc)[N], const uint32_t* pre_x, const uint32_t* mask_day, uint32_t (&k)[N], const uint32_t (&k1)[N],
+                                          const uint32_t (&rows)[N + 1], int lane) {
+  uint32_t x[D][N][kPullGroup];
+#pragma unroll
+  for (int q = 0; q < D; ++q)
+#pragma unroll
+    for (int u = 0; u < N; ++u) pull_load(x[q][u], pre_x, mask_day, k[u] + (uint32_t)(q * kPullGroup), k1[u], rows[u], rows[u + 1], lane);
+#pragma unroll
+  for (int q = 0; q < D; ++q)
+#pragma unroll
+    for (int u = 0; u < N; ++u) vadd4(vc[u], x[q][u]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) k[u] += (uint32_t)(D * kPullGroup);
+}
+// N ward-days at once: their counters are flushed together (one chain of transposes).  Steps of up to kPullDepth groups per
+// ward-day (12 chunks: a whole config-2 ward in one round trip), shorter ones for what is left.
+constexpr int kPullDepth = 3;
+template <int N>
+__device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, const uint32_t (&rows)[N + 1], uint32_t (&cnt)[N], int lane) {
+  VCount vc[N];
+  uint32_t k[N], k1[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    vc[u].clear();
+    cnt[u] = 0u;
+    k[u] = rows[u] >> 5; k1[u] = max((rows[u + 1] + 31u) >> 5, k[u] + 1u);
+  }
+  VCount* vp[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) vp[u] = &vc[u];
+  VCount* const (&vr)[N] = vp;
+  uint32_t n_since = 0u;   // increments since the counters were flushed
+  for (;;) {
+    uint32_t rem = 0u;
+#pragma unroll
+    for (int u = 0; u < N; ++u) rem = max(rem, k1[u] > k[u] ? k1[u] - k[u] : 0u);
+    if (rem == 0u) break;
+    if (rem > 2u * kPullGroup) { pull_step<N, 3>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += 3u * kPullGroup; }
+    else if (rem > (uint32_t)kPullGroup) { pull_step<N, 2>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += 2u * kPullGroup; }
+    else { pull_step<N, 1>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += (uint32_t)kPullGroup; }
+    if (n_since + (uint32_t)(kPullDepth * kPullGroup) > (uint32_t)kFlushTrips) {
+      uint32_t o[N];
+      vflush<N>(vr, o, lane, n_since);
+#pragma unroll
+      for (int u = 0; u < N; ++u) cnt[u] += o[u];
+      n_since = 0u;
+    }
+  }
+  uint32_t o[N];
+  vflush<N>(vr, o, lane, n_since);
+#pragma unroll
+  for (int u = 0; u < N; ++u) cnt[u] += o[u];
+}
+
+// The same count for the instances that run many warps per SM (the 128- and 80-register ones): there the SM is busy with
+// other warps while a load is on its way, and what counts is the number of instructions -- chunks past the ward-day's end
+// are skipped instead of loaded and masked, one group per step (measured: profiles/sweeps.txt).
+__device__ __forceinline__ void pull_load_lean(uint32_t (&x)[kPullGroup], const uint32_t* pre_x, const uint32_t* mask_day, uint32_t k, uint32_t k1,
+                                               uint32_t rs, uint32_t re, int lane) {
 #pragma unroll
   for (int j = 0; j < kPullGroup; ++j) {
     const uint32_t kk = k + (uint32_t)j, pos = kk * 32u + (uint32_t)lane;
@@ -243,9 +319,9 @@ __device__ __forceinline__ void pull_load(uint32_t (&x)[kPullGroup], const uint3
     }
   }
 }
-// N ward-days at once: their counters are flushed together (one chain of transposes)
 template <int N>
-__device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, const uint32_t (&rows)[N + 1], uint32_t (&cnt)[N], int lane) {
+__device__ __forceinline__ void pull_pressure_lean(const uint32_t* pre_x, const uint32_t* mask_day, const uint32_t (&rows)[N + 1], uint32_t (&cnt)[N], int lane) {
+  constexpr uint32_t kGroupsPerFlush = 7;
   VCount vc[N];
   uint32_t k[N], k1[N], groups = 0u;
 #pragma unroll
@@ -258,12 +334,13 @@ __device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint3
   VCount* vp[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) vp[u] = &vc[u];
+  VCount* const (&vr)[N] = vp;
   while (groups > 0u) {
-    const uint32_t g = min(groups, (uint32_t)kPullGroupsPerFlush);
+    const uint32_t g = min(groups, kGroupsPerFlush);
     for (uint32_t i = 0; i < g; ++i) {
-      uint32_t x[N][kPullGroup];   // all the loads of the step first, then the adders
+      uint32_t x[N][kPullGroup];
 #pragma unroll
-      for (int u = 0; u < N; ++u) pull_load(x[u], pre_x, mask_day, k[u], k1[u], rows[u], rows[u + 1], lane);
+      for (int u = 0; u < N; ++u) pull_load_lean(x[u], pre_x, mask_day, k[u], k1[u], rows[u], rows[u + 1], lane);
 #pragma unroll
       for (int u = 0; u < N; ++u) {
         vadd4(vc[u], x[u]);
@@ -272,7 +349,6 @@ __device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint3
     }
     groups -= g;
     uint32_t o[N];
-    VCount* const (&vr)[N] = vp;
     vflush<N>(vr, o, lane, g * (uint32_t)kPullGroup);
 #pragma unroll
     for (int u = 0; u < N; ++u) cnt[u] += o[u];
@@ -288,6 +364,7 @@ struct DayIn {
   uint32_t* press_out;        // nullptr, or where the day's counts go ([ward-day of the day][kBW][32], + lane)
   bool test_h, test_a;
 };
+template <bool DEEP>   // DEEP: the instance that runs two or three CTAs per SM (latency-bound: deep, branch-free pull steps)
 __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const DayIn& in, uint32_t b0, uint32_t b1) {
   const int lane = threadIdx.x & 31;
   const int sim = c.w * 32 + lane;
@@ -303,11 +380,14 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
     uint32_t rows[3];
     if (lane < 3) rows[0] = (uint32_t)(__ldg(in.seg_rows + min(sl0 + (uint32_t)lane, b1)) - in.da);
     rows[2] = __shfl_sync(0xFFFFFFFFu, rows[0], 2); rows[1] = __shfl_sync(0xFFFFFFFFu, rows[0], 1); rows[0] = __shfl_sync(0xFFFFFFFFu, rows[0], 0);
-    if (sl0 + 1u < b1) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
-    else {   // a single ward-day: its tables are built twice
+    if (sl0 + 1u < b1) {
+      if (DEEP) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
+      else pull_pressure_lean<2>(in.pre_x, in.mask_day, rows, cnt, lane);
+    } else {   // a single ward-day: its tables are built twice
       const uint32_t r1[2] = {rows[0], rows[1]};
       uint32_t c1[1];
-      pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
+      if (DEEP) pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
+      else pull_pressure_lean<1>(in.pre_x, in.mask_day, r1, c1, lane);
       cnt[0] = cnt[1] = c1[0];
     }
 #pragma unroll
@@ -388,7 +468,7 @@ struct DayState {
   }
 };
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
-template <int TTD>
+template <int TTD, bool DEEP>
 __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
                                                  int64_t seg0_next, TeamBarrier& bar, const DayState& ds) {
   const int lane = threadIdx.x & 31;
@@ -431,7 +511,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 #ifdef AMRO_EXP_NOTABLES   // timing experiment (wrong results): tables built on the first two days only
       if (d < 2)
 #endif
-      finish_tables_bits(sh, c, in, sl, sl + n_tab);
+      finish_tables_bits<DEEP>(sh, c, in, sl, sl + n_tab);
       __syncwarp();
       const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(in.seg_rows + sl) - da)) - pl.w0;
       const uint32_t re = min(pl.w1, (uint32_t)(__ldg(in.seg_rows + sl + n_tab) - da)) - pl.w0;
@@ -621,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     if (d < 2)
 #endif
     bar.wait();
-    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, ds);
+    process_day_bits<TTD, (MINB < kTeamMinBlocks)>(sh, a, c, d, plan, seg0_next, bar, ds);
     ds.next(a);
     plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
