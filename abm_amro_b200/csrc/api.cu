@@ -804,8 +804,38 @@ void hash_matrix(Hash128& h, const double* m, int64_t rows, int64_t cols, int64_
   else for (int64_t c = 0; c < cols; ++c) hash_dense(h, m + c * ld, (size_t)rows);
 }
 
+// What a call can tell about its tables without reading them: where they are, their shapes, and a sample of their contents
+// (64 bytes out of every ~1/256th).  Two calls with the same quick key almost always pass the same tables -- "almost": the
+// content hash decides, the quick key only picks the hospital a run may START on while the tables are being hashed.
+struct QuickKey {
+  const void* wm = nullptr; const void* tp = nullptr;
+  int64_t dims[6] = {0, 0, 0, 0, 0, 0};
+  Hash128 sample;
+  bool operator==(const QuickKey& o) const {
+    return wm == o.wm && tp == o.tp && std::memcmp(dims, o.dims, sizeof dims) == 0 && sample.a == o.sample.a && sample.b == o.sample.b;
+  }
+};
+void sample_matrix(Hash128& h, const double* m, int64_t rows, int64_t cols, int64_t ld) {
+  const int64_t n = rows * cols;
+  if (n <= 0) return;
+  if (ld != rows || n <= 256 * 8) { for (int64_t c = 0; c < cols; ++c) hash_bytes(h, m + c * ld, sizeof(double) * (size_t)std::min<int64_t>(rows, 64)); return; }
+  const int64_t step = n / 256;
+  for (int64_t i = 0; i + 8 <= n; i += step) hash_bytes(h, m + i, 64);
+  hash_bytes(h, m + n - 8, 64);
+}
+QuickKey quick_key(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K, int64_t t_cols, int64_t t_ld) {
+  QuickKey q;
+  q.wm = wm; q.tp = tp;
+  const int64_t d[6] = {R, w_cols, w_ld, K, t_cols, t_ld};
+  std::memcpy(q.dims, d, sizeof d);
+  sample_matrix(q.sample, wm, R, w_cols, w_ld);
+  sample_matrix(q.sample, tp, K, t_cols, t_ld);
+  return q;
+}
+
 struct CachedTopology {
   Hash128 key;
+  QuickKey quick;                         // of the call that last used the entry
   int64_t n_init = 0;
   int device = -1;
   uint64_t stamp = 0;
@@ -852,18 +882,14 @@ void enforce_cache_budget(const CachedTopology* keep) {
 
 // Returns a reference to a compiled hospital held by the cache.  The lookup key is the CONTENT of the two tables (a caller
 // that edits its arrays in place gets a new topology), n_init and the device.
-std::shared_ptr<amro_topology> cached_topology(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K,
-                                               int64_t t_cols, int64_t t_ld, int64_t n_init, int device) {
-  Hash128 key;
-  Timer th;
-  hash_matrix(key, wm, R, w_cols, w_ld);
-  hash_matrix(key, tp, K, t_cols, t_ld);
-  if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] cache key of %lld + %lld rows hashed in %.3f ms\n", (long long)R, (long long)K, th.ms());
+std::shared_ptr<amro_topology> lookup_or_compile(const Hash128& key, const QuickKey& quick, const double* wm, int64_t R, int64_t w_cols, int64_t w_ld,
+                                                 const double* tp, int64_t K, int64_t t_cols, int64_t t_ld, int64_t n_init, int device) {
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     for (auto& c : g_cache)
       if (c.t && c.key.a == key.a && c.key.b == key.b && c.n_init == n_init && c.device == device) {
         c.stamp = ++g_cache_clock;
+        c.quick = quick;
         ++g_cache_hits;
         return c.t;
       }
@@ -884,9 +910,55 @@ std::shared_ptr<amro_topology> cached_topology(const double* wm, int64_t R, int6
     if (!c.t) { slot = &c; break; }
     if (c.stamp < slot->stamp) slot = &c;
   }
-  *slot = CachedTopology{key, n_init, device, ++g_cache_clock, 0, t};
+  *slot = CachedTopology{key, quick, n_init, device, ++g_cache_clock, 0, t};
   enforce_cache_budget(slot);
   return t;
+}
+Hash128 content_key(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K, int64_t t_cols, int64_t t_ld) {
+  Hash128 key;
+  Timer th;
+  hash_matrix(key, wm, R, w_cols, w_ld);
+  hash_matrix(key, tp, K, t_cols, t_ld);
+  if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] cache key of %lld + %lld rows hashed in %.3f ms\n", (long long)R, (long long)K, th.ms());
+  return key;
+}
+
+// run(topology) on the cached hospital of these tables.  Hashing 175 MB of tables takes as long as the run it guards, so a call
+// whose QUICK key (pointers, shapes, a sample of the contents) matches a cached hospital starts the run on that hospital at once
+// and hashes the tables on other threads meanwhile; the content hash has the last word: if it differs (the tables were edited
+// in place where the sample did not look) the speculative results are thrown away and the run is repeated on the right hospital.
+template <class Run>
+void run_on_cached(const double* wm, int64_t R, int64_t w_cols, int64_t w_ld, const double* tp, int64_t K, int64_t t_cols, int64_t t_ld,
+                   int64_t n_init, int device, Run run) {
+  const QuickKey quick = quick_key(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld);
+  std::shared_ptr<amro_topology> cand;
+  Hash128 cand_key;
+  if (!std::getenv("AMRO_CACHE_NO_SPECULATION")) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto& c : g_cache)
+      if (c.t && c.quick == quick && c.n_init == n_init && c.device == device) { cand = c.t; cand_key = c.key; break; }
+  }
+  if (cand) {
+    Hash128 full;
+    std::thread hasher([&] { full = content_key(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld); });
+    std::exception_ptr err;
+    try { run(cand); } catch (...) { err = std::current_exception(); }
+    hasher.join();
+    if (full.a == cand_key.a && full.b == cand_key.b) {
+      {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        for (auto& c : g_cache) if (c.t == cand) c.stamp = ++g_cache_clock;
+        ++g_cache_hits;
+      }
+      if (err) std::rethrow_exception(err);
+      return;
+    }
+    cand.reset();   // the tables changed under the same pointers: whatever the speculative run wrote is overwritten below
+    run(lookup_or_compile(full, quick, wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device));
+    return;
+  }
+  const Hash128 full = content_key(wm, R, w_cols, w_ld, tp, K, t_cols, t_ld);
+  run(lookup_or_compile(full, quick, wm, R, w_cols, w_ld, tp, K, t_cols, t_ld, n_init, device));
 }
 
 // amro_simulate on a cached hospital; on a CUDA failure (typically out of memory: the workspaces of other cached hospitals
@@ -977,20 +1049,20 @@ extern "C" int amro_simulate_discrete_model(const double* icp, int64_t i_rows, i
     if (d_rows != i_rows) fail(AMRO_ERUNTIME, "element-wise multiplication: incompatible matrix dimensions: %lldx%lld and %lldx%lld",
                                (long long)d_rows, (long long)S, (long long)i_rows, (long long)S);
     if (p_cols < 6) fail(AMRO_EINDEX, "Mat::operator(): index out of bounds");
-    const std::shared_ptr<amro_topology> topo = cached_topology(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device);
-    amro_sim_args a{};
-    a.n_sims = S; a.sim_offset = 0; a.time_to_detect = time_to_detect;
-    a.testing_schedule_hospitalized = tsh; a.testing_schedule_arrivals = tsa; a.seed = seed;
-    a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 1;
-    a.parameters = parameters; a.p_rows = p_rows; a.p_ld = p_ld;
-    a.icp = icp; a.icp_rs = 1; a.icp_cs = i_ld;
-    a.idp = idp; a.idp_rs = 1; a.idp_cs = d_ld;
-    a.state_out = out + 6 * R; a.so_ld = R;
-    simulate_cached(topo, a);
-    {   // the packed trajectory (2 bytes per record and simulation) is of no use to the next call: give it back
+    run_on_cached(ward_matrix, R, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, i_rows, device, [&](const std::shared_ptr<amro_topology>& topo) {
+      amro_sim_args a{};
+      a.n_sims = S; a.sim_offset = 0; a.time_to_detect = time_to_detect;
+      a.testing_schedule_hospitalized = tsh; a.testing_schedule_arrivals = tsa; a.seed = seed;
+      a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 1;
+      a.parameters = parameters; a.p_rows = p_rows; a.p_ld = p_ld;
+      a.icp = icp; a.icp_rs = 1; a.icp_cs = i_ld;
+      a.idp = idp; a.idp_rs = 1; a.idp_cs = d_ld;
+      a.state_out = out + 6 * R; a.so_ld = R;
+      simulate_cached(topo, a);
+      // the packed trajectory (2 bytes per record and simulation) is of no use to the next call: give it back
       std::lock_guard<std::mutex> lock(topo->mu);
       topo->ws_traj.release();
-    }
+    });
     for (int64_t c = 0; c < 6; ++c) std::memcpy(out + c * R, ward_matrix + c * w_ld, sizeof(double) * (size_t)R);  // :375
   });
 }
@@ -1008,22 +1080,25 @@ void collapse_impl(const double* ward_matrix, int64_t n_rows, int64_t w_cols, in
   if (n_rows < 1 || w_cols < 1) fail(AMRO_ERUNTIME, "max(): object has no elements");
   const int64_t S = n_sims;
   if (S < 1) fail(AMRO_EINDEX, "Mat::submat(): indices out of bounds or incorrectly used");
-  const std::shared_ptr<amro_topology> topo = cached_topology(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device);
-  const int64_t Dd = topo->H.n_days_out;
+  int64_t Dd = 0;
   std::vector<double> par((size_t)(S * 6));
   const double v[6] = {alpha, beta, gamma, rho_hospital, alpha2, rho_imported};
   for (int c = 0; c < 6; ++c) for (int64_t s = 0; s < S; ++s) par[s + S * c] = v[c];     // :584-590
-  std::vector<int32_t> cc((size_t)(Dd * S)), cd((size_t)(Dd * S));
-  amro_sim_args a{};
-  a.n_sims = S; a.time_to_detect = (int)time_to_detect;                                    // uword -> const int& (:606-608)
-  a.testing_schedule_hospitalized = (int)tsh; a.testing_schedule_arrivals = (int)tsa; a.seed = seed;
-  a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 0;
-  a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
-  a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
-  a.counts_colonized = cc.data(); a.counts_detected = cd.data();
-  Timer ts;
-  simulate_cached(topo, a);
-  if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] simulate_and_collapse: run %.3f ms (kernel %.3f)\n", ts.ms(), a.kernel_ms);
+  std::vector<int32_t> cc, cd;
+  run_on_cached(ward_matrix, n_rows, w_cols, w_ld, tppw, t_rows, t_cols, t_ld, initial_patients, device, [&](const std::shared_ptr<amro_topology>& topo) {
+    Dd = topo->H.n_days_out;
+    cc.assign((size_t)(Dd * S), 0); cd.assign((size_t)(Dd * S), 0);
+    amro_sim_args a{};
+    a.n_sims = S; a.time_to_detect = (int)time_to_detect;                                    // uword -> const int& (:606-608)
+    a.testing_schedule_hospitalized = (int)tsh; a.testing_schedule_arrivals = (int)tsa; a.seed = seed;
+    a.rng_mode = AMRO_RNG_PHILOX; a.path = AMRO_PATH_AUTO; a.keep_trajectory = 0;
+    a.parameters = par.data(); a.p_rows = S; a.p_ld = S;
+    a.icp = &icp; a.idp = &idp;                                                              // scalar broadcast (:593-597)
+    a.counts_colonized = cc.data(); a.counts_detected = cd.data();
+    Timer ts;
+    simulate_cached(topo, a);
+    if (std::getenv("AMRO_FAST_VERBOSE")) std::fprintf(stderr, "[amro] simulate_and_collapse: run %.3f ms (kernel %.3f)\n", ts.ms(), a.kernel_ms);
+  });
   double* out = alloc(Dd, ctx);
   if (!out) fail(AMRO_ERUNTIME, "simulate_and_collapse: no result buffer");
   std::vector<double> mc(Dd), md(Dd), sc(Dd), sd(Dd);

@@ -465,6 +465,35 @@ def test_compiled_hospital_cache_of_the_one_call_entry_points():
     assert capi.cache_stats()["entries"] == 0
 
 
+def test_cache_speculation_never_trusts_the_quick_key():
+    # A call whose quick key (pointers, shapes, a 1/256th sample of the contents) matches a cached hospital starts its run on that
+    # hospital while the tables are hashed; the content hash decides.  One edited cell that the sample cannot see must still be
+    # simulated: the speculative results are thrown away and the run is repeated on the newly compiled hospital.
+    from abm_amro_b200 import amro
+    amro.clear_cache()
+    base = capi.cache_stats()
+    wm, tp, n_init = synth.make_hospital(6, 400, 20, seed=8)   # 8000 rows x 6 columns: the sample reads 8 doubles out of every 187
+    args = (0.2, 0.3, n_init, .15, .55, .05, .6, .35, .9, 32, 2, 7, 1, 9)
+    a = amro.simulate_and_collapse(wm, tp, *args)
+    b = amro.simulate_and_collapse(wm, tp, *args)               # same arrays again: speculative run, confirmed by the hash
+    s = capi.cache_stats()
+    assert (s["misses"] - base["misses"], s["hits"] - base["hits"]) == (1, 1) and np.array_equal(a, b)
+    R = wm.shape[0]
+    step = (R * 6) // 256
+    flat = 3 * R + 5 * 400 + 100                                 # is_new of a day-5 record ...
+    while flat % step < 8 or flat >= 6 * R - 8:                  # ... that is not among the sampled doubles
+        flat += 1
+    r, c = flat % R, flat // R
+    assert c == 3
+    wm[r, c] = 1.0 - wm[r, c]                                    # in place, same pointer, same shape, same sample
+    e = amro.simulate_and_collapse(wm, tp, *args)
+    s = capi.cache_stats()
+    assert s["misses"] - base["misses"] == 2 and s["entries"] == 2
+    ref = oracle.simulate_and_collapse(wm, tp, *args, rng=oracle.Rng(oracle.RNG_PHILOX))
+    assert np.array_equal(e, ref) and not np.array_equal(e, a)
+    amro.clear_cache()
+
+
 # ---- hospitals generated on the device against the host compiler and the oracle ---------------------------
 @pytest.mark.parametrize("shape", [(5, 300, 12), (40, 100, 8), (3, 2000, 5), (1, 33, 3)], ids=lambda s: "x".join(map(str, s)))
 def test_device_generated_hospital_matches_host_compile_and_oracle(shape):
