@@ -409,6 +409,42 @@ def test_benchmarked_launch_shapes_match_the_oracle(name):
             assert np.array_equal(got.counts_detected[:, off:off + 32], det), f"{name}: detected counts of members {off}.. differ"
 
 
+@pytest.mark.parametrize("members,instance", [(96, "roomy"), (30_016, "team")])
+def test_large_wards_are_counted_in_several_flushes(members, instance):
+    # The bit-sliced kernel PULLS a ward-day's pressure: it counts the colonised plane of the ward-day's records with a vertical
+    # counter that holds 31, flushed as often as the ward is long.  Two wards of ~1500 records (47 chunks of 32) need several flushes
+    # in both variants of the count: deep branch-free steps (the roomy instance: few CTAs) and lean groups (the 128-register
+    # instance: more teams than three CTAs per SM).  Ward pressures and day totals against the oracle, bit for bit.
+    wm, tp, n_init = synth.make_hospital(2, 3000, 6, seed=5)
+    par = synth.particle_parameters(members, seed=3)
+    with engine.Topology(wm, tp, n_init) as topo:
+        got = topo.simulate(par, 0.2, 0.2, 2, 3, 1, 77, want_pressure=True)
+        assert got.kernel_kind == capi.KERNEL_BITS
+        assert (got.grid <= 3 * 148) == (instance == "roomy")
+        for off in (0, members - 32):
+            ref = oracle.simulate_discrete_model(np.full((n_init, 32), 0.2), np.full((n_init, 32), 0.2), wm, tp, par[off:off + 32], 2, 3, 1, 77,
+                                                 rng=oracle.Rng(oracle.RNG_PHILOX, sim_offset=off))
+            day = wm[:, 0].astype(int)
+            col = np.stack([np.bincount(day, weights=(ref[:, 6 + s] == 1), minlength=6) for s in range(32)], 1)
+            det = np.stack([np.bincount(day, weights=(ref[:, 38 + s] <= 0), minlength=6) for s in range(32)], 1)
+            assert np.array_equal(got.counts_colonized[:, off:off + 32], col) and np.array_equal(got.counts_detected[:, off:off + 32], det)
+        # the exported pressure = colonised patients every ward-day STARTS with: day 0 from the initial state, later days = what the
+        # ward's records carried over; compared with the count of the oracle's previous-day states through the links
+        nxt = wm[:, 5].astype(np.int64)
+        seg = {}
+        for i, (d, w) in enumerate(tp[:, :2]):
+            seg[(int(d), int(w))] = i
+        ref = oracle.simulate_discrete_model(np.full((n_init, 32), 0.2), np.full((n_init, 32), 0.2), wm, tp, par[:32], 2, 3, 1, 77,
+                                             rng=oracle.Rng(oracle.RNG_PHILOX, sim_offset=0))
+        want = np.zeros((tp.shape[0], 32), dtype=np.int64)
+        src = np.nonzero(nxt >= 0)[0]
+        for r in src:
+            t = nxt[r]
+            want[seg[(int(wm[t, 0]), int(wm[t, 1]))]] += (ref[r, 6:38] == 1)
+        later = tp[:, 0] > 0
+        assert np.array_equal(got.pressure[later, :32].astype(np.int64), want[later])
+
+
 def test_ward_sized_ensemble_matches_reference_mean_and_variance(golden):
     # The daily draws of one ward-day and simulation share a threshold dither (rng.cuh): marginals are exact, and the joint law
     # is argued to be over-dispersed by at most n * 2^-14.  This checks it where it matters: wards of config 2's size (333
