@@ -4,7 +4,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 
 #include "common.hpp"
@@ -30,6 +33,32 @@ struct PairHash {
 };
 
 constexpr int64_t kMaxDays = 10'000'000;
+
+// Hospitals of millions of rows are compiled by a few threads: every phase below that is a loop over rows or positions is cut
+// into contiguous blocks (results do not depend on the number of threads).  AMRO_COMPILE_THREADS caps the threads (1 = serial),
+// AMRO_COMPILE_PAR_MIN_ROWS sets the size below which one thread does everything (tests force the threaded path with it).
+int compile_threads(int64_t n) {
+  const char* e_min = std::getenv("AMRO_COMPILE_PAR_MIN_ROWS");
+  const char* e_cap = std::getenv("AMRO_COMPILE_THREADS");
+  const int64_t min_rows = e_min ? std::atoll(e_min) : (int64_t)200'000;
+  const int cap = e_cap ? std::max(1, std::atoi(e_cap)) : 16;
+  if (n < std::max<int64_t>(min_rows, 2)) return 1;
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(hw, cap), n / 2));
+}
+// f(lo, hi, block) on n_thr contiguous blocks of [0, n); exceptions of a block are rethrown (the first block's first)
+template <class F>
+void parallel_blocks(int64_t n, int n_thr, F f) {
+  if (n_thr <= 1) { f((int64_t)0, n, 0); return; }
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> err((size_t)n_thr);
+  for (int t = 0; t < n_thr; ++t)
+    pool.emplace_back([&, t] {
+      try { f(n * t / n_thr, n * (t + 1) / n_thr, t); } catch (...) { err[(size_t)t] = std::current_exception(); }
+    });
+  for (auto& th : pool) th.join();
+  for (auto& e : err) if (e) std::rethrow_exception(e);
+}
 
 // integer-valued, in [0, limit] -> the integer; else -1   (the reference compares `col == day` with an
 // unsigned loop counter converted to double, abm_wards.cpp:384,387,447)
@@ -68,45 +97,84 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   T.h.resize(R);
   T.w.resize(R);
   T.count_day.assign(R, -1);
+  const int n_thr = compile_threads(R);
   double cmax = R ? at(wm, ld, 0, 0) : 0.0;
-  for (int64_t r = 0; r < R; ++r) cmax = std::max(cmax, at(wm, ld, r, 0));
+  {
+    std::vector<double> part((size_t)n_thr, cmax);
+    parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int t) {
+      double m = part[(size_t)t];
+      for (int64_t r = lo; r < hi; ++r) m = std::max(m, at(wm, ld, r, 0));
+      part[(size_t)t] = m;
+    });
+    for (double m : part) cmax = std::max(cmax, m);
+  }
   if (!(cmax >= 0.0) || cmax > (double)kMaxDays)
     fail(AMRO_EINVAL, "ward_matrix: largest day must be in [0, %lld]", (long long)kMaxDays);
   T.n_days_out = (int64_t)cmax + 1;
+  // Sortedness: the stepped rows, in row order, must not go back in (day, ward), and no stepped row may follow a row that is
+  // never stepped.  Every block reports its own verdict and its first / last stepped row; the blocks are stitched afterwards.
+  struct Block {
+    int64_t n_stepped = 0, first_unstepped = -1, last_stepped = -1, nan_row = -1;
+    bool ordered = true, unit = true, dyadic = true, half = false, binary_h = true;
+    int64_t first_day = -1, last_day = -1;
+    double first_ward = 0.0, last_ward = 0.0;
+  };
+  std::vector<Block> blocks((size_t)n_thr);
+  parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int t) {
+    Block b;
+    for (int64_t r = lo; r < hi; ++r) {
+      const double dv = at(wm, ld, r, 0), wv = at(wm, ld, r, 1);
+      const int64_t d = as_day(dv, T.total_days);
+      row_day[r] = d;
+      T.count_day[r] = (int32_t)as_day(dv, T.n_days_out - 1);
+      T.h[r] = at(wm, ld, r, 3);
+      T.w[r] = at(wm, ld, r, 4);
+      if (d >= 0) {
+        if (wv != wv) { if (b.nan_row < 0) b.nan_row = r; continue; }
+        if (b.last_stepped >= 0) {
+          if (d < b.last_day || (d == b.last_day && wv < b.last_ward)) b.ordered = false;
+        } else { b.first_day = d; b.first_ward = wv; }
+        b.last_stepped = r; b.last_day = d; b.last_ward = wv;
+        b.n_stepped++;
+        if (T.w[r] != 1.0) b.unit = false;
+        if (T.w[r] == 0.5) b.half = true;
+        else if (T.w[r] != 1.0) b.dyadic = false;
+        if (!(T.h[r] == 0.0 || T.h[r] == 1.0)) b.binary_h = false;
+      } else if (b.first_unstepped < 0) {
+        b.first_unstepped = r;
+      }
+    }
+    blocks[(size_t)t] = b;
+  });
   bool sorted = true;
   T.unit_weights = true;
   T.dyadic_weights = true;
   T.binary_h = true;
-  int64_t prev_day = -1;
-  double prev_ward = 0.0;
-  bool seen_unstepped = false;
-  for (int64_t r = 0; r < R; ++r) {
-    const double dv = at(wm, ld, r, 0), wv = at(wm, ld, r, 1);
-    const int64_t d = as_day(dv, T.total_days);
-    row_day[r] = d;
-    T.count_day[r] = (int32_t)as_day(dv, T.n_days_out - 1);
-    T.h[r] = at(wm, ld, r, 3);
-    T.w[r] = at(wm, ld, r, 4);
-    if (d >= 0) {
-      if (wv != wv) fail(AMRO_EINVAL, "ward_matrix: NaN ward identifier in row %lld", (long long)r);
-      if (seen_unstepped || d < prev_day || (d == prev_day && wv < prev_ward)) sorted = false;
-      prev_day = d;
-      prev_ward = wv;
-      T.Rp++;
-      if (T.w[r] != 1.0) T.unit_weights = false;
-      if (T.w[r] == 0.5) T.has_half = true;
-      else if (T.w[r] != 1.0) T.dyadic_weights = false;
-      if (!(T.h[r] == 0.0 || T.h[r] == 1.0)) T.binary_h = false;
-    } else {
-      seen_unstepped = true;
+  {
+    int64_t first_unstepped = -1, last_stepped = -1, prev_day = -1;
+    double prev_ward = 0.0;
+    for (const Block& b : blocks) {
+      if (b.nan_row >= 0) fail(AMRO_EINVAL, "ward_matrix: NaN ward identifier in row %lld", (long long)b.nan_row);
+      T.Rp += b.n_stepped;
+      if (!b.unit) T.unit_weights = false;
+      if (!b.dyadic) T.dyadic_weights = false;
+      if (b.half) T.has_half = true;
+      if (!b.binary_h) T.binary_h = false;
+      if (!b.ordered) sorted = false;
+      if (b.last_stepped >= 0) {
+        if (last_stepped >= 0 && (b.first_day < prev_day || (b.first_day == prev_day && b.first_ward < prev_ward))) sorted = false;
+        last_stepped = b.last_stepped; prev_day = b.last_day; prev_ward = b.last_ward;
+      }
+      if (first_unstepped < 0 && b.first_unstepped >= 0) first_unstepped = b.first_unstepped;
     }
+    if (first_unstepped >= 0 && last_stepped > first_unstepped) sorted = false;
   }
   T.identity_order = sorted;
 
   // ---- visiting order: (day, ward, original index), never-stepped rows last ------------------------
   T.order.resize(R);
   if (sorted) {
-    std::iota(T.order.begin(), T.order.end(), (int64_t)0);
+    parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int) { for (int64_t r = lo; r < hi; ++r) T.order[r] = r; });
   } else {
     int64_t a = 0, b = T.Rp;
     for (int64_t r = 0; r < R; ++r) {
@@ -118,7 +186,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
     });
   }
   T.pos_of.resize(R);
-  for (int64_t p = 0; p < R; ++p) T.pos_of[T.order[p]] = p;
+  parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int) { for (int64_t p = lo; p < hi; ++p) T.pos_of[T.order[p]] = p; });
 
   // ---- first tppw row of every (day, ward)   (abm_wards.cpp:384 then :242,249) ---------------------
   std::unordered_map<std::pair<uint64_t, uint64_t>, int64_t, PairHash> first_row;
@@ -171,14 +239,88 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   // C/D columns of row trunc(next_day); a later source wins.  A stepped row therefore starts its own day
   // from the last write made on an EARLIER day (or its initial state), and a write made on its own or a
   // later day only changes what the returned matrix shows for it.
-  struct Written { int64_t writer, day; };   // last source row and the day it wrote on: one cache line per target
-  std::vector<Written> written(R, Written{-1, -1});
   std::vector<int64_t> pre_src(T.Rp, -1);  // original row of the effective predecessor
-  T.push_src.reserve((size_t)T.Rp);
-  T.push_dst.reserve((size_t)T.Rp);
   T.day_push_start.assign(D + 1, 0);
   T.simple_final = (T.Rp == R);
   bool ring = true;
+  // Threaded pass for the ordinary hospital -- no row is the target of two links: then every link is its day's winner, a
+  // stepped target's predecessor is its one source if that source lives on an earlier day, and the push list of a day is its
+  // links in ascending source order.  Anything else (several sources for one row) takes the sequential pass below, which
+  // replays the reference's order of writes.
+  bool links_done = false;
+  if (n_thr > 1) {
+    std::vector<int64_t> target(T.Rp, -1);                       // per position: the row its record writes to, or -1
+    std::vector<std::atomic<uint32_t>> n_src((size_t)R);         // per row: links that point to it
+    std::vector<int64_t> src_of((size_t)R, -1);                  // per row: its source (meaningful where n_src == 1)
+    parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int) { for (int64_t r = lo; r < hi; ++r) n_src[(size_t)r].store(0u, std::memory_order_relaxed); });
+    std::atomic<int64_t> bad_pos{INT64_MAX};
+    std::atomic<bool> multi{false};
+    parallel_blocks(T.Rp, n_thr, [&](int64_t lo, int64_t hi, int) {
+      for (int64_t p = lo; p < hi; ++p) {
+        const int64_t r = T.order[p];
+        const double nd = at(wm, ld, r, 5);
+        if (!(nd > 0.0)) continue;
+        if (!(nd < 18446744073709551616.0) || (uint64_t)nd >= (uint64_t)R) {
+          int64_t cur = bad_pos.load(std::memory_order_relaxed);
+          while (p < cur && !bad_pos.compare_exchange_weak(cur, p, std::memory_order_relaxed)) {}
+          continue;
+        }
+        const int64_t t = (int64_t)(uint64_t)nd;
+        target[p] = t;
+        if (n_src[(size_t)t].fetch_add(1u, std::memory_order_relaxed) != 0u) multi.store(true, std::memory_order_relaxed);
+        src_of[(size_t)t] = r;
+      }
+    });
+    // (an out-of-range link: the sequential pass reports the first one in the reference's order of writes)
+    if (!multi.load() && bad_pos.load() == INT64_MAX) {
+      std::vector<int64_t> n_push((size_t)D, 0);
+      std::atomic<bool> not_final{false}, not_ring{false};
+      parallel_blocks(D, std::min<int64_t>(n_thr, std::max<int64_t>(D, 1)), [&](int64_t dlo, int64_t dhi, int) {
+        for (int64_t d = dlo; d < dhi; ++d) {
+          int64_t n = 0;
+          for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
+            const int64_t src = src_of[(size_t)T.order[p]];
+            if (src >= 0 && row_day[src] >= 0 && row_day[src] < d) {   // written on an earlier day: this is what the row starts from
+              pre_src[p] = src;
+              if (row_day[src] != d - 1) not_ring.store(true, std::memory_order_relaxed);
+            }
+            const int64_t t = target[p];
+            if (t >= 0) {
+              ++n;
+              if (row_day[t] < 0 || row_day[t] <= d) not_final.store(true, std::memory_order_relaxed);
+            }
+          }
+          n_push[(size_t)d] = n;
+        }
+      });
+      for (int64_t d = 0; d < D; ++d) T.day_push_start[d + 1] = T.day_push_start[d] + n_push[(size_t)d];
+      T.push_src.resize((size_t)T.day_push_start[D]);
+      T.push_dst.resize((size_t)T.day_push_start[D]);
+      parallel_blocks(D, std::min<int64_t>(n_thr, std::max<int64_t>(D, 1)), [&](int64_t dlo, int64_t dhi, int) {
+        std::vector<std::pair<int64_t, int64_t>> ev;
+        for (int64_t d = dlo; d < dhi; ++d) {
+          int64_t q = T.day_push_start[d];
+          if (sorted) {
+            for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p)
+              if (target[p] >= 0) { T.push_src[(size_t)q] = T.order[p]; T.push_dst[(size_t)q] = target[p]; ++q; }
+          } else {   // positions of a day are in (ward, row) order; the reference writes in row order
+            ev.clear();
+            for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) if (target[p] >= 0) ev.emplace_back(T.order[p], target[p]);
+            std::sort(ev.begin(), ev.end());
+            for (const auto& e : ev) { T.push_src[(size_t)q] = e.first; T.push_dst[(size_t)q] = e.second; ++q; }
+          }
+        }
+      });
+      if (not_final.load()) T.simple_final = false;
+      if (not_ring.load()) ring = false;
+      links_done = true;
+    }
+  }
+  if (!links_done) {
+  struct Written { int64_t writer, day; };   // last source row and the day it wrote on: one cache line per target
+  std::vector<Written> written(R, Written{-1, -1});
+  T.push_src.reserve((size_t)T.Rp);
+  T.push_dst.reserve((size_t)T.Rp);
   std::vector<int64_t> ev;
   for (int64_t d = 0; d < D; ++d) {
     const int64_t a = T.day_start[d], b = T.day_start[d + 1];
@@ -211,6 +353,7 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
     std::reverse(T.push_dst.begin() + base, T.push_dst.end());
   }
   T.day_push_start[D] = (int64_t)T.push_src.size();
+  }
 
   // ---- FAST path encodings ------------------------------------------------------------------------------
   T.why_not_fast.clear();
@@ -243,28 +386,39 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
           if (it != seg_of.end()) T.seg_main_next[sg] = it->second;
         }
     }
-    for (int64_t d = 0; d < D; ++d) {
-      for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
-        const int64_t r = T.order[p];
-        const uint32_t seg_local = seg_of_pos[p] - (uint32_t)T.day_seg_start[d];
-        uint32_t kind = kSrcNone;
-        if (pre_src[p] >= 0) {
-          kind = kSrcPrev;
+    // two passes over the positions (blocks of days): what a record says about itself, then what its successor adds to it --
+    // a record has one successor, so no two positions write the same predecessor
+    std::atomic<bool> init_late{false};
+    const int n_day_thr = (int)std::min<int64_t>(n_thr, std::max<int64_t>(D, 1));
+    parallel_blocks(D, n_day_thr, [&](int64_t dlo, int64_t dhi, int) {
+      for (int64_t d = dlo; d < dhi; ++d)
+        for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
+          const int64_t r = T.order[p];
+          const uint32_t seg_local = seg_of_pos[p] - (uint32_t)T.day_seg_start[d];
+          uint32_t kind = kSrcNone;
+          if (pre_src[p] >= 0) kind = kSrcPrev;
+          else if (r < n_init) {
+            kind = kSrcInit;
+            if (d != 0) init_late.store(true, std::memory_order_relaxed);
+            T.init_seg[r] = seg_of_pos[p];
+            T.init_slot[r] = (uint32_t)(p - T.day_start[d]);
+            T.day_has_init[d] = 1;
+          }
+          T.meta_info[p] = (T.h[r] == 1.0 ? (1u << kInfoHShift) : 0u) | (kind << kInfoSrcShift) |
+                           (T.w[r] == 0.5 ? (1u << kInfoHalfShift) : 0u) | seg_local;
+        }
+    });
+    parallel_blocks(D, n_day_thr, [&](int64_t dlo, int64_t dhi, int) {
+      for (int64_t d = dlo; d < dhi; ++d)
+        for (int64_t p = T.day_start[d]; p < T.day_start[d + 1]; ++p) {
+          if (pre_src[p] < 0) continue;
           const int64_t pp = T.pos_of[pre_src[p]];  // in day d-1 (ring property)
           T.meta_next[pp] = (uint32_t)(p - T.day_start[d]);
           T.meta_nseg[pp] = seg_of_pos[p];
-          if (T.w[r] == 0.5) T.meta_info[pp] |= 1u << kInfoNextHalfShift;   // what pp's state adds to this ward-day's sum(W) is w of THIS row
-        } else if (r < n_init) {
-          kind = kSrcInit;
-          if (d != 0) T.why_not_fast = "initial-state rows outside day 0";
-          T.init_seg[r] = seg_of_pos[p];
-          T.init_slot[r] = (uint32_t)(p - T.day_start[d]);
-          T.day_has_init[d] = 1;
+          if (T.w[T.order[p]] == 0.5) T.meta_info[pp] |= 1u << kInfoNextHalfShift;   // what pp's state adds to this ward-day's sum(W) is w of THIS row
         }
-        T.meta_info[p] = (T.h[r] == 1.0 ? (1u << kInfoHShift) : 0u) | (kind << kInfoSrcShift) |
-                         (T.w[r] == 0.5 ? (1u << kInfoHalfShift) : 0u) | seg_local;
-      }
-    }
+    });
+    if (init_late.load()) T.why_not_fast = "initial-state rows outside day 0";
   }
   T.fast_eligible = T.why_not_fast.empty();
   if (!T.fast_eligible) {

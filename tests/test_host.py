@@ -88,6 +88,40 @@ def test_topology_compiler_on_a_synthetic_hospital():
         assert np.array_equal(t.debug_arrays()["seg_N"], a["seg_N"])
 
 
+@pytest.mark.parametrize("kind", ["sorted", "shuffled", "exotic"])
+def test_threaded_compile_gives_the_arrays_of_the_serial_one(monkeypatch, kind):
+    # hospitals of millions of rows are compiled by up to 16 threads (topology.cpp: blocks of rows / days); every array must be
+    # what one thread produces -- sorted input, shuffled rows, and links with several sources per row (sequential fallback)
+    wm, tp, n_init = synth.make_hospital(5, 300, 14, seed=21, p_split=0.1)
+    rng = np.random.default_rng(4)
+    R = wm.shape[0]
+    if kind != "sorted":
+        perm = rng.permutation(R)
+        inv = np.empty(R, dtype=np.int64)
+        inv[perm] = np.arange(R)
+        wm = wm[perm].copy(order="F")
+        nd = wm[:, 5].astype(np.int64)
+        nd[nd >= 0] = inv[nd[nd >= 0]]
+        wm[:, 5] = nd
+    if kind == "exotic":
+        idx = rng.integers(0, R, size=R // 25)
+        wm[idx, 5] = rng.integers(0, R, size=idx.size)
+        wm[rng.integers(0, R, size=5), 0] += 0.5
+    got = {}
+    for name, env in (("serial", {"AMRO_COMPILE_THREADS": "1"}), ("threads", {"AMRO_COMPILE_PAR_MIN_ROWS": "1", "AMRO_COMPILE_THREADS": "5"})):
+        for k in ("AMRO_COMPILE_THREADS", "AMRO_COMPILE_PAR_MIN_ROWS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with engine.Topology(wm, tp, n_init, device=-1) as t:
+            i = t.info
+            got[name] = (t.debug_arrays(), (i.n_rows_stepped, i.n_segments, i.max_rows_per_day, i.fast_eligible, i.identity_order, bytes(i.why_not_fast)))
+    assert got["serial"][1] == got["threads"][1]
+    for k, v in got["serial"][0].items():
+        w = got["threads"][0][k]
+        assert (v is None) == (w is None) and (v is None or np.array_equal(v, w)), k
+
+
 def test_topology_compiler_sorts_like_the_reference_visits():
     wm, tp, n_init = synth.make_hospital(3, 30, 6, seed=5)
     g = np.random.default_rng(0)
