@@ -534,6 +534,14 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.pre = T->ws_pre.p; f.traj = nullptr;
   f.pressure = A->pressure_out ? T->ws_pressure.p : nullptr;
   f.src_mask = T->src_mask.p; f.day_chunk_start = T->day_chunk_start.p;
+  {
+    // Counting a ward's pressure: deep branch-free steps (12 chunks per ward-day in one round trip) where the launch is bound by
+    // latency -- few warps per SM (config 2: 8) or long wards (configs 4 and 5) -- and lean groups where
+    // many warps share an SM and the wards are short (the 64k-particle sweep).  AMRO_BITS_PULL=deep|lean overrides.
+    const double warps_per_sm = (double)(n_teams * G + extra) * (kTeamThreads / 32) / sms;
+    f.pull_deep = (warps_per_sm <= 8.5 || H.max_seg_rows > 1024) ? 1 : 0;
+    if (const char* e = std::getenv("AMRO_BITS_PULL")) f.pull_deep = e[0] == 'd';
+  }
   f.counts_col = T->ws_counts.p; f.counts_det = T->ws_counts.p + H.n_days_out * S_pad; f.counts_ld = H.n_days_out;
   ensure_size(T->ws_barrier, (size_t)n_teams);
   AMRO_CUDA(cudaMemsetAsync(T->ws_barrier.p, 0, sizeof(unsigned) * n_teams, st));

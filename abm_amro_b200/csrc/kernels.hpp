@@ -127,6 +127,7 @@ struct FastArgs {
   int press_days;
   const uint32_t* src_mask;        // one bit per record: it has a source (a predecessor or an initial row); word = 32-record chunk of a day
   const int64_t* day_chunk_start;  // [n_days + 1] first chunk of every day in src_mask
+  int pull_deep;                   // which variant counts the ward pressure (kernels_bits.cu: pull_pressure / pull_pressure_lean)
 };
 
 // element (uint4) index of slot q of a team's first slice in a state-ring buffer laid out [chunk of 32 slots][slice][32]

@@ -303,9 +303,9 @@ __device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint3
   for (int u = 0; u < N; ++u) cnt[u] += o[u];
 }
 
-// The same count for the instances that run many warps per SM (the 128- and 80-register ones): there the SM is busy with
-// other warps while a load is on its way, and what counts is the number of instructions -- chunks past the ward-day's end
-// are skipped instead of loaded and masked, one group per step (measured: profiles/sweeps.txt).
+// The same count for launches that keep many warps per SM busy with short wards: there the SM has other warps to run while a
+// load is on its way, and what counts is the number of instructions -- chunks past the ward-day's end are skipped instead of
+// loaded and masked, one group per step (measured: profiles/sweeps.txt).  The host picks the variant per launch (pull_deep).
 __device__ __forceinline__ void pull_load_lean(uint32_t (&x)[kPullGroup], const uint32_t* pre_x, const uint32_t* mask_day, uint32_t k, uint32_t k1,
                                                uint32_t rs, uint32_t re, int lane) {
 #pragma unroll
@@ -364,8 +364,8 @@ struct DayIn {
   uint32_t* press_out;        // nullptr, or where the day's counts go ([ward-day of the day][kBW][32], + lane)
   bool test_h, test_a;
 };
-template <bool DEEP>   // DEEP: the instance that runs two or three CTAs per SM (latency-bound: deep, branch-free pull steps)
-__device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const DayIn& in, uint32_t b0, uint32_t b1) {
+// deep: the launch keeps few warps per SM busy, or its wards are long (latency-bound counting: deep, branch-free pull steps)
+__device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const DayIn& in, uint32_t b0, uint32_t b1, bool deep) {
   const int lane = threadIdx.x & 31;
   const int sim = c.w * 32 + lane;
   const bool test_h = in.test_h, test_a = in.test_a;
@@ -381,12 +381,12 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
     if (lane < 3) rows[0] = (uint32_t)(__ldg(in.seg_rows + min(sl0 + (uint32_t)lane, b1)) - in.da);
     rows[2] = __shfl_sync(0xFFFFFFFFu, rows[0], 2); rows[1] = __shfl_sync(0xFFFFFFFFu, rows[0], 1); rows[0] = __shfl_sync(0xFFFFFFFFu, rows[0], 0);
     if (sl0 + 1u < b1) {
-      if (DEEP) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
+      if (deep) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
       else pull_pressure_lean<2>(in.pre_x, in.mask_day, rows, cnt, lane);
     } else {   // a single ward-day: its tables are built twice
       const uint32_t r1[2] = {rows[0], rows[1]};
       uint32_t c1[1];
-      if (DEEP) pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
+      if (deep) pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
       else pull_pressure_lean<1>(in.pre_x, in.mask_day, r1, c1, lane);
       cnt[0] = cnt[1] = c1[0];
     }
@@ -468,7 +468,7 @@ struct DayState {
   }
 };
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
-template <int TTD, bool DEEP>
+template <int TTD>
 __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
                                                  int64_t seg0_next, TeamBarrier& bar, const DayState& ds) {
   const int lane = threadIdx.x & 31;
@@ -511,7 +511,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 #ifdef AMRO_EXP_NOTABLES   // timing experiment (wrong results): tables built on the first two days only
       if (d < 2)
 #endif
-      finish_tables_bits<DEEP>(sh, c, in, sl, sl + n_tab);
+      finish_tables_bits(sh, c, in, sl, sl + n_tab, a.pull_deep != 0);
       __syncwarp();
       const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(in.seg_rows + sl) - da)) - pl.w0;
       const uint32_t re = min(pl.w1, (uint32_t)(__ldg(in.seg_rows + sl + n_tab) - da)) - pl.w0;
@@ -606,9 +606,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   const int G = a.ctas_per_team + (in_big ? 1 : 0);
   const int64_t team = in_big ? blockIdx.x / G : a.teams_plus_one + ((int)blockIdx.x - big) / G;
   const int rank = in_big ? blockIdx.x % G : ((int)blockIdx.x - big) % G;
-  // the warps of a team pair up: pair `gw` of `n_gw` steps a run of the day's records, warp `w` of the pair its word
-  static_assert(kWarps % kBW == 0, "whole pairs per CTA");
-  const uint32_t gw_all = (uint32_t)(rank * kWarps + warp), gw = gw_all / kBW, n_gw = (uint32_t)(G * kWarps) / kBW;
+  // the warps of a team pair up: pair `gw` of `n_gw` steps a run of the day's records, warp `w` of the pair its word.  A team
+  // whose second word holds no simulation (the last team of a run, or the only one: 32 members per GPU) does not pair: every
+  // warp takes its own run of word 0 (twice as many, half as long).
+  static_assert(kWarps % kBW == 0 && kBW == 2, "whole pairs per CTA");
+  const uint32_t words = (a.S - team * kBitsSims > 32) ? (uint32_t)kBW : 1u;
+  const uint32_t gw_all = (uint32_t)(rank * kWarps + warp), gw = gw_all / words, n_gw = (uint32_t)(G * kWarps) / words;
   TeamBarrier bar{a.team_barrier + team, 0u, (unsigned)(G * kWarps), G == 1 ? kBarCta : (a.cluster_barrier ? kBarCluster : kBarGlobal)};
   const int64_t ring = a.ring_chunks * (kBW * 32);
 
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
   const uint32_t team_gsim0 = (uint32_t)(a.sim_offset + (uint64_t)team * kBitsSims);
   const int64_t team_sim0 = team * kBitsSims;
   BitsCtx c;
-  c.w = (int)(gw_all % kBW);
+  c.w = (int)(gw_all % words);
   c.pre = team_pre + c.w * 32;
   c.press = team_press ? team_press + c.w * 32 : nullptr;
   c.gsim0 = team_gsim0 + (uint32_t)c.w * 32u;
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     if (d < 2)
 #endif
     bar.wait();
-    process_day_bits<TTD, (MINB < kTeamMinBlocks)>(sh, a, c, d, plan, seg0_next, bar, ds);
+    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, ds);
     ds.next(a);
     plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
