@@ -58,7 +58,8 @@ class SimArgs(C.Structure):
 # every entry point include/amro_b200.h declares (tests/test_host.py checks this list against the header)
 EXPORTS = ["amro_last_error", "amro_version", "amro_device_count", "amro_topology_create", "amro_topology_destroy",
            "amro_topology_get_info", "amro_topology_generate", "amro_hospital_tables", "amro_topology_kernel_times", "amro_topology_cache_clear", "amro_topology_cache_stats", "amro_simulate", "amro_simulate_discrete_model", "amro_simulate_and_collapse", "amro_simulate_and_collapse_alloc",
-           "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive", "amro_summary_of_total_positive_device"]
+           "amro_progress_patients", "amro_total_positive", "amro_summary_of_total_positive", "amro_summary_of_total_positive_device",
+           "amro_day_moments_peers"]
 
 _lib = None
 
@@ -96,6 +97,7 @@ def lib():
                                           C.POINTER(_i64), C.c_void_p]
         L.amro_summary_of_total_positive.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_void_p]
         L.amro_summary_of_total_positive_device.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_int, C.c_void_p]
+        L.amro_day_moments_peers.argtypes = [C.c_void_p, C.c_void_p, _i64, _i64, _i64, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
         L.amro_topology_debug_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 11 + [C.POINTER(_i64)]
         _lib = L
     return _lib

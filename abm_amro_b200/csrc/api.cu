@@ -126,6 +126,19 @@ int amro_topology_get_info(const amro_topology* topo, amro_topology_info* info) 
 
 }  // extern "C"
 
+extern "C" int amro_day_moments_peers(const int32_t* counts_colonized, const int32_t* counts_detected, int64_t n_days, int64_t n_sims,
+                                      int64_t ld_counts, double* const* dst, int n_dst, int device, void* stream) {
+  return guarded([&] {
+    if (!counts_colonized || !counts_detected || !dst) fail(AMRO_EINVAL, "NULL argument");
+    if (n_days < 0 || n_sims < 1 || ld_counts < n_days) fail(AMRO_EINVAL, "bad shape");
+    if (n_dst < 1 || n_dst > kMaxPeers) fail(AMRO_EINVAL, "between 1 and %d destinations", kMaxPeers);
+    for (int i = 0; i < n_dst; ++i) if (!dst[i]) fail(AMRO_EINVAL, "destination %d is NULL", i);
+    use_device(device);
+    day_moments_peers((cudaStream_t)stream, counts_colonized, counts_detected, n_days, n_sims, ld_counts, dst, n_dst, n_days);
+    AMRO_CUDA(cudaGetLastError());
+  });
+}
+
 extern "C" int amro_topology_kernel_times(amro_topology* topo, int n, float* ms) {
   return guarded([&] {
     if (!topo || !ms || n < 0) fail(AMRO_EINVAL, "bad argument");
@@ -866,7 +879,7 @@ size_t topology_bytes(const amro_topology& t) {
   // meta per record + the general path's arrays when uploaded + workspaces that grow with the runs
   size_t b = (size_t)H.R * (8 + 8 + 8 + 8 + 4) + (size_t)H.Rp * 16 + (H.push_src.size() + H.push_dst.size()) * 8;
   b += (size_t)H.Rp * 16 + (size_t)H.R * 8;
-  b += t.ws_pre.n * 16 + t.ws_traj.n * 16 + t.ws_pressure.n * 4 + t.ws_counts.n * 4;
+  b += t.ws_pre.n * 16 + t.ws_traj.n * 16 + t.ws_pressure.n * 4 + t.ws_counts.n * 4 + t.src_mask.n * 4;
   return b;
 }
 void destroy_topology(amro_topology* t) { amro_topology_destroy(t); }

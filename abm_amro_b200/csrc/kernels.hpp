@@ -55,6 +55,10 @@ void distance_to_data(cudaStream_t st, const int32_t* col, const int32_t* det, i
 // (arma::quantile, Hyndman & Fan 5) over the simulations; the same operation order as the host routine (bit-identical)
 void device_summary(cudaStream_t st, const double* X, int64_t n_days, int64_t S, int64_t ld, const double* q_dev, int64_t nq, double* out,
                     int64_t ld_out);
+// the same, stored into n_dst <= kMaxPeers buffers (this GPU's and its peers' over NVLink): the run's collective as peer stores
+constexpr int kMaxPeers = 16;
+void day_moments_peers(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
+                       double* const* dst, int n_dst, int64_t ld);
 void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld);
 
 // ----------------------------------------------------------------------------------------------------

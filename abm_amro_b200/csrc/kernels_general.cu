@@ -187,6 +187,31 @@ __global__ void k_day_moments(const int32_t* __restrict__ col, const int32_t* __
   if (lane == 0) { out[day] = a; out[day + ld] = b; out[day + 2 * ld] = c; out[day + 3 * ld] = d; }
 }
 
+// The same moments delivered to every GPU of the box in the same pass: lane 0 of a day's warp stores the four sums into the
+// slot of this rank in EVERY rank's buffer (peer memory mapped over NVLink / NVSwitch; the own buffer is one of them).  No
+// rank waits for another inside a run: readers add the slots up after the barrier that ends a batch of runs.
+struct PeerDst { double* p[kMaxPeers]; };
+__global__ void k_day_moments_peers(const int32_t* __restrict__ col, const int32_t* __restrict__ det, int64_t n_days, int64_t S,
+                                    int64_t ld_c, PeerDst dst, int n_dst, int64_t ld) {
+  const int64_t day = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (day >= n_days) return;
+  double a = 0, b = 0, c = 0, d = 0;
+  for (int64_t s = lane; s < S; s += 32) {
+    const double x = (double)col[day + ld_c * s], y = (double)det[day + ld_c * s];
+    a += x; b += x * x; c += y; d += y * y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o); d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+  }
+  // lanes 0 .. n_dst-1 each serve one destination (the stores of a day go out together)
+  if (lane < n_dst) {
+    double* out = dst.p[lane];
+    out[day] = a; out[day + ld] = b; out[day + 2 * ld] = c; out[day + 3 * ld] = d;
+  }
+}
+
 // per-simulation squared distance between the per-day counts and observed series: one warp per simulation (its days are
 // contiguous: coalesced).  Sums of squares of integers minus data, accumulated in float64 in a fixed lane/shuffle order.
 __global__ void k_distance(const int32_t* __restrict__ col, const int32_t* __restrict__ det, int64_t n_days, int64_t S, int64_t ld_c,
@@ -240,6 +265,13 @@ void gen_count(cudaStream_t st, const double* plane, int64_t ld, int64_t R, int6
 void day_moments(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c, double* out, int64_t ld) {
   if (n_days <= 0) return;
   k_day_moments<<<blocks_for(n_days * 32), kThreads, 0, st>>>(col, det, n_days, S, ld_c, out, ld);
+}
+void day_moments_peers(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
+                       double* const* dst, int n_dst, int64_t ld) {
+  if (n_days <= 0 || n_dst <= 0) return;
+  PeerDst d{};
+  for (int i = 0; i < n_dst; ++i) d.p[i] = dst[i];
+  k_day_moments_peers<<<blocks_for(n_days * 32), kThreads, 0, st>>>(col, det, n_days, S, ld_c, d, n_dst, ld);
 }
 void distance_to_data(cudaStream_t st, const int32_t* col, const int32_t* det, int64_t n_days, int64_t S, int64_t ld_c,
                       const double* obs_col, const double* obs_det, double* out) {

@@ -239,22 +239,36 @@ def time_workload(topo, par_np, S, sim_offset, dev, steps, warmup, world, dist, 
     idp_d = torch.tensor([IDP], dtype=torch.float64, device=dev)
     cc_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)               # == [n_days x S] column-major
     cd_d = torch.zeros((S, n_days), dtype=torch.int32, device=dev)
-    # day moments of a run: two buffers, so that the all-reduce of run k (on NCCL's own stream) overlaps run k + 1
+    # The run's collective (N > 1): the per-day moments of every run, delivered to all ranks.  Peer stores when the ranks can map
+    # each other's memory (ensemble.PeerMoments: one small kernel per run, no rank waits for another), else an NCCL all-reduce per
+    # run on NCCL's stream (two buffers, so that the reduction of run k overlaps run k + 1).
     mom = [torch.zeros((4, n_days), dtype=torch.float64, device=dev) for _ in range(2)]   # == [n_days x 4] column-major
     pending = [None, None]
     stream = torch.cuda.current_stream(dev)
     count = [0]
+    peers = None
+    no_coll = bool(os.environ.get("AMRO_BENCH_NO_COLLECTIVE"))          # (development switch: what the collective costs)
+    if world > 1 and not no_coll and not os.environ.get("AMRO_BENCH_NCCL"):
+        try:
+            peers = ensemble.PeerMoments(n_days, dev)
+        except Exception as e:                                            # noqa: BLE001 -- any failure of the rendezvous: NCCL does it
+            print(f"[bench] peer stores unavailable ({type(e).__name__}: {e}); the collective is an NCCL all-reduce", file=sys.stderr)
+            peers = None
 
     def step_device():
         k = count[0] & 1
         count[0] += 1
         flush.zero_()                                                            # evict L2 between steps
+        use_nccl = world > 1 and peers is None and not no_coll
         if pending[k] is not None:
             pending[k].wait()                                                    # (stream-side wait) run k - 2's reduction has read this buffer
         r = topo.simulate_device(par_d.data_ptr(), S, S, icp_d.data_ptr(), idp_d.data_ptr(), cc_d.data_ptr(),
                                  cd_d.data_ptr(), S, TTD, TSH, TSA, SEED, sim_offset=sim_offset, stream=stream.cuda_stream,
-                                 day_moments_ptr=mom[k].data_ptr() if world > 1 else 0, asynchronous=True)
-        if world > 1:  # the run's one collective: per-day (sum, sum^2) of both metrics over all members, summed in place
+                                 day_moments_ptr=mom[k].data_ptr() if use_nccl else 0, asynchronous=True)
+        if peers is not None:
+            peers.publish(count[0] - 1, cc_d.data_ptr(), cd_d.data_ptr(), S, n_days, stream=stream.cuda_stream)
+            r.launches += 1
+        elif use_nccl:  # per-day (sum, sum^2) of both metrics over all members, summed in place
             pending[k] = dist.all_reduce(mom[k], op=dist.ReduceOp.SUM, async_op=True)
         return r
 
@@ -283,12 +297,26 @@ def time_workload(topo, par_np, S, sim_offset, dev, steps, warmup, world, dist, 
         e1.record(stream)
         barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    collective = "none (1 GPU)" if world == 1 else ("skipped (development switch)" if no_coll else "nccl all_reduce per run")
+    if peers is not None:
+        # outside the timed region: the last run's moments as every rank received them == an NCCL all-reduce of the same run's
+        got = peers.reduced(count[0] - 1)
+        want = ensemble.day_moments(cc_d, cd_d).T.contiguous()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        if not torch.equal(got, want):
+            raise SystemExit("peer-store collective disagrees with the all-reduce of the same moments")
+        collective = "peer stores over NVLink from the moments kernel (torch symmetric memory); checked against an NCCL all-reduce of the last run"
     kernel_ms = topo.kernel_times(min(steps, 64))                               # CUDA events around each run's fused kernel
+    kernel_ms_ranks = None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    return dict(elapsed_ms=elapsed_ms, kernel_ms=float(np.mean(kernel_ms)), launches=launches, clocks=clocks.summary(), result=r,
+        # every rank's mean kernel time (outside the timed region): the step is the slowest GPU's
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev))
+        kernel_ms_ranks = [round(float(x.item()), 4) for x in g]
+    return dict(elapsed_ms=elapsed_ms, kernel_ms=float(np.mean(kernel_ms)), kernel_ms_ranks=kernel_ms_ranks, collective=collective, launches=launches, clocks=clocks.summary(), result=r,
                 cc_d=cc_d, cd_d=cd_d, mom_d=mom[(count[0] - 1) & 1], par_d=par_d)
 
 
@@ -406,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
             call()
         dt = (time.perf_counter() - t0) / 5
         dropin = {"value": float(R) * S / dt, "unit": "updates/s", "ms_per_call": dt * 1e3,
-                  "entry_point": "amro.simulate_and_collapse (content-hashed hospital cache warm; hashing the tables is inside)"}
+                  "entry_point": "amro.simulate_and_collapse (compiled-hospital cache warm; the content hash of the tables is inside: it runs on host threads while the kernel runs on the hospital the quick key points to)"}
 
     # ---- the 64k-particle sweep in the same process (config 3), so that its fraction is driver-timed too --------------------
     secondary = None
@@ -446,7 +474,8 @@ def run_ours(args, rank, world, local_rank):
                        "kernel": kinds.get(r.kernel_kind, "?"),
                        "launch": {"grid": r.grid, "ctas_per_team": r.ctas_per_team, "team_barrier": ["cta", "global", "cluster"][r.team_barrier]},
                        "l2": "256 MB buffer written between steps (inside the timed region)",
-                       "timed_region": "asynchronous runs enqueued back to back: kernel -> day moments -> all-reduce (N > 1; on NCCL's stream, overlapping the next run), one sync at the end",
+                       "timed_region": "asynchronous runs enqueued back to back: kernel -> day moments -> the run's collective (N > 1), one sync at the end",
+                       "collective": m["collective"],
                        "topology_compile_ms": topo_ms,
                        "hospital": "generated on the device (amro_topology_generate)" if generated else "numpy tables through the C ABI (synth.make_hospital)",
                        "counts_match_between_device_and_host_api": same},
@@ -454,7 +483,8 @@ def run_ours(args, rank, world, local_rank):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": b_alg,
                          "kernel_ms": k_ms,
                          "note": "algorithmic bytes per SURVEY.md 8(d); the kernel itself keeps 4 bits per (record, member): it moves about "
-                                 "1 B per update and is bound by the integer ALU pipe, not by HBM (DESIGN.md 3.4)"},
+                                 "1 B per update and is bound by the integer ALU pipe and, on config 2, by per-day latency -- not by HBM (DESIGN.md 3.5)",
+                         "kernel_ms_ranks": m.get("kernel_ms_ranks")},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "updates/s",
                     "h2d_bytes_per_step": int(S * 6 * 8 + 16 + (4 * n_days * 8 if world > 1 else 0)),

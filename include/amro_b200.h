@@ -244,6 +244,15 @@ int amro_total_positive(const double* model, int64_t n_rows, int64_t n_cols, int
                         int64_t n_sims, int mode, int device,
                         int64_t* n_days, int64_t* n_out_cols, double* out);
 
+/* The run's collective as peer stores (the reference has no counterpart: its OpenMP loop over simulations,
+ * abm_wards.cpp:92, shares one address space).  Per-day sum and sum of squares over this GPU's simulations of the colonised and
+ * detected counts (device arrays [n_days x n_sims], ld_counts, as amro_simulate leaves them with pointers_on_device), stored
+ * as [n_days x 4] (ld = n_days) into EVERY destination: dst[i] are device pointers -- this GPU's buffer and its peers'
+ * buffers mapped over NVLink (CUDA IPC / torch symmetric memory), n_dst <= 16.  One small kernel on `stream`, no host
+ * synchronisation, no rank waits for another; the reader adds the ranks' slots after its own barrier. */
+int amro_day_moments_peers(const int32_t* counts_colonized, const int32_t* counts_detected, int64_t n_days, int64_t n_sims,
+                           int64_t ld_counts, double* const* dst, int n_dst, int device, void* stream);
+
 /* The same on the device (per-day segmented sort across the simulations; bit-identical to the host routine): worth it from a
  * few hundred thousand values on. */
 int amro_summary_of_total_positive_device(const double* positive, int64_t n_days, int64_t n_sims, int64_t ld,

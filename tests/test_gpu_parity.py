@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from abm_amro_b200 import capi, engine, synth
+from abm_amro_b200 import capi, engine, ensemble, synth
 from oracle import oracle
 from tests import reference_cases
 from tests.helpers import expected_pressure, random_tensors, stream_to_tensors
@@ -632,3 +632,26 @@ def test_device_pointer_api_matches_host_api():
                              stream=torch.cuda.current_stream(dev).cuda_stream)
         torch.cuda.synchronize()
         assert np.array_equal(cc.cpu().numpy().T, host.counts_colonized) and np.array_equal(cd.cpu().numpy().T, host.counts_detected)
+
+
+def test_day_moments_peer_stores_match_the_all_reduce_arithmetic():
+    # The run's collective as peer stores (amro_day_moments_peers): per-day sum / sum of squares of this GPU's counts, stored into
+    # every destination.  On one GPU the destinations are three local buffers standing in for the peers' mapped memory; the
+    # two-rank arithmetic (slots added in rank order) is what ensemble.PeerMoments.reduced returns on a real box.
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    n_days, S = 37, 203
+    cc = torch.from_numpy(rng.integers(0, 900, size=(S, n_days)).astype(np.int32)).to(dev)      # == [n_days x S] column-major
+    cd = torch.from_numpy(rng.integers(0, 300, size=(S, n_days)).astype(np.int32)).to(dev)
+    bufs = [torch.full((4, n_days), -1.0, dtype=torch.float64, device=dev) for _ in range(3)]
+    dst = (C.c_void_p * 3)(*[b.data_ptr() for b in bufs])
+    capi.check(capi.lib().amro_day_moments_peers(cc.data_ptr(), cd.data_ptr(), n_days, S, n_days, dst, 3, 0,
+                                                 torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    want = ensemble.day_moments(cc, cd).T.contiguous()                    # [4 x n_days]: integers below 2^53, exact in any order
+    for b in bufs:
+        assert torch.equal(b, want)
+    with pytest.raises(ValueError):
+        capi.check(capi.lib().amro_day_moments_peers(cc.data_ptr(), cd.data_ptr(), n_days, S, n_days, dst, 17, 0, 0))
