@@ -351,6 +351,8 @@ def run_ours(args, rank, world, local_rank):
     generated = args.workload in GENERATED
     if args.days:
         days = args.days
+    torch.zeros(1, device=dev)                                                   # the CUDA context exists before the compile is timed
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     if generated:
         topo = engine.Topology.generate(engine.hospital_spec(wards, census, days, seed=1), device=local_rank)
