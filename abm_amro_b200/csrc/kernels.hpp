@@ -156,7 +156,7 @@ void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_s
 // unit-weight hospitals with time_to_detect <= 2 in free-running mode.  See kernels_bits.cu.  Same ring / meta / launch
 // shapes (kShapeTeam, kShapeRoomy) as the FAST path; a team steps bits_sims_per_team() simulations.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kBitsMaxTtd = 2;
+constexpr int kBitsMaxTtd = 6;   // 0 .. 2: shift-register planes; 3 .. 6: a 3-bit countdown code per simulation
 int bits_sims_per_team();
 int bits_words_per_team();   // groups of 32 simulations of a team: the warps of a team pair up, one warp per word
 size_t bits_shared_bytes();

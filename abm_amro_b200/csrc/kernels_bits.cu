@@ -1,5 +1,5 @@
 // BITS path: the ward-level colonisation step with the state BIT-SLICED over simulations -- summary runs (per-day counts,
-// no trajectory) of unit-weight hospitals with time_to_detect <= 2, free-running mode, in ONE persistent kernel.
+// no trajectory) of unit-weight hospitals with time_to_detect <= 6, free-running mode, in ONE persistent kernel.
 //
 // Replaces the same nest as kernels_fast.cu (src/amro/abm_wards.cpp:322-414 / :219-257 / :70-159 fused with the totals
 // :435-509).  Where kernels_fast.cu keeps a 16-bit code per (record, simulation) and steps two simulations per 32-bit
@@ -9,6 +9,8 @@
 //                                                     an uncolonised patient whose D reads 0)
 //   q1   result due tomorrow  (D = 1)               (time_to_detect >= 1)
 //   q2   result due in two days (D = 2)             (time_to_detect == 2)
+// (time_to_detect 3 .. 6, the reference's default: planes det, q1, q2 hold a 3-bit code instead -- 0 nothing pending, 1 .. 6 days
+// until the result, 7 detected; the instance compiled for TTD = 3 reads the actual value from the arguments)
 // so a record x 32 simulations is one 16-byte word and every logical step of the update is one LOP3 for 32 simulations:
 //   draws        the record's 14 plane words (rng.cuh) are compared with the THRESHOLD PLANES of its (ward-day, is_new):
 //                lt = (t & ~u) | (~(t ^ u) & lt), least significant plane first -- one LOP3 per plane and probability
@@ -495,6 +497,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     char* nxt = reinterpret_cast<char*>(c.pre + ((d + 1) & 1) * ring);
     const uint4* pm = a.meta + da + pl.w0 + lane;
     const uint32_t g32 = c.gsim0 >> 5;
+    const uint32_t ttd_bit[3] = {(a.ttd & 1) ? ~0u : 0u, (a.ttd & 2) ? ~0u : 0u, (a.ttd & 4) ? ~0u : 0u};   // TTD > 2: the code a positive test starts
     DayIn in;
     in.pre_x = reinterpret_cast<const uint32_t*>(pday) + 4 * lane;
     in.mask_day = a.src_mask + __ldg(&a.day_chunk_start[d]);
@@ -558,21 +561,42 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
           const uint32_t fU = lt[0] | always[0], fA = lt[1] | always[1], fB = lt[2] | always[2];
           const uint32_t fUh = lt[3] | always[3], fAh = lt[4] | always[4];
           // ---- transition (:116-155) ----
-          const uint32_t cc = pre.x, det = pre.y, q1 = pre.z, q2 = pre.w;
-          const uint32_t col = (cc & ((det & fB) | (~det & fA))) | (~cc & fU);           // :116-120
-          const uint32_t hit = (cc & fAh) | (~cc & fUh);                                  // tested positive today (:134 / :146)
-          const uint32_t tested = col & hit & ~(det | q1 | q2);                           // no countdown running: D = ttd
           uint4 post;
-          post.x = col;
-          post.y = col & (det | q1);                                                      // D -= 1 reaches or stays below 0 (:131-132)
-          post.z = 0u; post.w = 0u;
-          if (TTD == 0) post.y |= tested;
-          if (TTD == 1) post.z = tested;
-          if (TTD == 2) { post.z = col & q2; post.w = tested; }
+          uint32_t col, det_post;
+          if (TTD <= 2) {
+            const uint32_t cc = pre.x, det = pre.y, q1 = pre.z, q2 = pre.w;
+            col = (cc & ((det & fB) | (~det & fA))) | (~cc & fU);                         // :116-120
+            const uint32_t hit = (cc & fAh) | (~cc & fUh);                                // tested positive today (:134 / :146)
+            const uint32_t tested = col & hit & ~(det | q1 | q2);                         // no countdown running: D = ttd
+            post.x = col;
+            post.y = col & (det | q1);                                                    // D -= 1 reaches or stays below 0 (:131-132)
+            post.z = 0u; post.w = 0u;
+            if (TTD == 0) post.y |= tested;
+            if (TTD == 1) post.z = tested;
+            if (TTD == 2) { post.z = col & q2; post.w = tested; }
+            det_post = post.y;
+          } else {
+            // time_to_detect 3 .. 6: planes y, z, w are a 3-bit code n per simulation -- 0 no result pending, 1 .. 6 days until
+            // the result (the reference's countdown D), 7 detected (D <= 0; with c = 0 the initial-state quirk)
+            const uint32_t cc = pre.x, n0 = pre.y, n1 = pre.z, n2 = pre.w;
+            const uint32_t det = n0 & n1 & n2, any = n0 | n1 | n2;
+            col = (cc & ((det & fB) | (~det & fA))) | (~cc & fU);
+            const uint32_t hit = (cc & fAh) | (~cc & fUh);
+            const uint32_t tested = col & hit & ~any;                                     // no countdown running: D = ttd (:134 / :146)
+            const uint32_t one = n0 & ~n1 & ~n2;                                          // D = 1: the result arrives (D -= 1 reaches 0)
+            const uint32_t to7 = col & (det | one);                                       // (one implies a running countdown)
+            const uint32_t dec = col & any & ~det & ~one;                                 // D -= 1 (:131-132), still positive
+            const uint32_t m1 = ~(n1 ^ n0), m2 = n2 ^ (~n0 & ~n1);                        // n - 1 (bit 0: ~n0)
+            post.x = col;
+            post.y = to7 | (dec & ~n0) | (tested & ttd_bit[0]);
+            post.z = to7 | (dec & m1) | (tested & ttd_bit[1]);
+            post.w = to7 | (dec & m2) | (tested & ttd_bit[2]);
+            det_post = post.y & post.z & post.w;
+          }
           // :402-407 the successor starts from this state -- and its ward counts it tomorrow (pull_pressure)
           if (next != kNone) __stcg(reinterpret_cast<uint4*>(nxt + next), post);
           vcol.add(col);
-          vdet.add(post.y);
+          vdet.add(det_post);
         }
         since += te - tb;
         tb = te;
@@ -685,7 +709,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
           // c); colonised, flag 0 -> D = 0: detected; flag 1 -> D = 1: due tomorrow if ttd >= 1, else neither pending nor
           // detected (it is re-tested like D = inf)
           const uint32_t flag1 = c0 & d0;
-          if (g == 0) __stcg(&team_pre[ring_slot_b(slot) + w * 32], make_uint4(c0, valid & ~flag1, TTD >= 1 ? flag1 : 0u, 0u));
+          if (g == 0) {
+            if (TTD <= 2) __stcg(&team_pre[ring_slot_b(slot) + w * 32], make_uint4(c0, valid & ~flag1, TTD >= 1 ? flag1 : 0u, 0u));
+            else __stcg(&team_pre[ring_slot_b(slot) + w * 32], make_uint4(c0, valid, valid & ~flag1, valid & ~flag1));   // code 7, or 1 where D0 = 1
+          }
         }
       }
     }
@@ -747,7 +774,7 @@ const void* bits_kernel_of(int shape) {
                                 : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks>;
 }
 const void* bits_kernel_ptr(int ttd, int shape) {
-  return ttd == 0 ? bits_kernel_of<0>(shape) : ttd == 1 ? bits_kernel_of<1>(shape) : bits_kernel_of<2>(shape);
+  return ttd == 0 ? bits_kernel_of<0>(shape) : ttd == 1 ? bits_kernel_of<1>(shape) : ttd == 2 ? bits_kernel_of<2>(shape) : bits_kernel_of<3>(shape);
 }
 
 }  // namespace
