@@ -623,6 +623,8 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
   if (on_device && A->state_out) { C = A->state_out; Dp = A->state_out + A->so_ld * S; ld = A->so_ld; }
   else { planes.alloc((size_t)(2 * R * S)); C = planes.p; Dp = planes.p + R * S; ld = R; }
   F.alloc((size_t)(std::max<int64_t>(H.max_segs_per_day, 1) * S));
+  DevBuf<uint32_t> dither;
+  if (!replay) dither.alloc((size_t)((std::max<int64_t>(H.max_segs_per_day, 1) + 1) * S));
   int64_t max_push = 0;
   for (int64_t d = 0; d < D; ++d) max_push = std::max(max_push, H.day_push_start[d + 1] - H.day_push_start[d]);
   tmp.alloc((size_t)(std::max<int64_t>(max_push, 1) * 2 * S));
@@ -636,6 +638,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
   g.params = in.params; g.p_ld = in.p_ld; g.S = S; g.F = F.p; g.ttd = A->time_to_detect;
   g.replay = replay; g.u_col = in.u_col; g.u_det = in.u_det; g.u_ld = in.u_ld;
   g.seed = (uint64_t)A->seed; g.sim_offset = (uint64_t)A->sim_offset;
+  g.dither = replay ? nullptr : dither.p; g.run_dither_row = std::max<int64_t>(H.max_segs_per_day, 1);
   if (A->p_out) {
     if (on_device) g.p_out = A->p_out;
     else { d_p.alloc((size_t)(R * S)); AMRO_CUDA(cudaMemsetAsync(d_p.p, 0xFF, sizeof(double) * R * S, st)); g.p_out = d_p.p; }
@@ -648,6 +651,7 @@ void run_general(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cud
   int launches = 1;
   gen_init(st, C, Dp, ld, R, S, H.n_init, in.icp, in.icp_rs, in.icp_cs, in.idp, in.idp_rs, in.idp_cs, replay,
            in.u_icol, in.u_idet, in.ui_ld, g.seed, g.sim_offset);
+  if (!replay) { gen_run_dither(st, g); launches++; }
   for (int64_t d = 0; d < D; ++d) {
     const int64_t sa = H.day_seg_start[d], sb = H.day_seg_start[d + 1];
     const int64_t ra = H.day_start[d], rb = H.day_start[d + 1];

@@ -33,12 +33,15 @@ struct GenArgs {
   uint64_t sim_offset;
   double* p_out;             // optional [rows x S]
   int64_t p_out_ld;
+  uint32_t* dither;          // free-running mode: [(ward-days of a day) + 1 x S] dithers of the day's ward-days (k_gen_pressure)
+  int64_t run_dither_row;    // ... and, in row run_dither_row, the run's dither of ward-free probabilities
 };
 
 void gen_init(cudaStream_t st, double* C, double* D, int64_t ld, int64_t R, int64_t S, int64_t n_init,
               const double* icp, int64_t icp_rs, int64_t icp_cs, const double* idp, int64_t idp_rs, int64_t idp_cs,
               int replay, const double* u_icol, const double* u_idet, int64_t ui_ld, uint64_t seed, uint64_t sim_offset);
 void gen_pressure(cudaStream_t st, const GenArgs& a, int64_t seg_begin, int64_t seg_end);
+void gen_run_dither(cudaStream_t st, const GenArgs& a);   // once per run, before the first day
 void gen_update(cudaStream_t st, const GenArgs& a, int64_t row_begin, int64_t row_end, int64_t seg_begin,
                 int test_h, int test_a);
 void gen_propagate(cudaStream_t st, double* C, double* D, int64_t ld, int64_t S, const int64_t* push_src,
