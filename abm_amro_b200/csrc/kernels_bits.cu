@@ -135,9 +135,18 @@ struct BitsShared {
   uint32_t* tab;
   double* prep_bn;
   uint32_t* prep_r16;
+#ifdef AMRO_BITS_TMA
+  uint4* tma;          // per warp: [2 stages][32 meta words | 32 state words]
+  uint64_t* tma_bar;   // per warp: one mbarrier per stage
+#endif
 };
 constexpr size_t kCtaSharedBytes = sizeof(double) * 6 * kBitsSims + sizeof(uint32_t) * kBitsSims + sizeof(uint32_t) * 2 * kBW * 48;
-constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32;
+#ifdef AMRO_BITS_TMA   // the measured-and-rejected variant of the trip loop: inputs staged by TMA bulk copies
+constexpr size_t kTmaBytes = 2 * 64 * sizeof(uint4) + 2 * sizeof(uint64_t);
+#else
+constexpr size_t kTmaBytes = 0;
+#endif
+constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32 + kTmaBytes;
 static_assert(kCtaSharedBytes % 16 == 0 && kWarpSharedBytes % 16 == 0, "table rows are read as uint4");
 __host__ __device__ inline size_t bits_smem_bytes(int threads) { return kCtaSharedBytes + (size_t)(threads / 32) * kWarpSharedBytes; }
 __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
@@ -149,6 +158,10 @@ __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
   s.tab = reinterpret_cast<uint32_t*>(mine);
   s.prep_bn = reinterpret_cast<double*>(s.tab + (kZeroRowB + 1) * kTabWords);
   s.prep_r16 = reinterpret_cast<uint32_t*>(s.prep_bn + kBSegs * 32);
+#ifdef AMRO_BITS_TMA
+  s.tma = reinterpret_cast<uint4*>(s.prep_r16 + kBSegs * 32);
+  s.tma_bar = reinterpret_cast<uint64_t*>(s.tma + 2 * 64);
+#endif
   return s;
 }
 
@@ -448,6 +461,26 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
   }
 }
 
+#ifdef AMRO_BITS_TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // per-simulation day totals (:445-459 fused): lane s adds the count of simulation s of the warp's word
@@ -463,6 +496,9 @@ __device__ __forceinline__ void add_day_counts(const FastArgs& a, int64_t d, int
 // What a warp keeps across the days of a run: d % tsh, d % tsa (:391-392; the schedules are 64-bit the way the reference's
 // unsigned % reads them), kept without the division
 struct DayState {
+#ifdef AMRO_BITS_TMA
+  uint32_t tma_stage, tma_phase;   // next stage of the warp's two-stage ring, expected parity of each stage's mbarrier
+#endif
   uint64_t th, ta;
   __device__ __forceinline__ void next(const FastArgs& a) {
     th = th + 1u == a.tsh ? 0u : th + 1u;
@@ -472,8 +508,12 @@ struct DayState {
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
 template <int TTD>
 __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
-                                                 int64_t seg0_next, TeamBarrier& bar, const DayState& ds) {
+                                                 int64_t seg0_next, TeamBarrier& bar, DayState& ds) {
   const int lane = threadIdx.x & 31;
+#ifdef AMRO_BITS_TMA
+  uint32_t tma_stage = ds.tma_stage, tma_phase = ds.tma_phase;
+  asm volatile("fence.proxy.async;" ::: "memory");   // yesterday's states (generic-proxy writes, acquired at the barrier) before the async-proxy reads
+#endif
   VCount vcol, vdet;
   vcol.clear(); vdet.clear();
   uint32_t since = 0;   // trips since the day counters were flushed
@@ -524,6 +564,30 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
         const uint32_t te = min(t_end, tb + ((uint32_t)kFlushTrips - since));
         const uint4* pmt = pm + (int64_t)tb * 32;
         const uint4* pct = pc + (int64_t)tb * (kBW * 32);
+#ifdef AMRO_BITS_TMA
+        // rejected variant: the 512 B of record words and the 512 B of state words of a trip are staged in shared memory by
+        // two TMA bulk copies, one trip ahead, completion on an mbarrier per stage (lane 0 issues, every lane waits)
+        auto tma_issue = [&](uint32_t trip, uint32_t stg) {
+          const uint32_t n_rec = min(32u, n_run - trip * 32u);
+          mbar_expect(&sh.tma_bar[stg], n_rec * 16u + 512u);
+          bulk_g2s(sh.tma + stg * 64, pm - lane + (int64_t)trip * 32, n_rec * 16u, &sh.tma_bar[stg]);
+          bulk_g2s(sh.tma + stg * 64 + 32, pc - lane + (int64_t)trip * (kBW * 32), 512u, &sh.tma_bar[stg]);
+        };
+        __syncwarp();
+        if (lane == 0 && tb * 32u < n_run) tma_issue(tb, tma_stage);
+        for (uint32_t i = tb * 32u + lane; i < te * 32u + (uint32_t)lane; i += 32u) {   // warp-uniform trip count
+          const uint32_t trip = i >> 5;
+          __syncwarp();   // every lane has read the other stage (the previous trip's)
+          if (lane == 0 && trip + 1u < te && (trip + 1u) * 32u < n_run) tma_issue(trip + 1u, tma_stage ^ 1u);
+          uint4 meta = make_uint4(0u, kNone, kNone, 0u), pre = make_uint4(0u, 0u, 0u, 0u);
+          if (trip * 32u < n_run) {
+            mbar_wait(&sh.tma_bar[tma_stage], (tma_phase >> tma_stage) & 1u);
+            tma_phase ^= 1u << tma_stage;
+            if (i < n_run) meta = sh.tma[tma_stage * 64 + lane];
+            pre = sh.tma[tma_stage * 64 + 32 + lane];
+          }
+          tma_stage ^= 1u;
+#else
         // software pipeline: the loads of the next trip are in flight while this one computes
         uint4 n_meta = make_uint4(0u, kNone, kNone, 0u), n_prev = make_uint4(0u, 0u, 0u, 0u);
         if (tb * 32u + (uint32_t)lane < n_run) { n_meta = __ldg(pmt); n_prev = __ldcg(pct); }
@@ -533,6 +597,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
           pmt += 32; pct += kBW * 32;
           n_meta = make_uint4(0u, kNone, kNone, 0u);
           if (i + 32u < min(n_run, te * 32u)) { n_meta = __ldg(pmt); n_prev = __ldcg(pct); }
+#endif
           const uint32_t info = meta.x, segl = info & kInfoSegMask, src = (info >> kInfoSrcShift) & 3u;
           const int h = (int)(info >> kInfoHShift);
           const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
@@ -617,6 +682,9 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
   vflush<2>(vc, v, lane, since);
   bar.arrive();   // tomorrow's states are out
   add_day_counts(a, d, c.sim0, v[0], v[1]);
+#ifdef AMRO_BITS_TMA
+  ds.tma_stage = tma_stage; ds.tma_phase = tma_phase;
+#endif
 }
 
 template <int TTD, int THREADS, int MINB>
@@ -721,7 +789,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 
   // ---- day loop (:381): one team barrier per day ------------------------------------------------------------------
   DayPlan plan = plan_day(a, 0, gw, n_gw, DayPlan{});
+#ifdef AMRO_BITS_TMA
+  DayState ds{0u, 0u, 0u, 0u};
+  if (lane == 0) { mbar_init(&sh.tma_bar[0]); mbar_init(&sh.tma_bar[1]); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+#else
   DayState ds{0u, 0u};
+#endif
   const int n_days = (int)a.n_days;
   for (int d = 0; d < n_days; ++d) {
     const int64_t seg0_next = __ldg(&a.day_seg_start[d + 1]);
