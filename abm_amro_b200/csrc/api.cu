@@ -458,7 +458,7 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 bool bits_eligible(const amro_topology* T, const amro_sim_args* A) {
   const HostTopology& H = T->H;
   if (std::getenv("AMRO_FAST_NOBITS")) return false;
-  return A->rng_mode != AMRO_RNG_REPLAY && !A->keep_trajectory && !A->state_out && !A->p_out && !H.has_half &&
+  return A->rng_mode != AMRO_RNG_REPLAY && !A->keep_trajectory && !A->state_out && !A->p_out &&
          A->time_to_detect >= 0 && A->time_to_detect <= kBitsMaxTtd;
 }
 
@@ -475,7 +475,8 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   int shape = kShapeTeam;
   if (const char* e = std::getenv("AMRO_BITS_SHAPE")) shape = e[0] == 'd' ? kShapeDense : e[0] == 'r' ? kShapeRoomy : kShapeTeam;
   const bool shape_forced = std::getenv("AMRO_BITS_SHAPE") != nullptr;
-  int cap = bits_max_coresident_ctas(T->device, ttd, shape);
+  const bool half = H.has_half;
+  int cap = bits_max_coresident_ctas(T->device, ttd, shape, half);
   if (cap <= 0) fail(AMRO_ECUDA, "bit-sliced kernel cannot be made resident on this device");
   if (const char* e = std::getenv("AMRO_BITS_CTAS_PER_SM")) cap = std::min(cap, std::max(1, std::atoi(e)) * sms);
   // A pair of warps steps a run of records (one warp per word).  Team size: the largest number of whole CTAs-per-SM layers
@@ -492,10 +493,12 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
     if (G >= useful) {
       extra = 0;
       G = 1;
+      bool found = false;
       for (int layers = cap / sms; layers >= 1; --layers) {
         const int g = (int)((int64_t)layers * sms / n_teams);
-        if (g >= 1 && g <= useful + useful / 8) { G = g; break; }
+        if (g >= 1 && g <= useful + useful / 8) { G = g; found = true; break; }
       }
+      if (!found) G = (int)useful;   // few teams: even one CTA per SM would be more than the records feed -- part of the SMs then
     }
   }
   if (const char* e = std::getenv("AMRO_BITS_G")) { G = std::max(1, std::atoi(e)); extra = 0; }
@@ -504,9 +507,9 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   if (G > 1 && G <= kMaxClusterCtas && extra == 0) {
     const char* e = std::getenv("AMRO_FAST_BARRIER");
     const bool want = e ? (e[0] == 'c') : kClusterBarrierByDefault;
-    if (want && bits_max_coresident_clusters(ttd, shape, G) >= n_teams) use_cluster = 1;
+    if (want && bits_max_coresident_clusters(ttd, shape, G, half) >= n_teams) use_cluster = 1;
   }
-  if ((G > 1 || extra > 0) && !use_cluster && (int64_t)n_teams * G + extra > bits_max_coresident_ctas(T->device, ttd, shape))
+  if ((G > 1 || extra > 0) && !use_cluster && (int64_t)n_teams * G + extra > bits_max_coresident_ctas(T->device, ttd, shape, half))
     fail(AMRO_ECUDA, "bit-sliced kernel: the teams cannot be co-resident");
   const int64_t ring_chunks = std::max<int64_t>((H.max_rows_per_day + 31) / 32, 1);
   if (!H.identity_order && H.R >= ((int64_t)1 << 32)) fail(AMRO_EINVAL, "fast path: more than 2^32 rows need the original row order");
@@ -546,7 +549,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   f.tsh = schedule_u64(A->testing_schedule_hospitalized); f.tsa = schedule_u64(A->testing_schedule_arrivals);
   f.pre = T->ws_pre.p; f.traj = nullptr;
   f.pressure = A->pressure_out ? T->ws_pressure.p : nullptr;
-  f.src_mask = T->src_mask.p; f.day_chunk_start = T->day_chunk_start.p;
+  f.src_mask = T->src_mask.p; f.half_mask = H.has_half ? T->half_mask.p : nullptr; f.day_chunk_start = T->day_chunk_start.p;
   {
     // Counting a ward's pressure: deep branch-free steps (12 chunks per ward-day in one round trip) where the launch is bound by
     // latency -- few warps per SM (config 2: 8) or long wards (configs 4 and 5) -- and lean groups where
@@ -563,7 +566,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 
   if (std::getenv("AMRO_FAST_VERBOSE"))
     std::fprintf(stderr, "[amro] bits launch: shape %d ttd %d teams %lld G %d extra %d cluster %d grid %lld threads %d smem %zu\n", shape, ttd,
-                 (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), kTeamThreads, bits_shared_bytes());
+                 (long long)n_teams, G, extra, use_cluster, (long long)(n_teams * G + extra), kTeamThreads, bits_shared_bytes(half));
   EventPair& ev = T->next_kernel_events();
   AMRO_CUDA(cudaEventRecord(ev.a, st));
   bits_launch(st, f, shape, (int)(n_teams * G + extra));
@@ -883,7 +886,7 @@ size_t topology_bytes(const amro_topology& t) {
   // meta per record + the general path's arrays when uploaded + workspaces that grow with the runs
   size_t b = (size_t)H.R * (8 + 8 + 8 + 8 + 4) + (size_t)H.Rp * 16 + (H.push_src.size() + H.push_dst.size()) * 8;
   b += (size_t)H.Rp * 16 + (size_t)H.R * 8;
-  b += t.ws_pre.n * 16 + t.ws_traj.n * 16 + t.ws_pressure.n * 4 + t.ws_counts.n * 4 + t.src_mask.n * 4;
+  b += t.ws_pre.n * 16 + t.ws_traj.n * 16 + t.ws_pressure.n * 4 + t.ws_counts.n * 4 + (t.src_mask.n + t.half_mask.n) * 4;
   return b;
 }
 void destroy_topology(amro_topology* t) { amro_topology_destroy(t); }

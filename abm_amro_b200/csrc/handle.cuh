@@ -42,7 +42,7 @@ struct amro_topology {
   amro::DevBuf<uint32_t> init_seg, init_slot, seg_main_next;
   // bit-sliced kernel (built on first use from the device arrays above: the same for compiled and generated hospitals)
   bool pull_ready = false;
-  amro::DevBuf<uint32_t> src_mask;
+  amro::DevBuf<uint32_t> src_mask, half_mask;
   amro::DevBuf<int64_t> day_chunk_start;
   void ensure_pull() {
     if (pull_ready) return;
@@ -52,7 +52,8 @@ struct amro_topology {
     for (int64_t d = 0; d < n_days; ++d) dc[d + 1] = dc[d] + (ds[d + 1] - ds[d] + 31) / 32;
     day_chunk_start.upload(dc.data(), dc.size());
     src_mask.alloc((size_t)std::max<int64_t>(dc[n_days], 1));
-    amro::bits_build_src_mask(0, meta.p, day_start.p, day_chunk_start.p, n_days, H.max_rows_per_day, src_mask.p);
+    if (H.has_half) half_mask.alloc((size_t)std::max<int64_t>(dc[n_days], 1));
+    amro::bits_build_src_mask(0, meta.p, day_start.p, day_chunk_start.p, n_days, H.max_rows_per_day, src_mask.p, H.has_half ? half_mask.p : nullptr);
     AMRO_CUDA(cudaStreamSynchronize(0));
     pull_ready = true;
   }

@@ -132,7 +132,8 @@ struct FastArgs {
   // [n_teams][press_days = n_days + 1][max_segs_per_day][words per team][32] of 32-bit counts
   int64_t max_segs_per_day;
   int press_days;
-  const uint32_t* src_mask;        // one bit per record: it has a source (a predecessor or an initial row); word = 32-record chunk of a day
+  const uint32_t* src_mask;        // one bit per record: it has a source (a predecessor or an initial row) and weighs 1; word = 32-record chunk of a day
+  const uint32_t* half_mask;       // nullptr, or the same for the records that weigh 1/2
   const int64_t* day_chunk_start;  // [n_days + 1] first chunk of every day in src_mask
   int pull_deep;                   // which variant counts the ward pressure (kernels_bits.cu: pull_pressure / pull_pressure_lean)
 };
@@ -162,14 +163,14 @@ void fast_export_pressure(cudaStream_t st, const uint32_t* pressure, int64_t n_s
 constexpr int kBitsMaxTtd = 6;   // 0 .. 2: shift-register planes; 3 .. 6: a 3-bit countdown code per simulation
 int bits_sims_per_team();
 int bits_words_per_team();   // groups of 32 simulations of a team: the warps of a team pair up, one warp per word
-size_t bits_shared_bytes();
-int bits_max_coresident_ctas(int device, int ttd, int shape);
-int bits_max_coresident_clusters(int ttd, int shape, int cluster_size);
+size_t bits_shared_bytes(bool half);   // half: the instances for hospitals with weights 1/2 (more table rows per warp)
+int bits_max_coresident_ctas(int device, int ttd, int shape, bool half);
+int bits_max_coresident_clusters(int ttd, int shape, int cluster_size, bool half);
 void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid);
 // out[ward-day + ld*sim] = colonised count the ward-day started with (press_days = n_days + 1 runs only)
 // src_mask / day_chunk_start of a compiled hospital (device arrays; day_chunk_start from the host copy of day_start)
 void bits_build_src_mask(cudaStream_t st, const uint4* meta, const int64_t* day_start, const int64_t* day_chunk_start, int64_t n_days,
-                         int64_t max_rows_per_day, uint32_t* src_mask);
+                         int64_t max_rows_per_day, uint32_t* src_mask, uint32_t* half_mask /* nullptr: no half weights */);
 void bits_export_pressure(cudaStream_t st, const uint32_t* pressure, const int64_t* day_seg_start, int64_t n_days, int64_t max_segs,
                           int64_t press_days, int64_t S, int32_t* out, int64_t ld);
 

@@ -1,5 +1,5 @@
 // BITS path: the ward-level colonisation step with the state BIT-SLICED over simulations -- summary runs (per-day counts,
-// no trajectory) of unit-weight hospitals with time_to_detect <= 6, free-running mode, in ONE persistent kernel.
+// no trajectory) of hospitals with weights 1 and 1/2 and time_to_detect <= 6, free-running mode, in ONE persistent kernel.
 //
 // Replaces the same nest as kernels_fast.cu (src/amro/abm_wards.cpp:322-414 / :219-257 / :70-159 fused with the totals
 // :435-509).  Where kernels_fast.cu keeps a 16-bit code per (record, simulation) and steps two simulations per 32-bit
@@ -41,7 +41,9 @@ constexpr int kBitsSims = 32 * kBW;                 // simulations of a team
 constexpr int kBSegs = AMRO_BITS_SEGS;              // ring of ward-day tables per warp (power of two)
 constexpr int kTabWords = 80;                       // a table row: 5 tables x 16 words (14 planes, the "always" mask, a zero)
 constexpr int kTU = 0, kTA = 16, kTB = 32, kTUh = 48, kTAh = 64;   // word offsets of the tables in a row
-constexpr int kZeroRowB = kBSegs * 2;               // rows (ward-day, is_new) + one all-zero row: lanes without a record step against it
+// table rows of a warp: (ward-day slot, is_new) -- times the weight class (1 | 1/2) in the instances for hospitals with half
+// weights -- plus one all-zero row: lanes without a record step against it
+__host__ __device__ constexpr int zero_row(bool half) { return kBSegs * (half ? 4 : 2); }
 constexpr int kCntPlanes = 5;                       // vertical counters count to 31
 #ifndef AMRO_BITS_DENSE_BLOCKS
 #define AMRO_BITS_DENSE_BLOCKS 6
@@ -124,7 +126,7 @@ __device__ __forceinline__ void vflush(VCount* const (&vc)[N], uint32_t (&out)[N
 //   par   double [6][kBitsSims]                      alpha, beta, gamma, rho_hospital, alpha2, rho_imported (:79-84)
 //   r16   uint32 [kBitsSims]                          the run's dither (rng.cuh: kRunDitherIndex)
 //   rc    uint32 [is_new][word][48]                   tables A, B, Ah under a finite force of infection (they do not depend on the ward)
-//   tab   uint32 [kZeroRowB + 1 rows][kTabWords]      per warp: rows (ward-day slot, is_new) of the warp's word
+//   tab   uint32 [zero_row(HALF) + 1 rows][kTabWords] per warp: rows (ward-day slot, is_new[, weight class]) of the warp's word
 //   prep  double [kBSegs][32] + uint32 [kBSegs][32]   per warp: beta / N and the dither of the next batch of ward-days (the part
 //                                                     of a table that does not depend on the ward's pressure, computed while
 //                                                     the warp would otherwise wait for the previous day to complete)
@@ -146,17 +148,20 @@ constexpr size_t kTmaBytes = 2 * 64 * sizeof(uint4) + 2 * sizeof(uint64_t);
 #else
 constexpr size_t kTmaBytes = 0;
 #endif
-constexpr size_t kWarpSharedBytes = sizeof(uint32_t) * (kZeroRowB + 1) * kTabWords + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32 + kTmaBytes;
-static_assert(kCtaSharedBytes % 16 == 0 && kWarpSharedBytes % 16 == 0, "table rows are read as uint4");
-__host__ __device__ inline size_t bits_smem_bytes(int threads) { return kCtaSharedBytes + (size_t)(threads / 32) * kWarpSharedBytes; }
+__host__ __device__ constexpr size_t warp_shared_bytes(bool half) {
+  return sizeof(uint32_t) * (zero_row(half) + 1) * kTabWords + (sizeof(double) + sizeof(uint32_t)) * kBSegs * 32 + kTmaBytes;
+}
+static_assert(kCtaSharedBytes % 16 == 0 && warp_shared_bytes(false) % 16 == 0 && warp_shared_bytes(true) % 16 == 0, "table rows are read as uint4");
+__host__ __device__ inline size_t bits_smem_bytes(int threads, bool half) { return kCtaSharedBytes + (size_t)(threads / 32) * warp_shared_bytes(half); }
+template <bool HALF>
 __device__ __forceinline__ BitsShared carve_bits(unsigned char* raw, int warp) {
   BitsShared s;
   s.par = reinterpret_cast<double*>(raw);
   s.r16 = reinterpret_cast<uint32_t*>(raw + sizeof(double) * 6 * kBitsSims);
   s.rc = s.r16 + kBitsSims;
-  unsigned char* mine = raw + kCtaSharedBytes + (size_t)warp * kWarpSharedBytes;
+  unsigned char* mine = raw + kCtaSharedBytes + (size_t)warp * warp_shared_bytes(HALF);
   s.tab = reinterpret_cast<uint32_t*>(mine);
-  s.prep_bn = reinterpret_cast<double*>(s.tab + (kZeroRowB + 1) * kTabWords);
+  s.prep_bn = reinterpret_cast<double*>(s.tab + (zero_row(HALF) + 1) * kTabWords);
   s.prep_r16 = reinterpret_cast<uint32_t*>(s.prep_bn + kBSegs * 32);
 #ifdef AMRO_BITS_TMA
   s.tma = reinterpret_cast<uint4*>(s.prep_r16 + kBSegs * 32);
@@ -373,13 +378,15 @@ __device__ __forceinline__ void pull_pressure_lean(const uint32_t* pre_x, const 
 // What finish_tables_bits needs about the day
 struct DayIn {
   const uint32_t* pre_x;      // colonised plane of the day's state-ring buffer: word .x of slot 0 of the warp's word, + 4 * lane
-  const uint32_t* mask_day;   // src_mask of the day's first chunk
+  const uint32_t* mask_day;   // src_mask of the day's first chunk (hospitals with half weights: the full-weight records only)
+  const uint32_t* half_day;   // nullptr, or the same for the records that weigh 1/2
   const int64_t* seg_rows;    // seg_row_start of the day's first ward-day
   int64_t da;                 // first position of the day
   uint32_t* press_out;        // nullptr, or where the day's counts go ([ward-day of the day][kBW][32], + lane)
   bool test_h, test_a;
 };
 // deep: the launch keeps few warps per SM busy, or its wards are long (latency-bound counting: deep, branch-free pull steps)
+template <bool HALF>
 __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const BitsCtx& c, const DayIn& in, uint32_t b0, uint32_t b1, bool deep) {
   const int lane = threadIdx.x & 31;
   const int sim = c.w * 32 + lane;
@@ -395,21 +402,27 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
     uint32_t rows[3];
     if (lane < 3) rows[0] = (uint32_t)(__ldg(in.seg_rows + min(sl0 + (uint32_t)lane, b1)) - in.da);
     rows[2] = __shfl_sync(0xFFFFFFFFu, rows[0], 2); rows[1] = __shfl_sync(0xFFFFFFFFu, rows[0], 1); rows[0] = __shfl_sync(0xFFFFFFFFu, rows[0], 0);
-    if (sl0 + 1u < b1) {
-      if (deep) pull_pressure<2>(in.pre_x, in.mask_day, rows, cnt, lane);
-      else pull_pressure_lean<2>(in.pre_x, in.mask_day, rows, cnt, lane);
-    } else {   // a single ward-day: its tables are built twice
-      const uint32_t r1[2] = {rows[0], rows[1]};
-      uint32_t c1[1];
-      if (deep) pull_pressure<1>(in.pre_x, in.mask_day, r1, c1, lane);
-      else pull_pressure_lean<1>(in.pre_x, in.mask_day, r1, c1, lane);
-      cnt[0] = cnt[1] = c1[0];
-    }
+    uint32_t cnth[2] = {0u, 0u};   // colonised records that weigh 1/2 (hospitals with patients split over two wards)
+    auto pull = [&](const uint32_t* mask, uint32_t (&out)[2]) {
+      if (sl0 + 1u < b1) {
+        if (deep) pull_pressure<2>(in.pre_x, mask, rows, out, lane);
+        else pull_pressure_lean<2>(in.pre_x, mask, rows, out, lane);
+      } else {   // a single ward-day: its tables are built twice
+        const uint32_t r1[2] = {rows[0], rows[1]};
+        uint32_t c1[1];
+        if (deep) pull_pressure<1>(in.pre_x, mask, r1, c1, lane);
+        else pull_pressure_lean<1>(in.pre_x, mask, r1, c1, lane);
+        out[0] = out[1] = c1[0];
+      }
+    };
+    pull(in.mask_day, cnt);
+    if (HALF) pull(in.half_day, cnth);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const uint32_t sl = min(sl0 + (uint32_t)u, b1 - 1u);
       slot[u] = (int)(sl & (kBSegs - 1));
-      if (in.press_out) in.press_out[(int64_t)sl * (kBW * 32)] = cnt[u];   // every run that touches the ward-day writes the same count
+      // every run that touches the ward-day writes the same count (in halves when the hospital has half weights, like k_fast)
+      if (in.press_out) in.press_out[(int64_t)sl * (kBW * 32)] = HALF ? 2u * cnt[u] + cnth[u] : cnt[u];
       bn[u] = sh.prep_bn[slot[u] * 32 + lane];
       r16[u] = sh.prep_r16[slot[u] * 32 + lane];
     }
@@ -417,7 +430,8 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
     bool finite[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      F[u] = __dmul_rn(bn[u], (double)cnt[u]);   // :98-99, sum(W) = the count of colonised records
+      // :98-99, sum(W) = colonised full-weight records + half of the colonised half-weight ones (exact in any order)
+      F[u] = __dmul_rn(bn[u], HALF ? __dadd_rn((double)cnt[u], __dmul_rn(0.5, (double)cnth[u])) : (double)cnt[u]);
       finite[u] = fabs(F[u]) <= 1.7976931348623157e308;
     }
     const bool all_finite = __all_sync(0xFFFFFFFFu, finite[0] && finite[1]);
@@ -442,7 +456,7 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
       const double rho = h ? rho_i : rho_h;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        uint32_t* row = sh.tab + (slot[u] * 2 + h) * kTabWords;
+        uint32_t* row = sh.tab + ((slot[u] * 2 + h) * (HALF ? 2 : 1)) * kTabWords;
         row[(lane < 16 ? kTU : kTUh - 16) + lane] = tw[h * 2 + u];
         if (all_finite) {
           const uint4* rc = reinterpret_cast<const uint4*>(sh.rc + (h * kBW + c.w) * 48);
@@ -457,6 +471,34 @@ __device__ __forceinline__ void finish_tables_bits(const BitsShared& sh, const B
           store_planes(row, kTAh, -1, bAh, 0u, lane);
         }
       }
+    }
+    if (HALF) {
+      // rows of the records that weigh 1/2: uncolonised ones feel the ward like everybody (W = 0: the planes above), colonised
+      // ones with W = 1/2 (P = coef / 2 + F / 2 + gamma h, :108-112): ward-dependent, dithered per ward-day
+      uint32_t ta[4], tah[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool flag = h ? test_a : test_h;
+        const double rho = h ? rho_i : rho_h;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double P1 = class_probability(1, h, F[u], alpha, alpha2, gamma, 0.5), P2 = class_probability(2, h, F[u], alpha, alpha2, gamma, 0.5);
+          const uint32_t bA = (threshold30(P1) + r16[u]) >> 16, bB = (threshold30(P2) + r16[u]) >> 16;
+          ta[h * 2 + u] = bA | (bB << 16);
+          tah[h * 2 + u] = flag ? (threshold30(__dmul_rn(clamp01(P1), rho)) + r16[u]) >> 16 : 0u;
+        }
+      }
+      warp_transpose32_multi<4>(ta, lane);
+      warp_transpose32_multi<4>(tah, lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t* row = sh.tab + ((slot[u] * 2 + h) * 2 + 1) * kTabWords;
+          row[(lane < 16 ? kTU : kTUh - 16) + lane] = tw[h * 2 + u];
+          row[(lane < 16 ? kTA : kTB - 16) + lane] = ta[h * 2 + u];
+          if (lane < 16) row[kTAh + lane] = tah[h * 2 + u];
+        }
     }
   }
 }
@@ -506,7 +548,7 @@ struct DayState {
   }
 };
 // ---- one day of the warp's word: the run of the day's records that belongs to this warp's pair (:384-407) ---------------
-template <int TTD>
+template <int TTD, bool HALF>
 __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const FastArgs& a, const BitsCtx& c, int d, const DayPlan& pl,
                                                  int64_t seg0_next, TeamBarrier& bar, DayState& ds) {
   const int lane = threadIdx.x & 31;
@@ -541,6 +583,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
     DayIn in;
     in.pre_x = reinterpret_cast<const uint32_t*>(pday) + 4 * lane;
     in.mask_day = a.src_mask + __ldg(&a.day_chunk_start[d]);
+    in.half_day = HALF ? a.half_mask + __ldg(&a.day_chunk_start[d]) : nullptr;
     in.seg_rows = a.seg_row_start + seg0;
     in.da = da;
     in.press_out = c.press ? c.press + (int64_t)d * a.max_segs_per_day * (kBW * 32) + lane : nullptr;
@@ -554,7 +597,7 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 #ifdef AMRO_EXP_NOTABLES   // timing experiment (wrong results): tables built on the first two days only
       if (d < 2)
 #endif
-      finish_tables_bits(sh, c, in, sl, sl + n_tab, a.pull_deep != 0);
+      finish_tables_bits<HALF>(sh, c, in, sl, sl + n_tab, a.pull_deep != 0);
       __syncwarp();
       const uint32_t rb = max(pl.w0, (uint32_t)(__ldg(in.seg_rows + sl) - da)) - pl.w0;
       const uint32_t re = min(pl.w1, (uint32_t)(__ldg(in.seg_rows + sl + n_tab) - da)) - pl.w0;
@@ -602,7 +645,9 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
           const int h = (int)(info >> kInfoHShift);
           const int64_t orig = a.identity_order ? da + pl.w0 + i : (int64_t)meta.w;
           const bool on = i < n_run && segl - sl < n_tab;   // this batch's records
-          const uint4* tr = reinterpret_cast<const uint4*>(sh.tab + (on ? (int)(segl & (kBSegs - 1)) * 2 + h : kZeroRowB) * kTabWords);
+          int row_i = (int)(segl & (kBSegs - 1)) * 2 + h;
+          if (HALF) row_i = row_i * 2 + (int)((info >> kInfoHalfShift) & 1u);   // the record weighs 1/2
+          const uint4* tr = reinterpret_cast<const uint4*>(sh.tab + (on ? row_i : zero_row(HALF)) * kTabWords);
           const uint32_t next = on ? meta.y : kNone;
           if (!on || src == kSrcNone) pre = make_uint4(0u, 0u, 0u, 0u);   // (C = 0, D = inf) x 32, :359-360
 
@@ -687,12 +732,12 @@ __device__ __forceinline__ void process_day_bits(const BitsShared& sh, const Fas
 #endif
 }
 
-template <int TTD, int THREADS, int MINB>
+template <int TTD, int THREADS, int MINB, bool HALF>
 __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kWarps = THREADS / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const BitsShared sh = carve_bits(smem_raw, warp);
+  const BitsShared sh = carve_bits<HALF>(smem_raw, warp);
   const int big = a.teams_plus_one * (a.ctas_per_team + 1);
   const bool in_big = (int)blockIdx.x < big;
   const int G = a.ctas_per_team + (in_big ? 1 : 0);
@@ -721,7 +766,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 
   // ---- team setup: parameters, run-constant tables and the all-zero rows to shared memory --------------------------------
   for (int q = tid; q < 6 * kBitsSims; q += THREADS) sh.par[q] = a.params[(team_sim0 + q % kBitsSims) + a.p_ld * (q / kBitsSims)];
-  for (int q = lane; q < kTabWords; q += 32) sh.tab[kZeroRowB * kTabWords + q] = 0u;
+  for (int q = lane; q < kTabWords; q += 32) sh.tab[zero_row(HALF) * kTabWords + q] = 0u;
   __syncthreads();
   for (int it = warp; it < 2 * kBW; it += kWarps) {   // (is_new, word): lane = simulation
     const int h = it / kBW, w = it % kBW, sim = w * 32 + lane;
@@ -806,7 +851,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
     if (d < 2)
 #endif
     bar.wait();
-    process_day_bits<TTD>(sh, a, c, d, plan, seg0_next, bar, ds);
+    process_day_bits<TTD, HALF>(sh, a, c, d, plan, seg0_next, bar, ds);
     ds.next(a);
     plan = plan_day(a, d + 1, gw, n_gw, plan);   // static: ready before the next wait ends
   }
@@ -814,18 +859,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_bits(const __grid_constant__ 
 }
 
 // src_mask: bit j of word day_chunk_start[d] + k <=> record 32 k + j of day d has a source (a predecessor or an initial row).
+// Hospitals with half weights get two masks: src_mask = the sourced records that weigh 1, half_mask = those that weigh 1/2.
 // One warp per chunk (grid.y = day).
 __global__ void k_bits_src_mask(const uint4* __restrict__ meta, const int64_t* __restrict__ day_start, const int64_t* __restrict__ day_chunk_start,
-                                int64_t n_days, uint32_t* __restrict__ src_mask) {
+                                int64_t n_days, uint32_t* __restrict__ src_mask, uint32_t* __restrict__ half_mask) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_x = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t d = blockIdx.y; d < n_days; d += gridDim.y) {
     const int64_t da = day_start[d], n = day_start[d + 1] - da, n_chunks = (n + 31) / 32;
     for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < n_chunks; k += warps_x) {
       const int64_t i = k * 32 + lane;
-      const bool has = i < n && ((__ldg(&meta[da + i].x) >> kInfoSrcShift) & 3u) != kSrcNone;
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-      if (lane == 0) src_mask[day_chunk_start[d] + k] = m;
+      const uint32_t info = i < n ? __ldg(&meta[da + i].x) : 0u;
+      const bool has = i < n && ((info >> kInfoSrcShift) & 3u) != kSrcNone;
+      const bool half = has && half_mask != nullptr && ((info >> kInfoHalfShift) & 1u);
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, has && !half), mh = __ballot_sync(0xFFFFFFFFu, half);
+      if (lane == 0) {
+        src_mask[day_chunk_start[d] + k] = m;
+        if (half_mask) half_mask[day_chunk_start[d] + k] = mh;
+      }
     }
   }
 }
@@ -842,35 +893,38 @@ __global__ void k_bits_export_pressure(const uint32_t* __restrict__ pressure, co
   out[seg + ld * s] = (int32_t)pressure[((team * press_days + d) * max_segs + sl) * (kBW * 32) + w * 32 + lane];
 }
 
-template <int TTD>
+template <int TTD, bool HALF>
 const void* bits_kernel_of(int shape) {
-  return shape == kShapeRoomy   ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1>
-         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kBitsDenseBlocks>
-                                : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks>;
+  return shape == kShapeRoomy   ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1, HALF>
+         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kBitsDenseBlocks, HALF>
+                                : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks, HALF>;
 }
-const void* bits_kernel_ptr(int ttd, int shape) {
-  return ttd == 0 ? bits_kernel_of<0>(shape) : ttd == 1 ? bits_kernel_of<1>(shape) : ttd == 2 ? bits_kernel_of<2>(shape) : bits_kernel_of<3>(shape);
+template <bool HALF>
+const void* bits_kernel_half(int ttd, int shape) {
+  return ttd == 0 ? bits_kernel_of<0, HALF>(shape) : ttd == 1 ? bits_kernel_of<1, HALF>(shape) : ttd == 2 ? bits_kernel_of<2, HALF>(shape)
+                                                                                                    : bits_kernel_of<3, HALF>(shape);
 }
+const void* bits_kernel_ptr(int ttd, int shape, bool half) { return half ? bits_kernel_half<true>(ttd, shape) : bits_kernel_half<false>(ttd, shape); }
 
 }  // namespace
 
 int bits_sims_per_team() { return kBitsSims; }
 int bits_words_per_team() { return kBW; }
-size_t bits_shared_bytes() { return bits_smem_bytes(kTeamThreads); }
+size_t bits_shared_bytes(bool half) { return bits_smem_bytes(kTeamThreads, half); }
 
-int bits_max_coresident_ctas(int device, int ttd, int shape) {
+int bits_max_coresident_ctas(int device, int ttd, int shape, bool half) {
   int per_sm = 0, sms = 0;
-  const void* k = bits_kernel_ptr(ttd, shape);
-  const size_t smem = bits_smem_bytes(kTeamThreads);
+  const void* k = bits_kernel_ptr(ttd, shape, half);
+  const size_t smem = bits_smem_bytes(kTeamThreads, half);
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kTeamThreads, smem));
   return per_sm * sms;
 }
 
-int bits_max_coresident_clusters(int ttd, int shape, int cluster_size) {
-  const void* k = bits_kernel_ptr(ttd, shape);
-  const size_t smem = bits_smem_bytes(kTeamThreads);
+int bits_max_coresident_clusters(int ttd, int shape, int cluster_size, bool half) {
+  const void* k = bits_kernel_ptr(ttd, shape, half);
+  const size_t smem = bits_smem_bytes(kTeamThreads, half);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   if (cluster_size > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
   cudaLaunchConfig_t cfg{};
@@ -887,8 +941,8 @@ int bits_max_coresident_clusters(int ttd, int shape, int cluster_size) {
 }
 
 void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid) {
-  const void* k = bits_kernel_ptr(a.ttd, shape);
-  const size_t smem = bits_smem_bytes(kTeamThreads);
+  const void* k = bits_kernel_ptr(a.ttd, shape, a.half_mask != nullptr);
+  const size_t smem = bits_smem_bytes(kTeamThreads, a.half_mask != nullptr);
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
   if (a.cluster_barrier) {
@@ -911,12 +965,12 @@ void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid) {
 }
 
 void bits_build_src_mask(cudaStream_t st, const uint4* meta, const int64_t* day_start, const int64_t* day_chunk_start, int64_t n_days,
-                         int64_t max_rows_per_day, uint32_t* src_mask) {
+                         int64_t max_rows_per_day, uint32_t* src_mask, uint32_t* half_mask) {
   if (n_days <= 0) return;
   const int64_t chunks = (max_rows_per_day + 31) / 32;
   const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>((chunks + 7) / 8, 1), 4096);
   const unsigned gy = (unsigned)std::min<int64_t>(n_days, 65535);
-  k_bits_src_mask<<<dim3(gx, gy), 256, 0, st>>>(meta, day_start, day_chunk_start, n_days, src_mask);
+  k_bits_src_mask<<<dim3(gx, gy), 256, 0, st>>>(meta, day_start, day_chunk_start, n_days, src_mask, half_mask);
   AMRO_CUDA(cudaGetLastError());
 }
 

@@ -98,7 +98,7 @@ CASES = [  # wards, census, days, S, ttd, tsh, tsa
     (12, 150, 9, 33, 5, 2, 2), (2, 700, 6, 8, 1, 3, 1),
     (40, 100, 8, 17, 1, 2, 1),   # tiny wards: a 32-record trip spans more ward-days than a warp's table ring holds
     (5, 300, 30, 20, 6, 7, 1), (3, 200, 25, 40, 3, 2, 1), (4, 100, 15, 64, 4, 1, 3),   # time_to_detect 3 .. 6: the 3-bit countdown code of k_bits
-    (6, 400, 12, 19, 2, 3, 1, 0.2), (3, 90, 10, 16, 0, 1, 1, 0.5)]   # last entry: share of patients split over two wards (weight 1/2)
+    (6, 400, 12, 19, 2, 3, 1, 0.2), (3, 90, 10, 16, 0, 1, 1, 0.5), (4, 1200, 10, 70, 6, 7, 1, 0.3), (2, 50, 8, 33, 1, 2, 2, 0.6)]   # last entry: share of patients split over two wards (weight 1/2)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
@@ -127,7 +127,7 @@ def test_replay_and_philox_match_oracle(case, shape):
             summary_only = topo.simulate(par, icp, idp, ttd, tsh, tsa, 5, path=path, want_moments=True)  # two-day ring, no trajectory
             assert np.array_equal(summary_only.counts_colonized, free.counts_colonized)
             assert np.array_equal(summary_only.counts_detected, free.counts_detected)
-            if path == capi.PATH_FAST and p_split == 0.0 and ttd <= 6:    # the bit-sliced kernel takes every time_to_detect up to 6
+            if path == capi.PATH_FAST and ttd <= 6:    # the bit-sliced kernel takes weights 1 and 1/2 and every time_to_detect up to 6
                 assert summary_only.kernel_kind == capi.KERNEL_BITS
             c, d = free.counts_colonized.astype(float), free.counts_detected.astype(float)   # exact integers in float64
             assert np.array_equal(summary_only.moments, np.stack([c.sum(1), (c * c).sum(1), d.sum(1), (d * d).sum(1)], 1))

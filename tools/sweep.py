@@ -17,14 +17,14 @@ import numpy as np  # noqa: E402
 from abm_amro_b200 import engine, synth  # noqa: E402
 
 SHAPES = {"cfg2": (30, 10_000, 365, 1000), "cfg3": (20, 5_000, 180, 65_536), "cfg3s": (20, 5_000, 180, 16_384),
-          "cfg4s": (500, 200_000, 30, 256), "mid": (30, 40_000, 60, 768)}
+          "cfg3x8": (20, 5_000, 180, 8_192), "cfg4s": (500, 200_000, 30, 256), "mid": (30, 40_000, 60, 768)}
 
 
 def main():
     name = sys.argv[1]
     nw, cen, nd, S = SHAPES[name]
     wm, tp, n_init = synth.make_hospital(nw, cen, nd, seed=1)
-    par = synth.tutorial_parameters(S) if name != "cfg3" and name != "cfg3s" else synth.particle_parameters(S, seed=100)
+    par = synth.tutorial_parameters(S) if not name.startswith("cfg3") else synth.particle_parameters(S, seed=100)
     updates = float(wm.shape[0]) * S
     managed = set()
     with engine.Topology(wm, tp, n_init) as topo:

@@ -11,4 +11,7 @@ for (nw, cen, nd, S, ps) in [(30, 10000, 60, 256, 0.05), (30, 10000, 60, 1000, 0
         for _ in range(2):
             r = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42, path=capi.PATH_GENERAL)
         upd = wm.shape[0] * S
+        f = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)
+        f = topo.simulate(par, 0.2, 0.2, 2, 7, 1, 42)
+        print(f"fused kernel kind {f.kernel_kind} (2 = bit-sliced): kernel {f.kernel_ms:.2f} ms; counts equal to the float64 path: {bool((f.counts_colonized == r.counts_colonized).all() and (f.counts_detected == r.counts_detected).all())}")
         print(f"{("fast" if r.path_used == capi.PATH_FAST else "general")} path {nw}w x {cen} x {nd}d x {S}: kernel {r.kernel_ms:.2f} ms, {upd / r.kernel_ms / 1e6:.1f} G updates/s, launches {r.launches}")
