@@ -658,3 +658,20 @@ def test_day_moments_peer_stores_match_the_all_reduce_arithmetic():
         assert torch.equal(b, want)
     with pytest.raises(ValueError):
         capi.check(capi.lib().amro_day_moments_peers(cc.data_ptr(), cd.data_ptr(), n_days, S, n_days, dst, 17, 0, 0))
+
+
+def test_half_weight_hospital_pressures_agree_between_the_fused_kernels(monkeypatch):
+    # patients split over two wards weigh 1/2 in each: the bit-sliced kernel pulls sum(W) through two masks (full- and half-weight
+    # records) and exports it in halves, like the 16-bit-code kernel's pushed counts; same draws, so the same numbers
+    wm, tp, n_init = synth.make_hospital(5, 600, 12, seed=11, p_split=0.25)
+    S = 70
+    par = synth.particle_parameters(S, seed=2)
+    with engine.Topology(wm, tp, n_init) as topo:
+        assert topo.info.fast_eligible
+        a = topo.simulate(par, 0.3, 0.4, 3, 2, 1, 17, want_pressure=True)
+        assert a.kernel_kind == capi.KERNEL_BITS
+        monkeypatch.setenv("AMRO_FAST_NOBITS", "1")
+        b = topo.simulate(par, 0.3, 0.4, 3, 2, 1, 17, want_pressure=True)
+        assert b.kernel_kind == capi.KERNEL_CODES
+        assert np.array_equal(a.counts_colonized, b.counts_colonized) and np.array_equal(a.counts_detected, b.counts_detected)
+        assert np.array_equal(a.pressure, b.pressure) and a.pressure.max() > 2     # in halves
