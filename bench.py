@@ -230,7 +230,8 @@ def _algorithmic_bytes(S):
 
 def time_workload(topo, par_np, S, sim_offset, dev, steps, warmup, world, dist, flush, local_rank):
     """`steps` device-resident runs of one compiled hospital, enqueued back to back on the current stream (asynchronous C ABI
-    calls: kernel -> day moments -> all-reduce, no host synchronisation inside the timed region).  Returns a dict."""
+    calls: kernel -> the run's collective (N > 1: peer-store moments kernel, or day moments + NCCL all-reduce), no host synchronisation
+    inside the timed region).  Returns a dict."""
     import torch
     from abm_amro_b200 import ensemble
     n_days = topo.info.n_days_out
