@@ -458,6 +458,18 @@ void run_fast(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
 bool bits_eligible(const amro_topology* T, const amro_sim_args* A) {
   const HostTopology& H = T->H;
   if (std::getenv("AMRO_FAST_NOBITS")) return false;
+  if (!std::getenv("AMRO_FAST_BITS")) {
+    // The bit-sliced kernel counts a ward-day's pressure once per run that touches it.  Hospitals whose wards are many times
+    // longer than a run (one ward of 10 000 beds: every warp would count the whole ward to step 280 records) go to the kernel
+    // that pushes pressure instead (measured: 1.16 against 1.89 ms, profiles/sweeps.txt).  The run length is estimated the way
+    // run_bits sizes its teams: all CTA slots dealt out to the teams, at least 8 trips of 32 records per warp.
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, T->device) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+    const int64_t n_teams = (A->n_sims + bits_sims_per_team() - 1) / bits_sims_per_team();
+    const int64_t pairs = std::max<int64_t>(1, (int64_t)sms * kTeamMinBlocks / std::max<int64_t>(n_teams, 1)) * (kTeamThreads / 32) / bits_words_per_team();
+    const int64_t run = std::max<int64_t>(256, H.max_rows_per_day / pairs);
+    if (H.max_seg_rows > 8 * run) return false;
+  }
   return A->rng_mode != AMRO_RNG_REPLAY && !A->keep_trajectory && !A->state_out && !A->p_out &&
          A->time_to_detect >= 0 && A->time_to_detect <= kBitsMaxTtd;
 }
@@ -482,9 +494,9 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // A pair of warps steps a run of records (one warp per word).  Team size: the largest number of whole CTAs-per-SM layers
   // (the grid then loads every SM alike) that still leaves a warp about `trips` 32-record trips a day -- measured on config 2:
   // 18 CTAs per team (2 per SM, 8.7 trips) beat 12, 16, 24 and 36 (profiles/sweeps.txt).
-  // A ward-day's pressure is counted by every run that touches it: runs much shorter than the wards would spend their day counting,
-  // so a run is at least a quarter of the largest ward-day.
-  int trips = (int)std::max<int64_t>(8, (H.max_seg_rows + 127) / 128);
+  // (A ward-day's pressure is counted by every run that touches it, but counting a chunk costs a thirteenth of stepping it and a
+  // warp counts its wards whole however short its run is: more, shorter runs still win -- measured on a one-ward hospital.)
+  int trips = 8;
   if (const char* e = std::getenv("AMRO_BITS_TRIPS")) trips = std::max(1, std::atoi(e));
   int G = 1, extra = 0;
   const int64_t useful = std::max<int64_t>(1, H.max_rows_per_day * bits_words_per_team() / ((int64_t)trips * kTeamThreads));

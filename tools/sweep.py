@@ -17,7 +17,7 @@ import numpy as np  # noqa: E402
 from abm_amro_b200 import engine, synth  # noqa: E402
 
 SHAPES = {"cfg2": (30, 10_000, 365, 1000), "cfg3": (20, 5_000, 180, 65_536), "cfg3s": (20, 5_000, 180, 16_384),
-          "cfg3x8": (20, 5_000, 180, 8_192), "cfg4s": (500, 200_000, 30, 256), "mid": (30, 40_000, 60, 768)}
+          "cfg3x8": (20, 5_000, 180, 8_192), "oneward": (1, 10_000, 60, 1000), "twoward64": (2, 20_000, 30, 64), "cfg4s": (500, 200_000, 30, 256), "mid": (30, 40_000, 60, 768)}
 
 
 def main():
