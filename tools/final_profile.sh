@@ -2,7 +2,7 @@
 # The round's measured artefacts, one GPU (run under gpurun; results land in gpurun_out/<tag>_*):
 #   tools/final_profile.sh <tag>
 # gpu tests, smoke, the default bench line (config 2 + the config-3 block), the reference arm, configs 3 / 4 / 5 as their own
-# lines, the ncu launch list of the default command and one full capture of the bit-sliced kernel on configs 2, 3 and 4.
+# lines, the ncu launch list of the default command and one full capture of the bit-sliced kernel on configs 2, 3, 4 and 5.
 tag=${1:-run}; o=gpurun_out; mkdir -p $o
 timeout 1200 python -m pytest tests -m gpu -x -q > $o/${tag}_pytest.txt 2>&1; tail -1 $o/${tag}_pytest.txt
 python __graft_entry__.py smoke > $o/${tag}_smoke.txt 2>&1; tail -1 $o/${tag}_smoke.txt
@@ -22,4 +22,15 @@ ncu --set full --clock-control none --import-source on -k regex:k_bits -s 1 -c 1
 B4="python bench.py --workload cfg4_500w_1Mp_365d_256s --steps 2 --warmup 1 --no-cpu-baseline"
 $B4 > $o/${tag}_plain4.json 2>> $o/${tag}_bench.err && \
 ncu --set full --clock-control none --import-source on -k regex:k_bits -s 1 -c 1 -f -o $o/${tag}_k_bits_cfg4 $B4 > $o/${tag}_ncu4.log 2>&1
-ls -la $o | tail -25
+B5="python bench.py --workload cfg5_5kw_10Mp_730d_32s --steps 2 --warmup 1 --no-cpu-baseline"
+$B5 > $o/${tag}_plain5.json 2>> $o/${tag}_bench.err && \
+ncu --set full --clock-control none --import-source on -k regex:k_bits -s 1 -c 1 -f -o $o/${tag}_k_bits_cfg5 $B5 > $o/${tag}_ncu5.log 2>&1
+# summaries on the box; the reports themselves (12 MB each) stay behind except config 2's: gpurun_out/ comes back only below 64 MiB
+for c in "cfg2 3.65e9 cfg2_30w_10kp_365d_1000s" "cfg3 5.8982e10 cfg3_20w_5kp_180d_65536s" "cfg4 9.344e10 cfg4_500w_1Mp_365d_256s" "cfg5 2.336e11 cfg5_5kw_10Mp_730d_32s"; do
+  set -- $c; rep=$o/${tag}_k_bits_$1.ncu-rep
+  [ -f $rep ] || continue
+  python tools/ncu_summary.py $rep $2 > $o/${tag}_k_bits_$1_summary.txt 2>/dev/null
+  ncu -i $rep --page details > $o/${tag}_k_bits_$1_details.txt 2>/dev/null
+  [ "$1" = cfg2 ] || rm -f $rep
+done
+ls -la $o | tail -30
