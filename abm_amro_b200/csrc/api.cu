@@ -485,7 +485,7 @@ void run_bits(amro_topology* T, amro_sim_args* A, const DeviceInputs& in, cudaSt
   // about `trips` 32-record trips a day (every warp pays a fixed price per day: barrier, tables, count flushes).
   // AMRO_BITS_G fixes the team size, AMRO_BITS_CTAS_PER_SM caps the slots, AMRO_BITS_TRIPS sets the target.
   int shape = kShapeTeam;
-  if (const char* e = std::getenv("AMRO_BITS_SHAPE")) shape = e[0] == 'd' ? kShapeDense : e[0] == 'r' ? kShapeRoomy : kShapeTeam;
+  if (const char* e = std::getenv("AMRO_BITS_SHAPE")) shape = e[0] == 'r' ? kShapeRoomy : kShapeTeam;
   const bool shape_forced = std::getenv("AMRO_BITS_SHAPE") != nullptr;
   const bool half = H.has_half;
   int cap = bits_max_coresident_ctas(T->device, ttd, shape, half);

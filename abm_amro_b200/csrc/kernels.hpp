@@ -84,7 +84,6 @@ constexpr int kMaxCountdown = 8000;        // |countdown| representable in a 13-
 #define AMRO_TEAM_MINBLOCKS 4
 #endif
 constexpr int kShapeWide = 0, kShapeTeam = 1, kShapeRoomy = 2;   // Roomy: Team with the register budget of 3 CTAs per SM
-constexpr int kShapeDense = 3;                                   // bit-sliced kernel only: the register budget of 6 CTAs per SM
 constexpr int kWideThreads = AMRO_WIDE_THREADS;     // one CTA per SM
 constexpr int kTeamThreads = AMRO_TEAM_THREADS;
 constexpr int kTeamMinBlocks = AMRO_TEAM_MINBLOCKS; // CTAs per SM the team shape's register budget is sized for

@@ -45,10 +45,7 @@ constexpr int kTU = 0, kTA = 16, kTB = 32, kTUh = 48, kTAh = 64;   // word offse
 // weights -- plus one all-zero row: lanes without a record step against it
 __host__ __device__ constexpr int zero_row(bool half) { return kBSegs * (half ? 4 : 2); }
 constexpr int kCntPlanes = 5;                       // vertical counters count to 31
-#ifndef AMRO_BITS_DENSE_BLOCKS
-#define AMRO_BITS_DENSE_BLOCKS 6
-#endif
-constexpr int kBitsDenseBlocks = AMRO_BITS_DENSE_BLOCKS;   // CTAs per SM the dense shape's register budget is sized for
+// (an instance for 6 CTAs per SM -- 80 registers, 100-900 B of spills -- was measured slower on every configuration and is gone)
 constexpr int kFlushTrips = (1 << kCntPlanes) - 1;
 static_assert(kDrawBits == 14, "table rows hold 14 planes + the always mask");
 
@@ -895,9 +892,8 @@ __global__ void k_bits_export_pressure(const uint32_t* __restrict__ pressure, co
 
 template <int TTD, bool HALF>
 const void* bits_kernel_of(int shape) {
-  return shape == kShapeRoomy   ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1, HALF>
-         : shape == kShapeDense ? (const void*)k_bits<TTD, kTeamThreads, kBitsDenseBlocks, HALF>
-                                : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks, HALF>;
+  return shape == kShapeRoomy ? (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks - 1, HALF>
+                              : (const void*)k_bits<TTD, kTeamThreads, kTeamMinBlocks, HALF>;
 }
 template <bool HALF>
 const void* bits_kernel_half(int ttd, int shape) {
