@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <atomic>
 #include <cstdlib>
 #include <numeric>
@@ -46,6 +47,9 @@ int compile_threads(int64_t n) {
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
   return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(hw, cap), n / 2));
 }
+// scratch array of n elements set to `v` by n_thr threads (a std::vector would be filled -- and its pages touched -- by one)
+template <class T>
+std::unique_ptr<T[]> filled(int64_t n, T v, int n_thr);
 // f(lo, hi, block) on n_thr contiguous blocks of [0, n); exceptions of a block are rethrown (the first block's first)
 template <class F>
 void parallel_blocks(int64_t n, int n_thr, F f) {
@@ -66,6 +70,14 @@ inline int64_t as_day(double v, int64_t limit) {
   if (!(v >= 0.0) || v > (double)limit) return -1;
   const int64_t i = (int64_t)v;
   return ((double)i == v) ? i : -1;
+}
+
+template <class T>
+std::unique_ptr<T[]> filled(int64_t n, T v, int n_thr) {
+  std::unique_ptr<T[]> a(new T[(size_t)std::max<int64_t>(n, 1)]);
+  T* p = a.get();
+  parallel_blocks(n, n_thr, [&](int64_t lo, int64_t hi, int) { std::fill(p + lo, p + hi, v); });
+  return a;
 }
 
 }  // namespace
@@ -93,10 +105,11 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   const int64_t D = T.total_days + 1;
 
   // ---- per original row: day, totals day, h, w --------------------------------------------------
-  std::vector<int64_t> row_day(R);
+  const std::unique_ptr<int64_t[]> row_day_a(new int64_t[(size_t)std::max<int64_t>(R, 1)]);   // every element is written in the row pass
+  int64_t* const row_day = row_day_a.get();
   T.h.resize(R);
   T.w.resize(R);
-  T.count_day.assign(R, -1);
+  T.count_day.resize(R);   // every element is written below
   const int n_thr = compile_threads(R);
   double cmax = R ? at(wm, ld, 0, 0) : 0.0;
   {
@@ -239,7 +252,8 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   // C/D columns of row trunc(next_day); a later source wins.  A stepped row therefore starts its own day
   // from the last write made on an EARLIER day (or its initial state), and a write made on its own or a
   // later day only changes what the returned matrix shows for it.
-  std::vector<int64_t> pre_src(T.Rp, -1);  // original row of the effective predecessor
+  const std::unique_ptr<int64_t[]> pre_src_a = filled<int64_t>(T.Rp, -1, n_thr);   // original row of the effective predecessor
+  int64_t* const pre_src = pre_src_a.get();
   T.day_push_start.assign(D + 1, 0);
   T.simple_final = (T.Rp == R);
   bool ring = true;
@@ -249,9 +263,11 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   // replays the reference's order of writes.
   bool links_done = false;
   if (n_thr > 1) {
-    std::vector<int64_t> target(T.Rp, -1);                       // per position: the row its record writes to, or -1
-    std::vector<std::atomic<uint32_t>> n_src((size_t)R);         // per row: links that point to it
-    std::vector<int64_t> src_of((size_t)R, -1);                  // per row: its source (meaningful where n_src == 1)
+    const std::unique_ptr<int64_t[]> target_a = filled<int64_t>(T.Rp, -1, n_thr);   // per position: the row its record writes to, or -1
+    const std::unique_ptr<int64_t[]> src_of_a = filled<int64_t>(R, -1, n_thr);      // per row: its source (meaningful where n_src == 1)
+    int64_t* const target = target_a.get();
+    int64_t* const src_of = src_of_a.get();
+    std::unique_ptr<std::atomic<uint32_t>[]> n_src(new std::atomic<uint32_t>[(size_t)std::max<int64_t>(R, 1)]);   // per row: links that point to it
     parallel_blocks(R, n_thr, [&](int64_t lo, int64_t hi, int) { for (int64_t r = lo; r < hi; ++r) n_src[(size_t)r].store(0u, std::memory_order_relaxed); });
     std::atomic<int64_t> bad_pos{INT64_MAX};
     std::atomic<bool> multi{false};
@@ -366,9 +382,13 @@ void compile_topology(const double* wm, int64_t R, int64_t n_cols, int64_t ld,
   else if (T.max_rows_per_day >= (int64_t)0xFFFFFFF0u) T.why_not_fast = "too many records in one day";
   else if (T.max_segs_per_day >= (int64_t)kInfoSegMask) T.why_not_fast = "too many wards in one day";
   if (T.why_not_fast.empty()) {
-    T.meta_info.resize(T.Rp);
-    T.meta_next.assign(T.Rp, kNone);
-    T.meta_nseg.assign(T.Rp, kNone);
+    T.meta_info.resize(T.Rp);   // written for every position below
+    T.meta_next.resize(T.Rp);
+    T.meta_nseg.resize(T.Rp);
+    parallel_blocks(T.Rp, n_thr, [&](int64_t lo, int64_t hi, int) {
+      std::fill(T.meta_next.begin() + lo, T.meta_next.begin() + hi, kNone);
+      std::fill(T.meta_nseg.begin() + lo, T.meta_nseg.begin() + hi, kNone);
+    });
     T.init_seg.assign(n_init, kNone);
     T.init_slot.assign(n_init, kNone);
     T.day_has_init.assign(D, 0);

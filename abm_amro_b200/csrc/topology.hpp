@@ -6,7 +6,9 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace amro {
@@ -17,6 +19,21 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no segment" / "no successor
 constexpr uint32_t kSrcNone = 0u, kSrcPrev = 1u, kSrcInit = 2u;
 constexpr uint32_t kInfoHShift = 31, kInfoSrcShift = 29, kInfoHalfShift = 28, kInfoNextHalfShift = 27,
                    kInfoSegMask = (1u << kInfoNextHalfShift) - 1u;
+
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the per-row arrays of a hospital of millions of
+// rows are then first written -- and their pages first touched -- by the compiler's threads instead of one zero-filling loop
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T> using RowVec = std::vector<T, NoInitAlloc<T>>;
 
 struct HostTopology {
   int64_t R = 0, n_init = 0;
@@ -33,24 +50,24 @@ struct HostTopology {
   // position p in [0,R): stepped rows first, sorted by (day, ward, original index) -- the order the
   // reference visits them (day loop :381, unique() ascending wards :235, find() ascending rows :241);
   // rows that are never stepped follow in original order.
-  std::vector<int64_t> order;          // [R]  position -> original row
-  std::vector<int64_t> pos_of;         // [R]  original row -> position
+  RowVec<int64_t> order;               // [R]  position -> original row
+  RowVec<int64_t> pos_of;              // [R]  original row -> position
   std::vector<int64_t> day_start;      // [total_days+2] first position of each day
   std::vector<int64_t> day_seg_start;  // [total_days+2] first segment of each day
   std::vector<int64_t> seg_row_start;  // [n_seg+1] first position of each (day, ward) segment
   std::vector<double>  seg_N;          // [n_seg]  N of the first matching tppw row (:242,249)
   std::vector<double>  seg_ward;       // [n_seg]
-  std::vector<double>  h, w;           // [R] per ORIGINAL row: is_new, weight
-  std::vector<int32_t> count_day;      // [R] per ORIGINAL row: day index for the totals, -1 if none
+  RowVec<double>  h, w;                // [R] per ORIGINAL row: is_new, weight
+  RowVec<int32_t> count_day;           // [R] per ORIGINAL row: day index for the totals, -1 if none
 
   // GENERAL path: per day, the surviving (last-writer-wins) next_day copies   (:402-407)
   std::vector<int64_t> day_push_start; // [total_days+2]
-  std::vector<int64_t> push_src, push_dst;  // original row indices
+  RowVec<int64_t> push_src, push_dst;  // original row indices
 
   // FAST path per position (valid when fast_eligible)
-  std::vector<uint32_t> meta_info;     // [Rp] h<<31 | source kind<<29 | segment index within the day
-  std::vector<uint32_t> meta_next;     // [Rp] position of the successor record within the NEXT day, or kNone
-  std::vector<uint32_t> meta_nseg;     // [Rp] absolute segment of that successor, or kNone
+  RowVec<uint32_t> meta_info;          // [Rp] h<<31 | source kind<<29 | segment index within the day
+  RowVec<uint32_t> meta_next;          // [Rp] position of the successor record within the NEXT day, or kNone
+  RowVec<uint32_t> meta_nseg;          // [Rp] absolute segment of that successor, or kNone
   std::vector<uint32_t> init_seg;      // [n_init] absolute segment of init-sourced stepped rows, or kNone
   std::vector<uint32_t> init_slot;     // [n_init] position of that row within its day, or kNone
   std::vector<uint8_t>  day_has_init;  // [total_days+1] 1 if the day holds init-sourced rows
