@@ -87,13 +87,22 @@ int amro_topology_create(const double* ward_matrix, int64_t n_rows, int64_t n_co
       if (H.fast_eligible) {
         // one 16-byte word per record: what a lane needs about its record comes with ONE load, and the successor's slot
         // is already the byte offset inside a state-ring buffer laid out [chunk of 32][slice of the team][32]
-        std::vector<uint4> meta((size_t)H.Rp);
-        for (int64_t p = 0; p < H.Rp; ++p) {
-          const uint32_t nx = H.meta_next[p];
-          meta[p] = make_uint4(H.meta_info[p], nx == kNone ? kNone : (uint32_t)(fast_ring_slot(nx) * sizeof(uint4)),
-                               H.meta_nseg[p], (uint32_t)H.order[p]);
+        std::unique_ptr<uint4[]> meta(new uint4[(size_t)std::max<int64_t>(H.Rp, 1)]);   // packed by a few threads (58 MB for config 2)
+        {
+          const int n_thr = H.Rp < 200000 ? 1 : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+          std::vector<std::thread> pool;
+          auto pack = [&](int64_t lo, int64_t hi) {
+            for (int64_t p = lo; p < hi; ++p) {
+              const uint32_t nx = H.meta_next[p];
+              meta[(size_t)p] = make_uint4(H.meta_info[p], nx == kNone ? kNone : (uint32_t)(fast_ring_slot(nx) * sizeof(uint4)),
+                                           H.meta_nseg[p], (uint32_t)H.order[p]);
+            }
+          };
+          for (int k = 1; k < n_thr; ++k) pool.emplace_back(pack, H.Rp * k / n_thr, H.Rp * (k + 1) / n_thr);
+          pack(0, H.Rp / n_thr);
+          for (auto& th : pool) th.join();
         }
-        t->meta.upload(meta.data(), meta.size());
+        t->meta.upload(meta.get(), (size_t)H.Rp);
         t->init_seg.upload(H.init_seg.data(), H.init_seg.size());
         t->init_slot.upload(H.init_slot.data(), H.init_slot.size());
         t->seg_main_next.upload(H.seg_main_next.data(), H.seg_main_next.size());
