@@ -463,7 +463,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = float(R) * S * b_alg / (k_ms * 1e-3) / 1e9                    # this GPU's kernel
         traffic = ncu_traffic_bytes(args.workload)
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is timed at N = 1 only
             v, procs, kind, text = cpu_sample(args.workload)
             cpu = {"value": v, "unit": "updates/s", "cores": procs, "kind": kind, "sample": text}
         kinds = {capi.KERNEL_CODES: "16-bit state codes", capi.KERNEL_BITS: "bit-sliced state", capi.KERNEL_FLOAT64: "float64 planes"}
