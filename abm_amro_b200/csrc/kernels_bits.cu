@@ -28,6 +28,8 @@
 // transfer lists, no pressure buffers (kernels_fast.cu pushes; round 2 measured the push at a fifth of this kernel's
 // instructions).  A ward-day that spans several runs is counted by each of them (config 2: 2.2 times).
 // Work decomposition, team barrier and day plan: team.cuh, as in kernels_fast.cu; a team = 32 * kBW simulations.
+#include <atomic>
+
 #include "team.cuh"
 
 namespace amro {
@@ -908,13 +910,23 @@ int bits_sims_per_team() { return kBitsSims; }
 int bits_words_per_team() { return kBW; }
 size_t bits_shared_bytes(bool half) { return bits_smem_bytes(kTeamThreads, half); }
 
+// Per (device, instance): the dynamic shared memory opt-in and the occupancy of the instance are asked for once, not on every
+// run (a parameter sweep calls amro_simulate thousands of times).
+namespace {
+constexpr int kMaxCachedDevices = 16;
+std::atomic<int> g_bits_cap[kMaxCachedDevices][4][4][2];        // co-resident CTAs + 1 (0 = not asked yet)
+inline int ttd_index(int ttd) { return ttd < 0 ? 0 : (ttd > 3 ? 3 : ttd); }
+}  // namespace
 int bits_max_coresident_ctas(int device, int ttd, int shape, bool half) {
+  std::atomic<int>* slot = (device >= 0 && device < kMaxCachedDevices && shape >= 0 && shape < 4) ? &g_bits_cap[device][ttd_index(ttd)][shape][half ? 1 : 0] : nullptr;
+  if (slot) { const int v = slot->load(std::memory_order_acquire); if (v > 0) return v - 1; }
   int per_sm = 0, sms = 0;
   const void* k = bits_kernel_ptr(ttd, shape, half);
   const size_t smem = bits_smem_bytes(kTeamThreads, half);
   AMRO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AMRO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kTeamThreads, smem));
+  if (slot) slot->store(per_sm * sms + 1, std::memory_order_release);
   return per_sm * sms;
 }
 
@@ -939,7 +951,13 @@ int bits_max_coresident_clusters(int ttd, int shape, int cluster_size, bool half
 void bits_launch(cudaStream_t st, const FastArgs& a, int shape, int grid) {
   const void* k = bits_kernel_ptr(a.ttd, shape, a.half_mask != nullptr);
   const size_t smem = bits_smem_bytes(kTeamThreads, a.half_mask != nullptr);
-  AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    int device = -1;
+    AMRO_CUDA(cudaGetDevice(&device));
+    const bool known = device >= 0 && device < kMaxCachedDevices && shape >= 0 && shape < 4 &&
+                       g_bits_cap[device][ttd_index(a.ttd)][shape][a.half_mask != nullptr ? 1 : 0].load(std::memory_order_acquire) > 0;
+    if (!known) AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // else: set when the occupancy was asked for
+  }
   void* params[] = {(void*)&a};
   if (a.cluster_barrier) {
     if (a.ctas_per_team > 8) AMRO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
