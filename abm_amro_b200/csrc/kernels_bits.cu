@@ -284,7 +284,10 @@ __device__ __forceinline__ void pull_step(VCount (&vc)[N], const uint32_t* pre_x
 }
 // N ward-days at once: their counters are flushed together (one chain of transposes).  Steps of up to kPullDepth groups per
 // ward-day (12 chunks: a whole config-2 ward in one round trip), shorter ones for what is left.
-constexpr int kPullDepth = 3;
+#ifndef AMRO_BITS_PULL_DEPTH
+#define AMRO_BITS_PULL_DEPTH 3
+#endif
+constexpr int kPullDepth = AMRO_BITS_PULL_DEPTH;
 template <int N>
 __device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint32_t* mask_day, const uint32_t (&rows)[N + 1], uint32_t (&cnt)[N], int lane) {
   VCount vc[N];
@@ -305,9 +308,14 @@ __device__ __forceinline__ void pull_pressure(const uint32_t* pre_x, const uint3
 #pragma unroll
     for (int u = 0; u < N; ++u) rem = max(rem, k1[u] > k[u] ? k1[u] - k[u] : 0u);
     if (rem == 0u) break;
-    if (rem > 2u * kPullGroup) { pull_step<N, 3>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += 3u * kPullGroup; }
-    else if (rem > (uint32_t)kPullGroup) { pull_step<N, 2>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += 2u * kPullGroup; }
-    else { pull_step<N, 1>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += (uint32_t)kPullGroup; }
+    // (a lane's counter grows by one per chunk of its ward-day actually present: at most min(step, rem))
+#if AMRO_BITS_PULL_DEPTH >= 4
+    if (rem > 3u * kPullGroup) { pull_step<N, 4>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += min(rem, 4u * kPullGroup); }
+    else
+#endif
+    if (rem > 2u * kPullGroup) { pull_step<N, 3>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += min(rem, 3u * kPullGroup); }
+    else if (rem > (uint32_t)kPullGroup) { pull_step<N, 2>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += rem; }
+    else { pull_step<N, 1>(vc, pre_x, mask_day, k, k1, rows, lane); n_since += rem; }
     if (n_since + (uint32_t)(kPullDepth * kPullGroup) > (uint32_t)kFlushTrips) {
       uint32_t o[N];
       vflush<N>(vr, o, lane, n_since);
